@@ -1,0 +1,236 @@
+/*
+ * abides_b200.h -- C ABI of the B200-native batched ABIDES engine.
+ *
+ * The reference (abides-sim/abides) is pure Python and has no FFI; the surface this
+ * library sits under is the call a config module makes,
+ *     Kernel(...).runner(agents, startTime, stopTime, ..., agentLatencyModel,
+ *                        defaultComputationDelay, oracle, log_dir)   Kernel.py:51-55
+ * `abides_b200.Kernel.runner` lowers the agent / oracle / latency objects it is
+ * handed to the plain tables below and calls these entry points through ctypes.
+ *
+ * Conventions: every function returns 0 on success or a negative ABIDES_E* code and
+ * leaves a message for abides_last_error(); the caller owns every host buffer, the
+ * library owns every device buffer; one handle per device; no internal threads; there
+ * is NO CPU fallback -- without a CUDA device abides_create() fails.
+ *
+ * Times are integer nanoseconds (pandas Timestamp.value), prices integer cents.
+ */
+#ifndef ABIDES_B200_H
+#define ABIDES_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ABIDES_MT_N 624
+#define ABIDES_EXTRA_STREAMS 4          /* per instance, after the per-agent streams */
+#define ABIDES_STREAM_ORACLE  0         /* symbols[sym]['random_state']   config/sparse_zi_100.py:130 */
+#define ABIDES_STREAM_KERNEL  1         /* Kernel(random_state=...)       Kernel.py:12,:380 */
+#define ABIDES_STREAM_LATENCY 2         /* LatencyModel(random_state=...) model/LatencyModel.py:137 */
+#define ABIDES_STREAM_GLOBAL  3         /* the process-global np.random   e.g. agent/ValueAgent.py:199 */
+
+enum abides_error {
+  ABIDES_OK = 0, ABIDES_EINVAL = -1, ABIDES_ENOMEM = -2, ABIDES_ECUDA = -3,
+  ABIDES_ESTATE = -4, ABIDES_EOVERFLOW = -5
+};
+
+/* agent classes */
+enum abides_agent_class {
+  ABIDES_EXCHANGE = 0,      /* agent/ExchangeAgent.py */
+  ABIDES_ZI = 1,            /* agent/ZeroIntelligenceAgent.py */
+  ABIDES_VALUE = 2,         /* agent/ValueAgent.py */
+  ABIDES_NOISE = 3,         /* agent/NoiseAgent.py */
+  ABIDES_MOMENTUM = 4,      /* agent/examples/MomentumAgent.py */
+  ABIDES_ADAPTIVE_MM = 5,   /* agent/market_makers/AdaptiveMarketMakerAgent.py */
+  ABIDES_POV_EXEC = 6       /* agent/execution/POVExecutionAgent.py (trade=False heartbeat) */
+};
+
+enum abides_latency_kind {
+  ABIDES_LAT_DETERMINISTIC = 0,   /* model/LatencyModel.py:142-143 */
+  ABIDES_LAT_CUBIC = 1,           /* model/LatencyModel.py:131-140 */
+  ABIDES_LAT_LEGACY_NOISE = 2     /* Kernel.py:378-381 (agentLatency matrix + latencyNoise) */
+};
+
+enum abides_rng_mode {
+  ABIDES_RNG_MT19937 = 0,   /* the reference's np.random.RandomState streams, bit-exact */
+  ABIDES_RNG_PHILOX = 1     /* counter-based Philox4x32-10 keyed by (instance seed, stream) */
+};
+
+/* Strategy parameters shared by all agents of one "type" (one row per distinct ctor kwargs set). */
+typedef struct abides_agent_type {
+  int32_t klass;              /* enum abides_agent_class */
+  int32_t q_max;              /* ZI */
+  int64_t starting_cash;
+  double  sigma_n, r_bar, kappa, sigma_s, eta, lambda_a;     /* ZI / Value estimator */
+  int64_t R_min, R_max;       /* ZI */
+  int64_t wake_up_freq;       /* Momentum / AdaptiveMM / POV period, ns */
+  double  pov, level_spacing, spread_alpha, skew_beta;       /* AdaptiveMM */
+  int64_t min_order_size, num_ticks, cancel_limit_delay;
+  int64_t backstop_quantity;  /* < 0: None */
+  int64_t window_size;        /* < 0: 'adaptive' */
+  int32_t anchor;             /* 0 middle, 1 bottom, 2 top */
+  int32_t log_orders;         /* TradingAgent.log_orders: only affects order-id consumption of order 0 */
+  double  percent_aggr;       /* Value: 0.1 */
+  int64_t depth_spread;       /* Value: 2 */
+  int64_t reserved[2];
+} abides_agent_type;
+
+/* One simulation instance (one reference process). */
+typedef struct abides_instance_cfg {
+  int64_t start_time, stop_time;          /* Kernel.runner startTime / stopTime */
+  int64_t mkt_open, mkt_close;            /* ExchangeAgent */
+  int64_t default_computation_delay;      /* Kernel.runner defaultComputationDelay */
+  int64_t exch_pipeline_delay, exch_computation_delay;
+  int32_t stream_history;                 /* ExchangeAgent.stream_history */
+  int32_t exch_log_orders;
+  int32_t latency_kind;                   /* enum abides_latency_kind */
+  int32_t n_latency_noise;                /* len(latencyNoise) for the legacy model */
+  double  jitter, jitter_clip, jitter_unit;                 /* cubic model scalars */
+  double  r_bar, kappa, fund_vol;         /* SparseMeanRevertingOracle symbol parameters */
+  double  megashock_lambda_a, megashock_mean, megashock_var;
+  int64_t megashock_time0;                /* first megashock, drawn in the oracle ctor (:67-72) */
+  double  megashock_value0;
+  int64_t agent_offset;                   /* first row of this instance in the per-agent tables */
+  int32_t n_agents;                       /* rows (agent ids 0..n_agents-1; id 0 is the exchange) */
+  int32_t type_base;                      /* first row of this instance's types in `types` */
+  int64_t theta_offset;                   /* first int of this instance in `theta` */
+  uint64_t seed;                          /* Philox mode: instance key */
+  int64_t reserved[2];
+} abides_instance_cfg;
+
+/* A batch of instances: tables are concatenated over instances in instance order. */
+typedef struct abides_batch {
+  int32_t n_instances;
+  int32_t n_types;                        /* rows in `types` */
+  int64_t n_agents_total;                 /* sum of n_agents */
+  int64_t n_theta_total;                  /* ints in `theta` */
+  int32_t rng_mode;                       /* enum abides_rng_mode */
+  int32_t trace_capacity;                 /* per-instance trace records to keep (0 = off) */
+  const abides_instance_cfg* instances;   /* [n_instances] */
+  const abides_agent_type*   types;       /* [n_types] */
+  const int32_t* agent_type;              /* [n_agents_total] index relative to type_base */
+  const double*  lat_to_exch;             /* [n_agents_total] min latency agent -> exchange (ns) */
+  const double*  lat_from_exch;           /* [n_agents_total] min latency exchange -> agent (ns) */
+  const int64_t* agent_size;              /* [n_agents_total] Noise/Value/Momentum order size */
+  const int64_t* agent_wakeup_time;       /* [n_agents_total] Noise: wakeup_time[0] */
+  const int32_t* agent_theta;             /* [n_agents_total] offset into theta rel. to theta_offset, -1 none */
+  const int32_t* theta;                   /* [n_theta_total] ZI private values, 2*q_max each */
+  /* MT19937 mode: one stream per agent row plus ABIDES_EXTRA_STREAMS per instance, laid out as
+   * stream(inst, s) = agent_offset + ABIDES_EXTRA_STREAMS*inst + s, s < n_agents for agent streams,
+   * s = n_agents + ABIDES_STREAM_* for the extra ones.  NULL in Philox mode. */
+  const uint32_t* mt_key;                 /* [n_streams][624] */
+  const int32_t*  mt_pos;                 /* [n_streams] */
+  const int32_t*  mt_has_gauss;           /* [n_streams] */
+  const double*   mt_gauss;               /* [n_streams] */
+} abides_batch;
+
+/* Per-instance result (the record gathered at the end). */
+typedef struct abides_instance_result {
+  int64_t ttl_messages;                   /* Kernel.py:204 -- every queue pop incl. re-queues */
+  int64_t delivered;                      /* pops that reached wakeup()/receiveMessage() */
+  int64_t final_time;                     /* kernel currentTime at loop exit */
+  int64_t slowest_agent_finish_time;      /* Kernel.py:309 */
+  int64_t last_trade;                     /* OrderBook.last_trade */
+  int64_t final_fundamental;              /* oracle r at exit */
+  int64_t n_orders;                       /* order ids consumed */
+  int64_t n_fills;                        /* executions (each produces two ORDER_EXECUTED) */
+  int64_t traded_volume;                  /* sum of fill quantities */
+  int32_t status;                         /* 0 ok; else enum abides_error raised on device */
+  int32_t queue_peak;
+  int32_t book_peak_levels, book_peak_orders;
+  int64_t reserved[2];
+} abides_instance_result;
+
+/* Per-agent result (TradingAgent.kernelStopping, TradingAgent.py:122-147 and subclasses). */
+typedef struct abides_agent_result {
+  int64_t cash;                           /* holdings['CASH'] */
+  int64_t holdings;                       /* holdings[symbol] (0 if absent) */
+  int64_t marked_to_market;               /* markToMarket(holdings) */
+  double  final_valuation;                /* FINAL_VALUATION summary-log value (class specific) */
+} abides_agent_result;
+
+/* Dispatch trace record (parity tests): one per delivered event. */
+typedef struct abides_trace_rec {
+  int64_t time;
+  int32_t agent;                          /* recipient */
+  int32_t code;                           /* 0 = WAKEUP, else enum abides_msg */
+  int64_t p0, p1, p2, p3;                 /* message payload, see abides_msg */
+} abides_trace_rec;
+
+/* Message vocabulary.  Payload words for the trace:
+ *   to exchange  : p0 = sender; orders: p1 = order id, p2 = price, p3 = qty (negative = sell)
+ *   ORDER_*      : p0 = order id, p1 = price (limit), p2 = qty (negative = sell), p3 = fill price
+ *   QUERY_SPREAD reply : p0 = bid, p1 = bid volume, p2 = ask, p3 = ask volume (price -1 = none)
+ *   WHEN_MKT_* reply   : p0 = time ; QUERY_TRANSACTED_VOLUME reply: p0 = volume */
+enum abides_msg {
+  ABIDES_MSG_WAKEUP = 0,
+  ABIDES_MSG_WHEN_MKT_OPEN = 1, ABIDES_MSG_WHEN_MKT_CLOSE = 2,
+  ABIDES_MSG_QUERY_LAST_TRADE = 3, ABIDES_MSG_QUERY_SPREAD = 4,
+  ABIDES_MSG_QUERY_ORDER_STREAM = 5, ABIDES_MSG_QUERY_TRANSACTED_VOLUME = 6,
+  ABIDES_MSG_LIMIT_ORDER = 7, ABIDES_MSG_MARKET_ORDER = 8,
+  ABIDES_MSG_CANCEL_ORDER = 9, ABIDES_MSG_MODIFY_ORDER = 10,
+  ABIDES_MSG_ORDER_ACCEPTED = 11, ABIDES_MSG_ORDER_EXECUTED = 12,
+  ABIDES_MSG_ORDER_CANCELLED = 13, ABIDES_MSG_ORDER_MODIFIED = 14,
+  ABIDES_MSG_MKT_CLOSED = 15,
+  ABIDES_MSG_REPLY = 32          /* OR-ed in for exchange -> agent echoes of a query type */
+};
+
+/* ---- order-book replay harness (K2) -------------------------------------- */
+typedef struct abides_book_op {           /* one message handed to util/OrderBook.py */
+  int32_t kind;                           /* ABIDES_MSG_LIMIT_ORDER / MARKET_ORDER / CANCEL_ORDER / MODIFY_ORDER */
+  int32_t agent;
+  int64_t order_id;                       /* MARKET_ORDER children take ids from next_order_id */
+  int64_t price;                          /* limit price */
+  int64_t qty;                            /* >0 */
+  int32_t is_buy;
+  int32_t reserved;
+  int64_t new_qty;                        /* MODIFY_ORDER: quantity of new_order */
+  int64_t time;                           /* owner.currentTime */
+} abides_book_op;
+
+typedef struct abides_book_event {        /* outbound notification, in the order the book sends them */
+  int32_t op_index;                       /* which abides_book_op caused it */
+  int32_t kind;                           /* ORDER_ACCEPTED / ORDER_EXECUTED / ORDER_CANCELLED / ORDER_MODIFIED */
+  int32_t agent;                          /* recipient */
+  int32_t is_buy;
+  int64_t order_id, price, qty, fill_price;
+} abides_book_event;
+
+typedef struct abides_book_state {        /* after every op */
+  int64_t bid, bid_vol, ask, ask_vol;     /* getInsideBids(1) / getInsideAsks(1); price -1 = empty */
+  int64_t last_trade;                     /* -1 = None */
+  int32_t n_bid_levels, n_ask_levels;
+} abides_book_state;
+
+typedef struct abides_handle abides_handle;
+
+/* lifecycle */
+int  abides_create(int device, abides_handle** out);
+void abides_destroy(abides_handle* h);
+const char* abides_last_error(void);
+const char* abides_version(void);
+
+/* Kernel.runner: load a batch (host -> device), run it, read results (device -> host). */
+int  abides_load(abides_handle* h, const abides_batch* batch);
+int  abides_run(abides_handle* h, int64_t until_time);      /* INT64_MAX: to completion incl. kernelStopping */
+int  abides_read_results(abides_handle* h, abides_instance_result* inst_out /*[n_instances]*/,
+                         abides_agent_result* agents_out /*[n_agents_total] or NULL*/);
+int  abides_read_trace(abides_handle* h, int32_t instance, abides_trace_rec* out, int64_t capacity,
+                       int64_t* n_out);
+/* device-side timing of the last abides_run (CUDA events on the launching stream), ms */
+int  abides_last_run_ms(abides_handle* h, float* ms, int32_t* n_launches);
+
+/* util/OrderBook.py replay: n_books independent books, book b replays ops[op_offset[b] .. op_offset[b+1]).
+ * events_out is [n_ops_total * max_events_per_op]; event_count_out [n_ops_total]; states_out [n_ops_total]. */
+int  abides_replay_book(abides_handle* h, int32_t n_books, const int64_t* op_offset,
+                        const abides_book_op* ops, int32_t stream_history, int32_t max_events_per_op,
+                        abides_book_event* events_out, int32_t* event_count_out,
+                        abides_book_state* states_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ABIDES_B200_H */
