@@ -161,7 +161,8 @@ typedef struct abides_trace_rec {
 } abides_trace_rec;
 
 /* Message vocabulary.  Payload words for the trace:
- *   to exchange  : p0 = sender; orders: p1 = order id, p2 = price, p3 = qty (negative = sell)
+ *   to exchange  : p0 = sender; orders: p1 = order id, p2 = price, p3 = qty (negative = sell;
+ *                  CANCEL_ORDER: +-1, side only)
  *   ORDER_*      : p0 = order id, p1 = price (limit), p2 = qty (negative = sell), p3 = fill price
  *   QUERY_SPREAD reply : p0 = bid, p1 = bid volume, p2 = ask, p3 = ask volume (price -1 = none)
  *   WHEN_MKT_* reply   : p0 = time ; QUERY_TRANSACTED_VOLUME reply: p0 = volume */

@@ -28,9 +28,11 @@
 
 #if defined(__CUDACC__)
 #define ABM_HD __host__ __device__ __forceinline__
+#define ABM_HD_BIG __host__ __device__ __noinline__      /* keep the big bodies out of every call site */
 #define ABM_FMA(a, b, c) fma((a), (b), (c))
 #else
 #define ABM_HD static inline
+#define ABM_HD_BIG static
 #define ABM_FMA(a, b, c) __builtin_fma((a), (b), (c))
 #endif
 
@@ -76,7 +78,7 @@ ABM_HD abm_dd abm_dd_mul_d(abm_dd a, double b) {
 ABM_HD abm_dd abm_dd_scale2(abm_dd a, double pow2) {      /* exact: pow2 is a power of two */
   return abm_mk(a.hi * pow2, a.lo * pow2);
 }
-ABM_HD abm_dd abm_dd_div(abm_dd a, abm_dd b) {
+ABM_HD_BIG abm_dd abm_dd_div(abm_dd a, abm_dd b) {
   double q1 = a.hi / b.hi;
   abm_dd r = abm_dd_add(a, abm_dd_neg(abm_dd_mul_d(b, q1)));
   double q2 = r.hi / b.hi;
@@ -92,7 +94,7 @@ ABM_HD uint64_t abm_double_to_bits(double d) { uint64_t u; memcpy(&u, &d, sizeof
 ABM_HD double abm_pow2i(int k) { return abm_bits_to_double((uint64_t)(k + 1023) << 52); }
 
 /* e^a - 1 for |a| <= 2^-10, Taylor to a^10/10! (truncation < 2^-115 relative). */
-ABM_HD abm_dd abm_expm1_tiny(abm_dd a) {
+ABM_HD_BIG abm_dd abm_expm1_tiny(abm_dd a) {
   abm_dd p = abm_mk(0x1.27e4fb7789f5cp-22, 0x1.cbbc05b4fa99ap-76);                       /* 1/10! */
   p = abm_dd_add(abm_dd_mul(p, a), abm_mk(0x1.71de3a556c734p-19, -0x1.c154f8ddc6c00p-73)); /* 1/9! */
   p = abm_dd_add(abm_dd_mul(p, a), abm_mk(0x1.a01a01a01a01ap-16, 0x1.a01a01a01a01ap-76));  /* 1/8! */
@@ -108,7 +110,7 @@ ABM_HD abm_dd abm_expm1_tiny(abm_dd a) {
 
 /* exp of a double-double argument, |a| < 700, as an UNSCALED double-double m and an
  * exponent k with result = m * 2^k, m in [~0.7, ~1.42]. */
-ABM_HD abm_dd abm_exp_dd_k(abm_dd a, int* kout) {
+ABM_HD_BIG abm_dd abm_exp_dd_k(abm_dd a, int* kout) {
   const abm_dd LN2 = abm_mk(0x1.62e42fefa39efp-1, 0x1.abc9e3b39803fp-56);
   double kf = rint(a.hi * 0x1.71547652b82fep+0);
   abm_dd r = abm_dd_add(a, abm_dd_neg(abm_dd_mul_d(LN2, kf)));
@@ -129,7 +131,7 @@ ABM_HD double abm_scale_by_pow2(double m, int k) {
   return m * abm_pow2i(k);
 }
 
-ABM_HD double abm_exp(double x) {
+ABM_HD_BIG double abm_exp(double x) {
   if (x == 0.0) return 1.0;
   if (x > 709.0) return INFINITY;
   if (x < -708.0) return 0.0;
@@ -138,7 +140,7 @@ ABM_HD double abm_exp(double x) {
 }
 
 /* log(x) as a double-double; x > 0, normal. */
-ABM_HD abm_dd abm_log_dd(double x) {
+ABM_HD_BIG abm_dd abm_log_dd(double x) {
   const abm_dd LN2 = abm_mk(0x1.62e42fefa39efp-1, 0x1.abc9e3b39803fp-56);
   uint64_t bits = abm_double_to_bits(x);
   int e = (int)((bits >> 52) & 0x7ff) - 1023;
@@ -181,7 +183,7 @@ ABM_HD abm_dd abm_log_dd(double x) {
 ABM_HD double abm_log(double x) { return abm_log_dd(x).hi; }
 
 /* x ** y for x > 0 (C pow semantics for the finite, positive-base cases the reference hits). */
-ABM_HD double abm_pow(double x, double y) {
+ABM_HD_BIG double abm_pow(double x, double y) {
   if (y == 0.0 || x == 1.0) return 1.0;
   if (y == 1.0) return x;
   abm_dd l = abm_log_dd(x);
@@ -190,6 +192,24 @@ ABM_HD double abm_pow(double x, double y) {
   if (p.hi < -708.0) return 0.0;
   int k; abm_dd m = abm_exp_dd_k(p, &k);
   return abm_scale_by_pow2(m.hi, k);
+}
+
+/* x ** y given a precomputed l = abm_log_dd(x): bit-identical to abm_pow(x, y). */
+ABM_HD_BIG double abm_pow_with_log(abm_dd l, double x, double y) {
+  if (y == 0.0 || x == 1.0) return 1.0;
+  if (y == 1.0) return x;
+  abm_dd p = abm_dd_mul_d(l, y);
+  if (p.hi > 709.0) return INFINITY;
+  if (p.hi < -708.0) return 0.0;
+  int k; abm_dd m = abm_exp_dd_k(p, &k);
+  return abm_scale_by_pow2(m.hi, k);
+}
+
+/* x ** 3 (model/LatencyModel.py:138): the exact cube in double-double, rounded once. */
+ABM_HD double abm_cube(double x) {
+  abm_dd sq = abm_two_prod(x, x);
+  abm_dd c = abm_dd_mul_d(sq, x);
+  return c.hi;
 }
 
 #endif /* ABIDES_DD_MATH_H */

@@ -65,6 +65,10 @@ def main():
                 p[1] = o.order_id
                 p[2] = getattr(o, "limit_price", 0)
                 p[3] = o.quantity if o.is_buy_order else -o.quantity
+                if code_name == "CANCEL_ORDER":
+                    # the message aliases the sender's live order object, whose quantity the sender keeps
+                    # mutating on partial fills; only the side is meaningful to the book (OrderBook.py:300-348)
+                    p[3] = 1 if o.is_buy_order else -1
             elif code_name == "QUERY_SPREAD":
                 p[1] = body["depth"]
             return p
