@@ -139,7 +139,7 @@ LIB_PATH = os.path.join(_PKG_DIR, "csrc", "libabides_b200.so")
 
 EXPORTS = [
     "abides_create", "abides_destroy", "abides_last_error", "abides_version", "abides_load",
-    "abides_run", "abides_read_results", "abides_read_trace", "abides_last_run_ms",
+    "abides_reset", "abides_run", "abides_read_results", "abides_read_trace", "abides_last_run_ms", "abides_last_reset_ms",
     "abides_replay_book",
 ]
 
@@ -167,6 +167,8 @@ def lib():
     L.abides_version.restype = C.c_char_p
     L.abides_load.argtypes = [H, C.POINTER(Batch)]
     L.abides_load.restype = C.c_int
+    L.abides_reset.argtypes = [H]
+    L.abides_reset.restype = C.c_int
     L.abides_run.argtypes = [H, C.c_int64]
     L.abides_run.restype = C.c_int
     L.abides_read_results.argtypes = [H, C.POINTER(InstanceResult), C.POINTER(AgentResult)]
@@ -175,6 +177,8 @@ def lib():
     L.abides_read_trace.restype = C.c_int
     L.abides_last_run_ms.argtypes = [H, C.POINTER(C.c_float), C.POINTER(C.c_int32)]
     L.abides_last_run_ms.restype = C.c_int
+    L.abides_last_reset_ms.argtypes = [H, C.POINTER(C.c_float)]
+    L.abides_last_reset_ms.restype = C.c_int
     L.abides_replay_book.argtypes = [H, C.c_int32, C.POINTER(C.c_int64), C.POINTER(BookOp), C.c_int32,
                                      C.c_int32, C.POINTER(BookEvent), C.POINTER(C.c_int32),
                                      C.POINTER(BookState)]

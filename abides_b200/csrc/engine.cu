@@ -1418,6 +1418,17 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
 
 }  // namespace
 
+namespace {
+struct ShapeSig {
+  int ni = 0, n_types = 0, rng_mode = -1, trace_cap = -1, max_agents = 0, n_mom = 0;
+  long long na = -1, n_theta = -1;
+  bool operator==(const ShapeSig& o) const {
+    return ni == o.ni && n_types == o.n_types && rng_mode == o.rng_mode && trace_cap == o.trace_cap &&
+           max_agents == o.max_agents && n_mom == o.n_mom && na == o.na && n_theta == o.n_theta;
+  }
+};
+}  // namespace
+
 struct abides_handle {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -1427,9 +1438,13 @@ struct abides_handle {
   bool loaded = false;
   int n_instances = 0;
   long long n_agents_total = 0;
-  float last_ms = 0.f;
+  float last_ms = 0.f, last_reset_ms = 0.f;
   int last_launches = 0;
-  std::vector<int> inst_n_agents;
+  int launches_since_load = 0;
+  unsigned* mt_pristine = nullptr;
+  size_t n_streams = 0;
+  int n_mom = 0;
+  ShapeSig sig;
 };
 
 namespace {
@@ -1457,6 +1472,26 @@ void free_all(abides_handle* h) {
   h->loaded = false;
 }
 
+}  // namespace
+
+namespace {
+template <typename T>
+int h2d(abides_handle* h, const T* dst, const T* src, size_t count) {
+  if (count) CK(cudaMemcpyAsync(const_cast<T*>(dst), src, count * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+  return 0;
+}
+int launch_init(abides_handle* h) {
+  DevBatch& d = h->db;
+  if (d.rng_mode == ABIDES_RNG_MT19937)
+    CK(cudaMemcpyAsync(d.mt, h->mt_pristine, h->n_streams * ABIDES_MT_N * sizeof(unsigned), cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaMemsetAsync(d.mom_ring, 0, (size_t)(h->n_mom > 0 ? h->n_mom : 1) * MOM_RING * sizeof(double), h->stream));
+  CK(cudaMemsetAsync(d.res, 0, (size_t)d.n_instances * sizeof(abides_instance_result), h->stream));
+  init_types_kernel<<<(d.n_types + 63) / 64, 64, 0, h->stream>>>(d);
+  init_kernel<<<d.n_instances, 32, 0, h->stream>>>(d);
+  CK(cudaGetLastError());
+  h->launches_since_load += 2;
+  return 0;
+}
 }  // namespace
 
 extern "C" {
@@ -1493,6 +1528,7 @@ void abides_destroy(abides_handle* h) {
   delete h;
 }
 
+
 int abides_load(abides_handle* h, const abides_batch* b) {
   if (!h || !b) return fail(ABIDES_EINVAL, "abides_load: NULL argument");
   if (b->n_instances <= 0 || !b->instances || !b->types || !b->agent_type || !b->lat_to_exch || !b->lat_from_exch ||
@@ -1500,15 +1536,12 @@ int abides_load(abides_handle* h, const abides_batch* b) {
     return fail(ABIDES_EINVAL, "abides_load: missing table");
   if (b->rng_mode == ABIDES_RNG_MT19937 && (!b->mt_key || !b->mt_pos || !b->mt_has_gauss || !b->mt_gauss))
     return fail(ABIDES_EINVAL, "abides_load: MT19937 mode needs mt_key/mt_pos/mt_has_gauss/mt_gauss");
+  if (b->rng_mode != ABIDES_RNG_MT19937 && b->rng_mode != ABIDES_RNG_PHILOX) return fail(ABIDES_EINVAL, "abides_load: bad rng_mode");
   CK(cudaSetDevice(h->device));
-  free_all(h);
-  DevBatch& d = h->db;
-  memset(&d, 0, sizeof d);
   int ni = b->n_instances;
   long long na = b->n_agents_total;
   int max_agents = 0;
   long long off = 0;
-  h->inst_n_agents.assign(ni, 0);
   std::vector<int> mom_index((size_t)na, -1);
   int n_mom = 0;
   for (int i = 0; i < ni; i++) {
@@ -1516,6 +1549,7 @@ int abides_load(abides_handle* h, const abides_batch* b) {
     if (ic.agent_offset != off || ic.n_agents <= 0) return fail(ABIDES_EINVAL, "abides_load: agent_offset must be the prefix sum of n_agents");
     if (ic.type_base < 0 || ic.type_base >= b->n_types) return fail(ABIDES_EINVAL, "abides_load: bad type_base");
     if (ic.r_bar < 0 || ic.r_bar > 2.0e9) return fail(ABIDES_EINVAL, "abides_load: r_bar out of the int32 price range");
+    if (off + ic.n_agents > na) return fail(ABIDES_EINVAL, "abides_load: n_agents_total mismatch");
     for (int a = 0; a < ic.n_agents; a++) {
       int t = ic.type_base + b->agent_type[off + a];
       if (t < 0 || t >= b->n_types) return fail(ABIDES_EINVAL, "abides_load: agent_type out of range");
@@ -1525,54 +1559,97 @@ int abides_load(abides_handle* h, const abides_batch* b) {
       if (k == ABIDES_MOMENTUM) mom_index[off + a] = n_mom++;
       if (k == ABIDES_ZI && (b->agent_theta[off + a] < 0 || !b->theta)) return fail(ABIDES_EINVAL, "abides_load: ZI agent without theta");
     }
-    h->inst_n_agents[i] = ic.n_agents;
     if (ic.n_agents > max_agents) max_agents = ic.n_agents;
     off += ic.n_agents;
   }
   if (off != na) return fail(ABIDES_EINVAL, "abides_load: n_agents_total mismatch");
-  d.n_instances = ni; d.rng_mode = b->rng_mode; d.trace_cap = b->trace_capacity; d.n_types = b->n_types;
-  d.far_cap = 4 * max_agents + 4096;
-  d.arena_cap = 8 * max_agents + 4096;
+  ShapeSig sig;
+  sig.ni = ni; sig.n_types = b->n_types; sig.rng_mode = b->rng_mode; sig.trace_cap = b->trace_capacity;
+  sig.max_agents = max_agents; sig.n_mom = n_mom; sig.na = na; sig.n_theta = b->n_theta_total;
+  DevBatch& d = h->db;
   int rc;
-  abides_instance_cfg* dcfg; abides_agent_type* dty; int* dat; double *dlt, *dlf; long long *dsz, *dwk; int *dath, *dth, *dmi;
-  if ((rc = dev_upload(h, &dcfg, b->instances, (size_t)ni))) return rc;
-  if ((rc = dev_upload(h, &dty, b->types, (size_t)b->n_types))) return rc;
-  if ((rc = dev_upload(h, &dat, b->agent_type, (size_t)na))) return rc;
-  if ((rc = dev_upload(h, &dlt, b->lat_to_exch, (size_t)na))) return rc;
-  if ((rc = dev_upload(h, &dlf, b->lat_from_exch, (size_t)na))) return rc;
-  if ((rc = dev_upload(h, &dsz, reinterpret_cast<const long long*>(b->agent_size), (size_t)na))) return rc;
-  if ((rc = dev_upload(h, &dwk, reinterpret_cast<const long long*>(b->agent_wakeup_time), (size_t)na))) return rc;
-  if ((rc = dev_upload(h, &dath, b->agent_theta, (size_t)na))) return rc;
-  if ((rc = dev_upload(h, &dth, b->theta, (size_t)(b->n_theta_total > 0 ? b->n_theta_total : 0)))) return rc;
-  if ((rc = dev_upload(h, &dmi, mom_index.data(), (size_t)na))) return rc;
-  d.cfg = dcfg; d.types = dty; d.agent_type = dat; d.lat_to = dlt; d.lat_from = dlf; d.size = dsz; d.wakeup_time = dwk;
-  d.agent_theta = dath; d.theta = dth; d.mom_index = dmi;
-  if (b->rng_mode == ABIDES_RNG_MT19937) {
-    size_t ns = (size_t)na + (size_t)ABIDES_EXTRA_STREAMS * ni;
-    unsigned* dmt; int *dpos, *dhg; double* dg;
-    if ((rc = dev_upload(h, &dmt, b->mt_key, ns * ABIDES_MT_N))) return rc;
-    if ((rc = dev_upload(h, &dpos, b->mt_pos, ns))) return rc;
-    if ((rc = dev_upload(h, &dhg, b->mt_has_gauss, ns))) return rc;
-    if ((rc = dev_upload(h, &dg, b->mt_gauss, ns))) return rc;
-    d.mt = dmt; d.mt_pos = dpos; d.mt_has_gauss = dhg; d.mt_gauss = dg;
+  size_t ns = (size_t)na + (size_t)ABIDES_EXTRA_STREAMS * ni;
+  if (!(h->loaded && sig == h->sig)) {          // (re)allocate; same-shaped batches reuse the device buffers
+    free_all(h);
+    memset(&d, 0, sizeof d);
+    d.n_instances = ni; d.rng_mode = b->rng_mode; d.trace_cap = b->trace_capacity; d.n_types = b->n_types;
+    d.far_cap = 4 * max_agents + 4096;
+    d.arena_cap = 8 * max_agents + 4096;
+    abides_instance_cfg* dcfg; abides_agent_type* dty; int* dat; double *dlt, *dlf; long long *dsz, *dwk; int *dath, *dth, *dmi;
+    if ((rc = dev_alloc(h, &dcfg, (size_t)ni))) return rc;
+    if ((rc = dev_alloc(h, &dty, (size_t)b->n_types))) return rc;
+    if ((rc = dev_alloc(h, &dat, (size_t)na))) return rc;
+    if ((rc = dev_alloc(h, &dlt, (size_t)na))) return rc;
+    if ((rc = dev_alloc(h, &dlf, (size_t)na))) return rc;
+    if ((rc = dev_alloc(h, &dsz, (size_t)na))) return rc;
+    if ((rc = dev_alloc(h, &dwk, (size_t)na))) return rc;
+    if ((rc = dev_alloc(h, &dath, (size_t)na))) return rc;
+    if ((rc = dev_alloc(h, &dth, (size_t)(b->n_theta_total > 0 ? b->n_theta_total : 0)))) return rc;
+    if ((rc = dev_alloc(h, &dmi, (size_t)na))) return rc;
+    d.cfg = dcfg; d.types = dty; d.agent_type = dat; d.lat_to = dlt; d.lat_from = dlf; d.size = dsz; d.wakeup_time = dwk;
+    d.agent_theta = dath; d.theta = dth; d.mom_index = dmi;
+    if (b->rng_mode == ABIDES_RNG_MT19937) {
+      int *dpos, *dhg; double* dg;
+      if ((rc = dev_alloc(h, &d.mt, ns * ABIDES_MT_N))) return rc;
+      if ((rc = dev_alloc(h, &h->mt_pristine, ns * ABIDES_MT_N))) return rc;
+      if ((rc = dev_alloc(h, &dpos, ns))) return rc;
+      if ((rc = dev_alloc(h, &dhg, ns))) return rc;
+      if ((rc = dev_alloc(h, &dg, ns))) return rc;
+      d.mt_pos = dpos; d.mt_has_gauss = dhg; d.mt_gauss = dg;
+    }
+    if ((rc = dev_alloc(h, &d.type_log1mk, (size_t)b->n_types))) return rc;
+    if ((rc = dev_alloc(h, &d.agents, (size_t)na))) return rc;
+    if ((rc = dev_alloc(h, &d.state, (size_t)ni))) return rc;
+    if ((rc = dev_alloc(h, &d.far_keys, (size_t)ni * d.far_cap))) return rc;
+    if ((rc = dev_alloc(h, &d.far_pay, (size_t)ni * d.far_cap))) return rc;
+    if ((rc = dev_alloc(h, &d.arena, (size_t)ni * d.arena_cap))) return rc;
+    if ((rc = dev_alloc(h, &d.mom_ring, (size_t)(n_mom > 0 ? n_mom : 1) * MOM_RING))) return rc;
+    if ((rc = dev_alloc(h, &d.trace, (size_t)ni * (d.trace_cap > 0 ? d.trace_cap : 0)))) return rc;
+    if ((rc = dev_alloc(h, &d.res, (size_t)ni))) return rc;
+    if ((rc = dev_alloc(h, &d.ares, (size_t)na))) return rc;
+    h->sig = sig;
   }
-  if ((rc = dev_alloc(h, &d.type_log1mk, (size_t)b->n_types))) return rc;
-  if ((rc = dev_alloc(h, &d.agents, (size_t)na))) return rc;
-  if ((rc = dev_alloc(h, &d.state, (size_t)ni))) return rc;
-  if ((rc = dev_alloc(h, &d.far_keys, (size_t)ni * d.far_cap))) return rc;
-  if ((rc = dev_alloc(h, &d.far_pay, (size_t)ni * d.far_cap))) return rc;
-  if ((rc = dev_alloc(h, &d.arena, (size_t)ni * d.arena_cap))) return rc;
-  if ((rc = dev_alloc(h, &d.mom_ring, (size_t)(n_mom > 0 ? n_mom : 1) * MOM_RING))) return rc;
-  if ((rc = dev_alloc(h, &d.trace, (size_t)ni * (d.trace_cap > 0 ? d.trace_cap : 0)))) return rc;
-  if ((rc = dev_alloc(h, &d.res, (size_t)ni))) return rc;
-  if ((rc = dev_alloc(h, &d.ares, (size_t)na))) return rc;
-  CK(cudaMemsetAsync(d.mom_ring, 0, (size_t)(n_mom > 0 ? n_mom : 1) * MOM_RING * sizeof(double), h->stream));
-  CK(cudaMemsetAsync(d.res, 0, (size_t)ni * sizeof(abides_instance_result), h->stream));
-  init_types_kernel<<<(b->n_types + 63) / 64, 64, 0, h->stream>>>(d);
-  init_kernel<<<ni, 32, 0, h->stream>>>(d);
-  CK(cudaGetLastError());
-  CK(cudaStreamSynchronize(h->stream));
+  h->n_streams = ns; h->n_mom = n_mom;
+  if ((rc = h2d(h, d.cfg, b->instances, (size_t)ni))) return rc;
+  if ((rc = h2d(h, d.types, b->types, (size_t)b->n_types))) return rc;
+  if ((rc = h2d(h, d.agent_type, b->agent_type, (size_t)na))) return rc;
+  if ((rc = h2d(h, d.lat_to, b->lat_to_exch, (size_t)na))) return rc;
+  if ((rc = h2d(h, d.lat_from, b->lat_from_exch, (size_t)na))) return rc;
+  if ((rc = h2d(h, d.size, reinterpret_cast<const long long*>(b->agent_size), (size_t)na))) return rc;
+  if ((rc = h2d(h, d.wakeup_time, reinterpret_cast<const long long*>(b->agent_wakeup_time), (size_t)na))) return rc;
+  if ((rc = h2d(h, d.agent_theta, b->agent_theta, (size_t)na))) return rc;
+  if ((rc = h2d(h, d.theta, b->theta, (size_t)(b->n_theta_total > 0 ? b->n_theta_total : 0)))) return rc;
+  if ((rc = h2d(h, d.mom_index, mom_index.data(), (size_t)na))) return rc;
+  if (b->rng_mode == ABIDES_RNG_MT19937) {
+    if ((rc = h2d(h, (const unsigned*)h->mt_pristine, b->mt_key, ns * ABIDES_MT_N))) return rc;
+    if ((rc = h2d(h, d.mt_pos, b->mt_pos, ns))) return rc;
+    if ((rc = h2d(h, d.mt_has_gauss, b->mt_has_gauss, ns))) return rc;
+    if ((rc = h2d(h, d.mt_gauss, b->mt_gauss, ns))) return rc;
+  }
+  h->launches_since_load = 0;
+  if ((rc = launch_init(h))) return rc;
+  CK(cudaStreamSynchronize(h->stream));      // mom_index (a local vector) must outlive the copy
   h->n_instances = ni; h->n_agents_total = na; h->loaded = true;
+  return 0;
+}
+
+/* Re-arm the loaded batch (inputs stay resident in HBM): restores the MT19937 states and rebuilds the
+ * initial device state, so the same batch can be run again. */
+int abides_reset(abides_handle* h) {
+  if (!h || !h->loaded) return fail(ABIDES_ESTATE, "abides_reset: no batch loaded");
+  CK(cudaSetDevice(h->device));
+  CK(cudaEventRecord(h->ev0, h->stream));
+  int rc = launch_init(h);
+  if (rc) return rc;
+  CK(cudaEventRecord(h->ev1, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaEventElapsedTime(&h->last_reset_ms, h->ev0, h->ev1));
+  return 0;
+}
+
+int abides_last_reset_ms(abides_handle* h, float* ms) {
+  if (!h) return fail(ABIDES_EINVAL, "NULL handle");
+  if (ms) *ms = h->last_reset_ms;
   return 0;
 }
 
@@ -1586,6 +1663,7 @@ int abides_run(abides_handle* h, int64_t until_time) {
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
   h->last_launches = 1;
+  h->launches_since_load += 1;
   return 0;
 }
 

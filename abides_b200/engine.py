@@ -49,6 +49,10 @@ class Engine:
         self._ck(self._L.abides_load(self._h, C.byref(host_batch.c)), "abides_load")
         self.batch = host_batch
 
+    def reset(self):
+        """Re-arm the resident batch (no host->device traffic)."""
+        self._ck(self._L.abides_reset(self._h), "abides_reset")
+
     def run(self, until_time=INT64_MAX):
         self._ck(self._L.abides_run(self._h, int(until_time)), "abides_run")
 
@@ -56,6 +60,11 @@ class Engine:
         ms, n = C.c_float(0), C.c_int32(0)
         self._ck(self._L.abides_last_run_ms(self._h, C.byref(ms), C.byref(n)), "abides_last_run_ms")
         return ms.value, n.value
+
+    def last_reset_ms(self):
+        ms = C.c_float(0)
+        self._ck(self._L.abides_last_reset_ms(self._h, C.byref(ms)), "abides_last_reset_ms")
+        return ms.value
 
     def results(self, per_agent=True):
         hb = self.batch

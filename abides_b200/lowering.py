@@ -184,7 +184,10 @@ def lower_instance(agents, startTime, stopTime, defaultComputationDelay=1, defau
         m = agentLatencyModel
         kw = m.kwargs
         ml = kw["min_latency"]
-        if np.isscalar(ml):
+        if hasattr(ml, "to_exchange"):          # util.ExchangeStarLatency: row 0 / column 0 only
+            lat_to[:] = ml.to_exchange
+            lat_from[:] = ml.from_exchange
+        elif np.isscalar(ml):
             lat_to[:] = ml
             lat_from[:] = ml
         else:
@@ -215,6 +218,9 @@ def lower_instance(agents, startTime, stopTime, defaultComputationDelay=1, defau
         if agentLatency is None:
             lat_to[:] = defaultLatency
             lat_from[:] = defaultLatency
+        elif hasattr(agentLatency, "to_exchange"):
+            lat_to[:] = agentLatency.to_exchange
+            lat_from[:] = agentLatency.from_exchange
         else:
             lat_from[:] = np.asarray(agentLatency[0], dtype=np.float64)
             lat_to[:] = np.asarray([agentLatency[i][0] for i in range(n)], dtype=np.float64)

@@ -1,0 +1,202 @@
+"""Host runtime above the C ABI: run lowered instances on the GPU(s), batch seed sweeps, write
+results back into the descriptor objects, print the reference's end-of-run lines.
+
+Seed sweeps (reference: config/parallel.py:9-22 spawns one process per seed) become ONE batch: every
+seed's config module body is executed with `capture()` active, so `Kernel.runner` records the
+lowered instance instead of running it, and all instances then go to the device in one launch."""
+import contextlib
+import os
+import runpy
+import sys
+import time
+
+import numpy as np
+
+from . import _abi, lowering
+from .engine import Engine
+
+COMPAT_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "compat")
+_capture = None
+_engines = {}
+
+
+def capturing():
+    return _capture is not None
+
+
+def captured(spec, kernel):
+    _capture.append((spec, kernel))
+
+
+@contextlib.contextmanager
+def capture():
+    global _capture
+    prev, _capture = _capture, []
+    try:
+        yield _capture
+    finally:
+        _capture = prev
+
+
+def engine(device=0):
+    if device not in _engines:
+        _engines[device] = Engine(device)
+    return _engines[device]
+
+
+class RunOutput:
+    def __init__(self, hb, res, ares, kernel_ms, wall_s):
+        self.hb, self.res, self.ares, self.kernel_ms, self.wall_s = hb, res, ares, kernel_ms, wall_s
+
+    def agents(self, inst):
+        ic = self.hb.instances[inst]
+        return self.ares[ic.agent_offset:ic.agent_offset + ic.n_agents]
+
+
+def run_specs(specs, device=0, rng_mode=_abi.RNG_MT19937, trace_capacity=0):
+    """Kernel.runner for a list of lowered instances: H2D, run to completion, D2H."""
+    hb = lowering.HostBatch(specs, rng_mode=rng_mode, trace_capacity=trace_capacity)
+    eng = engine(device)
+    t0 = time.perf_counter()
+    eng.load(hb)
+    eng.run()
+    res, ares = eng.results_arrays()
+    wall = time.perf_counter() - t0
+    bad = np.nonzero(res["status"] != 0)[0]
+    if len(bad):
+        raise RuntimeError("device reported status %d for instance %d (see enum abides_error)"
+                           % (int(res["status"][bad[0]]), int(bad[0])))
+    return RunOutput(hb, res.copy(), ares.copy(), eng.last_run_ms()[0], wall)
+
+
+def write_back(kernel, out, inst):
+    """Copy the end-of-run portfolio of instance `inst` into kernel.agents (TradingAgent.py:122-147)."""
+    ar = out.agents(inst)
+    r = out.res[inst]
+    kernel.meanResultByAgentType, kernel.agentCountByType = {}, {}
+    ex = kernel.agents[0]
+    symbol = next(iter(ex.order_books))
+    ex.order_books[symbol].last_trade = int(r["last_trade"])
+    for a in kernel.agents[1:]:
+        rec = ar[a.id]
+        a.holdings = {'CASH': int(rec["cash"])}
+        if rec["holdings"] != 0:
+            a.holdings[symbol] = int(rec["holdings"])
+        a.marked_to_market = int(rec["marked_to_market"])
+        fv = float(rec["final_valuation"])
+        a.final_valuation = None if np.isnan(fv) else fv
+        gain = a.marked_to_market - a.starting_cash
+        kernel.meanResultByAgentType[a.type] = kernel.meanResultByAgentType.get(a.type, 0) + gain
+        kernel.agentCountByType[a.type] = kernel.agentCountByType.get(a.type, 0) + 1
+    kernel.ttl_messages = int(r["ttl_messages"])
+    kernel.custom_state['kernel_event_queue_elapsed_wallclock'] = out.wall_s
+    kernel.custom_state['kernel_slowest_agent_finish_time'] = int(r["slowest_agent_finish_time"])
+    kernel.custom_state['ttl_messages'] = int(r["ttl_messages"])
+
+
+def mean_ending_values(kernel):
+    """"Mean ending value by agent type" (Kernel.py:318-322): int(round(sum / count))."""
+    return {t: int(round(v / kernel.agentCountByType[t])) for t, v in kernel.meanResultByAgentType.items()}
+
+
+def report(kernel, out, inst, per_agent=True, file=None):
+    file = file or sys.stdout
+    if per_agent:
+        for a in kernel.agents[1:]:
+            print("Final holdings for {}: {}.  Marked to market: {}".format(
+                a.name, a.fmtHoldings(a.holdings), a.marked_to_market), file=file)
+    secs = max(out.wall_s, 1e-9)
+    print("Event Queue elapsed: {:.6f}s, messages: {}, messages per second: {:0.1f}".format(
+        secs, kernel.ttl_messages, kernel.ttl_messages / secs), file=file)
+    print("Mean ending value by agent type:", file=file)
+    for t, v in mean_ending_values(kernel).items():
+        print("{}: {:d}".format(t, v), file=file)
+    print("Simulation ending!", file=file)
+
+
+def find_config(name):
+    for base in (os.path.join(COMPAT_DIR, "config"), os.getcwd(), os.path.join(os.getcwd(), "config")):
+        p = os.path.join(base, name + ".py")
+        if os.path.exists(p):
+            return p
+    if os.path.exists(name):
+        return name
+    raise FileNotFoundError("config %r not found" % name)
+
+
+@contextlib.contextmanager
+def _compat_path():
+    sys.path.insert(0, COMPAT_DIR)
+    try:
+        yield
+    finally:
+        sys.path.remove(COMPAT_DIR)
+
+
+def _reset_process_globals():
+    """The reference keeps process-global counters; each captured instance starts from a clean process."""
+    for mod, attr in (("message.Message", "Message"), ("util.order.Order", "Order")):
+        m = sys.modules.get(mod)
+        if m is not None:
+            setattr(getattr(m, attr), "uniq" if attr == "Message" else "order_id", 0)
+
+
+def build_instances(config, arg_lists, quiet=True):
+    """Execute the config module body once per argument list (e.g. one per seed) under capture();
+    returns [(InstanceSpec, Kernel)]."""
+    path = find_config(config)
+    out = []
+    with _compat_path(), capture() as cap:
+        for args in arg_lists:
+            _reset_process_globals()
+            argv, sys.argv = sys.argv, ["abides.py", "-c", config] + [str(a) for a in args]
+            try:
+                if quiet:
+                    with open(os.devnull, "w") as dn, contextlib.redirect_stdout(dn):
+                        runpy.run_path(path, run_name="__abides_config__")
+                else:
+                    runpy.run_path(path, run_name="__abides_config__")
+            finally:
+                sys.argv = argv
+        out = list(cap)
+    return out
+
+
+def _build_chunk(job):
+    config, arg_lists = job
+    return [s for s, _ in build_instances(config, arg_lists)]
+
+
+def build_specs_parallel(config, arg_lists, workers=None):
+    """build_instances over a process pool (config-time numpy work is host-bound); returns specs only."""
+    import multiprocessing as mp
+    workers = workers or os.cpu_count() or 1
+    workers = max(1, min(workers, len(arg_lists)))
+    if workers == 1:
+        return _build_chunk((config, arg_lists))
+    chunks = [arg_lists[i::workers] for i in range(workers)]
+    with mp.get_context("fork").Pool(workers) as pool:
+        parts = pool.map(_build_chunk, [(config, c) for c in chunks])
+    specs = [None] * len(arg_lists)
+    for w, part in enumerate(parts):
+        for j, s in enumerate(part):
+            specs[w + j * workers] = s
+    return specs
+
+
+def parallel_seeds(seed, num_simulations):
+    """The seed stream of the reference's sweep driver (config/parallel.py:10-11)."""
+    rs = np.random.RandomState(seed)
+    return [int(s) for s in rs.randint(low=0, high=2 ** 32, size=num_simulations)]
+
+
+def run_config_batch(config, arg_lists, device=0, write=True):
+    """Seed sweep / parameter grid in one launch.  Returns (RunOutput, [Kernel])."""
+    built = build_instances(config, arg_lists)
+    specs = [s for s, _ in built]
+    kernels = [k for _, k in built]
+    out = run_specs(specs, device=device)
+    if write:
+        for i, k in enumerate(kernels):
+            write_back(k, out, i)
+    return out, kernels

@@ -216,6 +216,7 @@ const char* abides_version(void);
 
 /* Kernel.runner: load a batch (host -> device), run it, read results (device -> host). */
 int  abides_load(abides_handle* h, const abides_batch* batch);
+int  abides_reset(abides_handle* h);                        /* re-arm the resident batch for another run */
 int  abides_run(abides_handle* h, int64_t until_time);      /* INT64_MAX: to completion incl. kernelStopping */
 int  abides_read_results(abides_handle* h, abides_instance_result* inst_out /*[n_instances]*/,
                          abides_agent_result* agents_out /*[n_agents_total] or NULL*/);
@@ -223,6 +224,7 @@ int  abides_read_trace(abides_handle* h, int32_t instance, abides_trace_rec* out
                        int64_t* n_out);
 /* device-side timing of the last abides_run (CUDA events on the launching stream), ms */
 int  abides_last_run_ms(abides_handle* h, float* ms, int32_t* n_launches);
+int  abides_last_reset_ms(abides_handle* h, float* ms);
 
 /* util/OrderBook.py replay: n_books independent books, book b replays ops[op_offset[b] .. op_offset[b+1]).
  * events_out is [n_ops_total * max_events_per_op]; event_count_out [n_ops_total]; states_out [n_ops_total]. */
