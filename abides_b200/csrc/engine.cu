@@ -40,7 +40,7 @@ extern __shared__ __align__(128) unsigned char smem_raw[];
 constexpr int NEAR_CAP = 128;
 constexpr int FILL_MAX = 64;
 constexpr int FILL_MIN = 16;
-constexpr int BOOK_CAP = 256;
+constexpr int BOOK_TOP = 128;          // orders per side kept in shared memory
 constexpr int MOM_RING = 64;            // >= 51 prefix sums
 constexpr int TRACE_FUNDAMENTAL = 64;   // trace code of an oracle step (time = ts, p0 = value)
 
@@ -90,22 +90,22 @@ struct Hot {
   long long near_limit_t; unsigned long long near_limit_k; long long dT;
   unsigned uniq;
   int n_near, n_far_total, n_far_live;
-  int n_bids, n_asks, last_trade, has_last_trade;
-  int arena_top, status, n_trace, queue_peak, book_peak_orders, done, started, pad0;
+  int n_bids, n_asks, nd_bids, nd_asks, last_trade, has_last_trade;
+  int arena_top, status, n_trace, queue_peak, book_peak_orders, done;
   RngState rs[ABIDES_EXTRA_STREAMS];
 };
 
 struct __align__(128) InstShared {
   EvKey nkey[NEAR_CAP];
   EvPay npay[NEAR_CAP];
-  BookOrd bids[BOOK_CAP];
-  BookOrd asks[BOOK_CAP];
+  BookOrd bids[BOOK_TOP];
+  BookOrd asks[BOOK_TOP];
   AgentRec ag;
   Hot hot;
 };
 
 struct DevBatch {
-  int n_instances, rng_mode, trace_cap, far_cap, arena_cap, n_types;
+  int n_instances, rng_mode, trace_cap, far_cap, arena_cap, n_types, deep_cap;
   const abides_instance_cfg* cfg;
   const abides_agent_type* types;
   abm_dd* type_log1mk;                  // log(1 - kappa) per type, double-double
@@ -125,6 +125,7 @@ struct DevBatch {
   EvKey* far_keys;
   EvPay* far_pay;
   OpenOrd* arena;
+  BookOrd* deep_book;                   // [n_instances][2][deep_cap]
   double* mom_ring;
   const int* mom_index;                 // per agent row: ring index or -1
   abides_trace_rec* trace;
@@ -135,7 +136,7 @@ struct DevBatch {
 struct Run {                            // per-launch context, shared memory, not persisted
   DevBatch db;
   abides_instance_cfg cfg;
-  EvKey* far_keys; EvPay* far_pay; OpenOrd* arena;
+  EvKey* far_keys; EvPay* far_pay; OpenOrd* arena; BookOrd* deep;
   abides_trace_rec* trace;
   long long aoff;                       // agent_offset
   int inst, n_agents;
@@ -574,9 +575,24 @@ __device__ __forceinline__ EvPay pay_order(int code, int sender, int id, int pri
 }
 
 // ----------------------------------------------------------------------------------------------
-// order book (util/OrderBook.py): each side a price-time sorted array in shared memory
+// order book (util/OrderBook.py).  Each side is ONE price-time sorted sequence (index 0 = best
+// price, oldest first).  Its best BOOK_TOP entries live in shared memory; the rest -- the "deep
+// book" -- is spilled to HBM in REVERSE order (deep[nd-1] is the best deep entry), so that moving
+// entries across the boundary is an O(1) push/pop at the array's end and every scan or shift over
+// the deep part is a run of coalesced 512-byte warp transactions.
 // ----------------------------------------------------------------------------------------------
-__device__ __noinline__ void side_remove(BookOrd* s, int& n, int idx) {       // delete s[idx], keep order
+struct Side { BookOrd* top; int* ns; BookOrd* deep; int* nd; bool is_buy; };
+__device__ __forceinline__ Side book_side(bool is_buy) {
+  Side sd; InstShared* S = &SM->st;
+  sd.top = is_buy ? S->bids : S->asks;
+  sd.ns = is_buy ? &S->hot.n_bids : &S->hot.n_asks;
+  sd.deep = SM->run.deep + (is_buy ? 0 : SM->run.db.deep_cap);
+  sd.nd = is_buy ? &S->hot.nd_bids : &S->hot.nd_asks;
+  sd.is_buy = is_buy;
+  return sd;
+}
+// generic warp-parallel single-slot shifts on an array in shared or global memory
+__device__ __noinline__ void arr_remove(BookOrd* s, int n, int idx) {           // delete s[idx] from s[0..n)
   __syncwarp();
   for (int base = idx; base < n - 1; base += 32) {
     int j = base + LANE; BookOrd t;
@@ -586,11 +602,10 @@ __device__ __noinline__ void side_remove(BookOrd* s, int& n, int idx) {       //
     if (act) s[j] = t;
     __syncwarp();
   }
-  n--;
 }
-__device__ __noinline__ void side_insert(BookOrd* s, int& n, int idx, const BookOrd& o) {
+__device__ __noinline__ void arr_insert(BookOrd* s, int n, int idx, const BookOrd& o) {   // s[idx] = o, tail moves up
   __syncwarp();
-  int cnt = n - idx;                                   // elements to move right by one
+  int cnt = n - idx;
   for (int done = 0; done < cnt; done += 32) {
     int j = n - 1 - done - LANE; BookOrd t;
     bool act = j >= idx;
@@ -600,57 +615,123 @@ __device__ __noinline__ void side_insert(BookOrd* s, int& n, int idx, const Book
     __syncwarp();
   }
   if (LANE == 0) s[idx] = o;
-  n++;
   __syncwarp();
 }
-// getInsideBids(1)/getInsideAsks(1) (:378-399)
-__device__ __noinline__ void side_inside(const BookOrd* s, int n, int& price, int& vol) {
+// count entries of s[0..n) whose price is better than or equal to `price` for this side
+__device__ __noinline__ int arr_count_better_eq(const BookOrd* s, int n, int price, bool is_buy) {
   __syncwarp();
-  if (n == 0) { price = -1; vol = 0; return; }
-  int p = s[0].price, v = 0;
-  for (int base = 0; base < n; base += 32) {
+  int cnt = 0;
+  for (int j = LANE; j < n; j += 32) {
+    int p = s[j].price;
+    cnt += (is_buy ? p >= price : p <= price) ? 1 : 0;
+  }
+  return warp_sum_i(cnt);
+}
+// the shared-memory part ran empty: pull the best entries of the deep book back in
+__device__ __noinline__ void side_refill(const Side& sd) {
+  int nd = *sd.nd, ns = *sd.ns;
+  if (ns > 0 || nd == 0) return;
+  int k = nd < BOOK_TOP / 2 ? nd : BOOK_TOP / 2;
+  __syncwarp();
+  for (int i = LANE; i < k; i += 32) sd.top[i] = sd.deep[nd - 1 - i];
+  __syncwarp();
+  *sd.ns = k; *sd.nd = nd - k;
+}
+__device__ __noinline__ void side_pop_front(const Side& sd) {                   // remove the best entry
+  arr_remove(sd.top, *sd.ns, 0);
+  *sd.ns -= 1;
+  side_refill(sd);
+}
+// getInsideBids(1)/getInsideAsks(1) (:378-399): price and total quantity of the best level
+__device__ __noinline__ void side_inside(const Side& sd, int& price, int& vol) {
+  __syncwarp();
+  int ns = *sd.ns, nd = *sd.nd;
+  if (ns == 0) { price = -1; vol = 0; return; }
+  int p = sd.top[0].price, v = 0;
+  bool whole = true;                       // does the level run to the end of the shared part?
+  for (int base = 0; base < ns; base += 32) {
     int j = base + LANE;
-    bool in = j < n && s[j].price == p;
-    v += in ? s[j].qty : 0;
-    if (!__any_sync(FULL, in)) break;
+    bool in = j < ns && sd.top[j].price == p;
+    v += in ? sd.top[j].qty : 0;
+    if (__any_sync(FULL, j < ns && !in)) { whole = false; break; }
+  }
+  if (whole) {
+    for (int base = 0; base < nd; base += 32) {
+      int j = nd - 1 - base - LANE;
+      bool in = j >= 0 && sd.deep[j].price == p;
+      v += in ? sd.deep[j].qty : 0;
+      if (__any_sync(FULL, j >= 0 && !in)) break;
+    }
   }
   price = p; vol = warp_sum_i(v);
 }
 // OrderBook.enterOrder (:272-298): position = number of resting orders with better-or-equal price
 __device__ __noinline__ void book_enter(const BookOrd& o, bool is_buy) {
-  InstShared* S = &SM->st; Hot& h = S->hot;
-  BookOrd* s = is_buy ? S->bids : S->asks;
-  int& n = is_buy ? h.n_bids : h.n_asks;
-  if (n >= BOOK_CAP) { h.status = ABIDES_EOVERFLOW; return; }
-  __syncwarp();
-  int cnt = 0;
-  for (int j = LANE; j < n; j += 32) {
-    int p = s[j].price;
-    cnt += (is_buy ? p >= o.price : p <= o.price) ? 1 : 0;
+  Hot& h = SM->st.hot;
+  Side sd = book_side(is_buy);
+  int ns = *sd.ns, nd = *sd.nd;
+  int cs = arr_count_better_eq(sd.top, ns, o.price, is_buy);
+  bool to_top = cs < ns || nd == 0;
+  int cd = 0;
+  if (!to_top) {
+    cd = arr_count_better_eq(sd.deep, nd, o.price, is_buy);
+    if (cd == 0 && ns < BOOK_TOP) to_top = true;        // worse than all of top, better than all of deep
   }
-  cnt = warp_sum_i(cnt);
-  side_insert(s, n, cnt, o);
-  int tot = h.n_bids + h.n_asks;
+  if (to_top && ns == BOOK_TOP && cs == ns) to_top = false;   // full shared part and o is its new worst: goes deep
+  if (to_top) {
+    if (ns == BOOK_TOP) {                                // spill the worst shared entry to the deep book's best end
+      if (nd >= SM->run.db.deep_cap) { h.status = ABIDES_EOVERFLOW; return; }
+      __syncwarp();
+      if (LANE == 0) sd.deep[nd] = sd.top[ns - 1];
+      __syncwarp();
+      *sd.nd = nd + 1; ns--;
+    }
+    arr_insert(sd.top, ns, cs, o);
+    *sd.ns = ns + 1;
+  } else {
+    if (nd >= SM->run.db.deep_cap) { h.status = ABIDES_EOVERFLOW; return; }
+    arr_insert(sd.deep, nd, nd - cd, o);                 // logical index cd <-> physical nd - cd (reversed)
+    *sd.nd = nd + 1;
+  }
+  int tot = h.n_bids + h.n_asks + h.nd_bids + h.nd_asks;
   if (tot > h.book_peak_orders) h.book_peak_orders = tot;
 }
-
+// find (price, id) on a side; returns 0 = absent, 1 = in the shared part, 2 = in the deep part; idx physical
+__device__ __noinline__ int side_find(const Side& sd, int price, int id, int& idx) {
+  __syncwarp();
+  int ns = *sd.ns, nd = *sd.nd;
+  for (int base = 0; base < ns; base += 32) {
+    int j = base + LANE;
+    bool hit = j < ns && sd.top[j].price == price && sd.top[j].id == id;
+    unsigned m = __ballot_sync(FULL, hit);
+    if (m) { idx = base + __ffs(m) - 1; return 1; }
+  }
+  // deep part, scanned from its best end (highest physical index) so the FIRST match in book order wins
+  for (int base = 0; base < nd; base += 32) {
+    int j = nd - 1 - base - LANE;
+    bool hit = false;
+    if (j >= 0) { BookOrd e = sd.deep[j]; hit = e.price == price && e.id == id; }
+    unsigned m = __ballot_sync(FULL, hit);
+    if (m) { idx = nd - 1 - base - (__ffs(m) - 1); return 2; }
+  }
+  return 0;
+}
 
 // OrderBook.handleLimitOrder (:46-158)
 template <typename Send>
 __device__ __noinline__ void book_handle_limit(Send send, int agent, int id, int price, int qty, bool is_buy) {
-  InstShared* S = &SM->st; Hot& h = S->hot;
+  Hot& h = SM->st.hot;
   if (qty <= 0) return;
   long long ex_qty = 0, ex_pq = 0; int executed = 0;
-  BookOrd* opp = is_buy ? S->asks : S->bids;
-  int& nopp = is_buy ? h.n_asks : h.n_bids;
+  Side opp = book_side(!is_buy);
   for (;;) {
     __syncwarp();
     bool match = false; BookOrd top;
-    if (nopp > 0) { top = opp[0]; match = is_buy ? price >= top.price : price <= top.price; }
+    if (*opp.ns > 0) { top = opp.top[0]; match = is_buy ? price >= top.price : price <= top.price; }
     if (match) {                                               // executeOrder (:190-256)
       int fill;
-      if (qty >= top.qty) { fill = top.qty; side_remove(opp, nopp, 0); }
-      else { fill = qty; __syncwarp(); if (LANE == 0) opp[0].qty = top.qty - qty; __syncwarp(); }
+      if (qty >= top.qty) { fill = top.qty; side_pop_front(opp); }
+      else { fill = qty; __syncwarp(); if (LANE == 0) opp.top[0].qty = top.qty - qty; __syncwarp(); }
       qty -= fill;
       send(agent, pay_order(ABIDES_MSG_ORDER_EXECUTED, 0, id, price, fill, is_buy, top.price));
       send(top.agent, pay_order(ABIDES_MSG_ORDER_EXECUTED, 0, top.id, top.price, fill, !is_buy, top.price));
@@ -672,20 +753,21 @@ __device__ __noinline__ void book_handle_limit(Send send, int agent, int id, int
 // OrderBook.cancelOrder (:300-348)
 template <typename Send>
 __device__ __noinline__ void book_cancel(Send send, int agent, int id, int price, bool is_buy) {
-  InstShared* S = &SM->st; Hot& h = S->hot;
-  BookOrd* s = is_buy ? S->bids : S->asks;
-  int& n = is_buy ? h.n_bids : h.n_asks;
-  __syncwarp();
-  int found = -1;
-  for (int base = 0; base < n; base += 32) {
-    int j = base + LANE;
-    bool hit = j < n && s[j].price == price && s[j].id == id;
-    unsigned m = __ballot_sync(FULL, hit);
-    if (m) { found = base + __ffs(m) - 1; break; }
+  Side sd = book_side(is_buy);
+  int idx = 0;
+  int where = side_find(sd, price, id, idx);
+  if (where == 0) return;
+  BookOrd o;
+  if (where == 1) {
+    o = sd.top[idx];
+    arr_remove(sd.top, *sd.ns, idx);
+    *sd.ns -= 1;
+    side_refill(sd);
+  } else {
+    o = sd.deep[idx];
+    arr_remove(sd.deep, *sd.nd, idx);
+    *sd.nd -= 1;
   }
-  if (found < 0) return;
-  BookOrd o = s[found];
-  side_remove(s, n, found);
   send(agent, pay_order(ABIDES_MSG_ORDER_CANCELLED, 0, o.id, o.price, o.qty, is_buy, -1));
 }
 
@@ -1115,8 +1197,8 @@ __device__ __noinline__ void exchange_receive(const EvPay& m) {
     }
     case ABIDES_MSG_QUERY_SPREAD: {
       EvPay r = pay_zero((ABIDES_MSG_QUERY_SPREAD | ABIDES_MSG_REPLY) | cflag);
-      side_inside(SM->st.bids, h.n_bids, r.w[1], r.w[2]);
-      side_inside(SM->st.asks, h.n_asks, r.w[3], r.w[4]);
+      side_inside(book_side(true), r.w[1], r.w[2]);
+      side_inside(book_side(false), r.w[3], r.w[4]);
       r.w[5] = h.last_trade;
       send(sender, r);
       break;
@@ -1342,6 +1424,7 @@ __global__ void __launch_bounds__(32) sim_kernel(DevBatch db, long long until_ti
     r.far_keys = db.far_keys + (size_t)inst * db.far_cap;
     r.far_pay = db.far_pay + (size_t)inst * db.far_cap;
     r.arena = db.arena + (size_t)inst * db.arena_cap;
+    r.deep = db.deep_book + (size_t)inst * 2 * db.deep_cap;
     r.trace = db.trace_cap > 0 ? db.trace + (size_t)inst * db.trace_cap : nullptr;
     r.aoff = db.cfg[inst].agent_offset; r.inst = inst; r.n_agents = db.cfg[inst].n_agents; r.cur_agent = -1;
   }
@@ -1575,6 +1658,7 @@ int abides_load(abides_handle* h, const abides_batch* b) {
     d.n_instances = ni; d.rng_mode = b->rng_mode; d.trace_cap = b->trace_capacity; d.n_types = b->n_types;
     d.far_cap = 4 * max_agents + 4096;
     d.arena_cap = 8 * max_agents + 4096;
+    d.deep_cap = 4 * max_agents + 1024;
     abides_instance_cfg* dcfg; abides_agent_type* dty; int* dat; double *dlt, *dlf; long long *dsz, *dwk; int *dath, *dth, *dmi;
     if ((rc = dev_alloc(h, &dcfg, (size_t)ni))) return rc;
     if ((rc = dev_alloc(h, &dty, (size_t)b->n_types))) return rc;
@@ -1603,6 +1687,7 @@ int abides_load(abides_handle* h, const abides_batch* b) {
     if ((rc = dev_alloc(h, &d.far_keys, (size_t)ni * d.far_cap))) return rc;
     if ((rc = dev_alloc(h, &d.far_pay, (size_t)ni * d.far_cap))) return rc;
     if ((rc = dev_alloc(h, &d.arena, (size_t)ni * d.arena_cap))) return rc;
+    if ((rc = dev_alloc(h, &d.deep_book, (size_t)ni * 2 * d.deep_cap))) return rc;
     if ((rc = dev_alloc(h, &d.mom_ring, (size_t)(n_mom > 0 ? n_mom : 1) * MOM_RING))) return rc;
     if ((rc = dev_alloc(h, &d.trace, (size_t)ni * (d.trace_cap > 0 ? d.trace_cap : 0)))) return rc;
     if ((rc = dev_alloc(h, &d.res, (size_t)ni))) return rc;
