@@ -42,12 +42,15 @@ constexpr int FILL_MAX = 64;
 constexpr int FILL_MIN = 16;
 constexpr int BOOK_TOP = 128;          // orders per side kept in shared memory
 constexpr int MOM_RING = 64;            // >= 51 prefix sums
+constexpr int TXN_CAP = 1 << 16;        // ring of transaction rows since the last volume query (per instance)
+constexpr int UNR_CAP = 1 << 16;        // ring of de-duplicated rows the volume queries sum over
 constexpr int TRACE_FUNDAMENTAL = 64;   // trace code of an oracle step (time = ts, p0 = value)
 
 struct __align__(16) EvKey { long long t; unsigned long long k2; };   // k2 = rcpt<<33 | wakeup<<32 | uniq
 struct __align__(16) EvPay { int w[8]; };
 struct __align__(16) BookOrd { int price, qty, id, agent; };
 struct __align__(16) OpenOrd { int key, id, price, sqty; };            // sqty > 0 buy, < 0 sell
+struct __align__(16) TxnRow { long long t; int q; int seq; };          // OrderBook.history transaction + bucket of its record
 
 enum : unsigned {
   F_HAS_OPEN = 1u, F_HAS_CLOSE = 2u, F_MKT_CLOSED = 4u, F_HAS_LAST_TRADE = 8u, F_HAS_DAILY_CLOSE = 16u,
@@ -92,6 +95,8 @@ struct Hot {
   int n_near, n_far_total, n_far_live;
   int n_bids, n_asks, nd_bids, nd_asks, last_trade, has_last_trade;
   int arena_top, status, n_trace, queue_peak, book_peak_orders, done;
+  int hist_B, tv_prev_len;              // open history bucket; OrderBook._transacted_volume previous length
+  long long log_len, log_mark, unr_len; // transaction rows logged / scanned by the last query / unrolled rows
   RngState rs[ABIDES_EXTRA_STREAMS];
 };
 
@@ -100,6 +105,8 @@ struct __align__(128) InstShared {
   EvPay npay[NEAR_CAP];
   BookOrd bids[BOOK_TOP];
   BookOrd asks[BOOK_TOP];
+  int bid_seq[BOOK_TOP];                // history bucket in which each resting order was entered
+  int ask_seq[BOOK_TOP];
   AgentRec ag;
   Hot hot;
 };
@@ -126,6 +133,9 @@ struct DevBatch {
   EvPay* far_pay;
   OpenOrd* arena;
   BookOrd* deep_book;                   // [n_instances][2][deep_cap]
+  int* deep_seq;                        // [n_instances][2][deep_cap]
+  TxnRow* txn_log;                      // [n_instances][TXN_CAP]
+  TxnRow* unrolled;                     // [n_instances][UNR_CAP]
   double* mom_ring;
   const int* mom_index;                 // per agent row: ring index or -1
   abides_trace_rec* trace;
@@ -136,12 +146,13 @@ struct DevBatch {
 struct Run {                            // per-launch context, shared memory, not persisted
   DevBatch db;
   abides_instance_cfg cfg;
-  EvKey* far_keys; EvPay* far_pay; OpenOrd* arena; BookOrd* deep;
+  EvKey* far_keys; EvPay* far_pay; OpenOrd* arena; BookOrd* deep; int* deep_seq; TxnRow* txn_log; TxnRow* unrolled;
   abides_trace_rec* trace;
   long long aoff;                       // agent_offset
   int inst, n_agents;
   int cur_agent;                        // agent whose record sits in st.ag (-1 none)
-  int pad;
+  int rp_op, rp_max, rp_base;           // order-book replay harness: current op, events per op, first op
+  abides_book_event* rp_events; int* rp_counts;
 };
 struct __align__(128) Smem { InstShared st; Run run; };
 #define SM (reinterpret_cast<Smem*>(smem_raw))
@@ -301,6 +312,7 @@ __device__ __noinline__ void trace_write(long long time, int agent, int code, lo
     r.time = time; r.agent = agent; r.code = code; r.p0 = p0; r.p1 = p1; r.p2 = p2; r.p3 = p3;
     SM->run.trace[i] = r;
   }
+  __syncwarp();
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -336,6 +348,7 @@ __device__ __noinline__ void far_append(const EvKey& k, const EvPay& p) {
   if (LANE == 0) SM->run.far_keys[i] = k;
   else if (LANE == 1) *reinterpret_cast<int4*>(&SM->run.far_pay[i].w[0]) = make_int4(p.w[0], p.w[1], p.w[2], p.w[3]);
   else if (LANE == 2) *reinterpret_cast<int4*>(&SM->run.far_pay[i].w[4]) = make_int4(p.w[4], p.w[5], p.w[6], p.w[7]);
+  __syncwarp();
   h.n_far_total = i + 1;
   h.n_far_live++;
 }
@@ -581,40 +594,42 @@ __device__ __forceinline__ EvPay pay_order(int code, int sender, int id, int pri
 // entries across the boundary is an O(1) push/pop at the array's end and every scan or shift over
 // the deep part is a run of coalesced 512-byte warp transactions.
 // ----------------------------------------------------------------------------------------------
-struct Side { BookOrd* top; int* ns; BookOrd* deep; int* nd; bool is_buy; };
+struct Side { BookOrd* top; int* tseq; int* ns; BookOrd* deep; int* dseq; int* nd; bool is_buy; };
 __device__ __forceinline__ Side book_side(bool is_buy) {
   Side sd; InstShared* S = &SM->st;
   sd.top = is_buy ? S->bids : S->asks;
+  sd.tseq = is_buy ? S->bid_seq : S->ask_seq;
   sd.ns = is_buy ? &S->hot.n_bids : &S->hot.n_asks;
   sd.deep = SM->run.deep + (is_buy ? 0 : SM->run.db.deep_cap);
+  sd.dseq = SM->run.deep_seq + (is_buy ? 0 : SM->run.db.deep_cap);
   sd.nd = is_buy ? &S->hot.nd_bids : &S->hot.nd_asks;
   sd.is_buy = is_buy;
   return sd;
 }
-// generic warp-parallel single-slot shifts on an array in shared or global memory
-__device__ __noinline__ void arr_remove(BookOrd* s, int n, int idx) {           // delete s[idx] from s[0..n)
+// generic warp-parallel single-slot shifts on an (order, bucket) array pair in shared or global memory
+__device__ __noinline__ void arr_remove(BookOrd* s, int* q, int n, int idx) {   // delete slot idx from [0..n)
   __syncwarp();
   for (int base = idx; base < n - 1; base += 32) {
-    int j = base + LANE; BookOrd t;
+    int j = base + LANE; BookOrd t; int tq = 0;
     bool act = j < n - 1;
-    if (act) t = s[j + 1];
+    if (act) { t = s[j + 1]; tq = q[j + 1]; }
     __syncwarp();
-    if (act) s[j] = t;
+    if (act) { s[j] = t; q[j] = tq; }
     __syncwarp();
   }
 }
-__device__ __noinline__ void arr_insert(BookOrd* s, int n, int idx, const BookOrd& o) {   // s[idx] = o, tail moves up
+__device__ __noinline__ void arr_insert(BookOrd* s, int* q, int n, int idx, const BookOrd& o, int oseq) {
   __syncwarp();
   int cnt = n - idx;
   for (int done = 0; done < cnt; done += 32) {
-    int j = n - 1 - done - LANE; BookOrd t;
+    int j = n - 1 - done - LANE; BookOrd t; int tq = 0;
     bool act = j >= idx;
-    if (act) t = s[j];
+    if (act) { t = s[j]; tq = q[j]; }
     __syncwarp();
-    if (act) s[j + 1] = t;
+    if (act) { s[j + 1] = t; q[j + 1] = tq; }
     __syncwarp();
   }
-  if (LANE == 0) s[idx] = o;
+  if (LANE == 0) { s[idx] = o; q[idx] = oseq; }
   __syncwarp();
 }
 // count entries of s[0..n) whose price is better than or equal to `price` for this side
@@ -633,12 +648,12 @@ __device__ __noinline__ void side_refill(const Side& sd) {
   if (ns > 0 || nd == 0) return;
   int k = nd < BOOK_TOP / 2 ? nd : BOOK_TOP / 2;
   __syncwarp();
-  for (int i = LANE; i < k; i += 32) sd.top[i] = sd.deep[nd - 1 - i];
+  for (int i = LANE; i < k; i += 32) { sd.top[i] = sd.deep[nd - 1 - i]; sd.tseq[i] = sd.dseq[nd - 1 - i]; }
   __syncwarp();
   *sd.ns = k; *sd.nd = nd - k;
 }
 __device__ __noinline__ void side_pop_front(const Side& sd) {                   // remove the best entry
-  arr_remove(sd.top, *sd.ns, 0);
+  arr_remove(sd.top, sd.tseq, *sd.ns, 0);
   *sd.ns -= 1;
   side_refill(sd);
 }
@@ -670,6 +685,7 @@ __device__ __noinline__ void book_enter(const BookOrd& o, bool is_buy) {
   Hot& h = SM->st.hot;
   Side sd = book_side(is_buy);
   int ns = *sd.ns, nd = *sd.nd;
+  int oseq = h.hist_B;                                   // history[0][order_id] = {...} (:60-64)
   int cs = arr_count_better_eq(sd.top, ns, o.price, is_buy);
   bool to_top = cs < ns || nd == 0;
   int cd = 0;
@@ -682,15 +698,15 @@ __device__ __noinline__ void book_enter(const BookOrd& o, bool is_buy) {
     if (ns == BOOK_TOP) {                                // spill the worst shared entry to the deep book's best end
       if (nd >= SM->run.db.deep_cap) { h.status = ABIDES_EOVERFLOW; return; }
       __syncwarp();
-      if (LANE == 0) sd.deep[nd] = sd.top[ns - 1];
+      if (LANE == 0) { sd.deep[nd] = sd.top[ns - 1]; sd.dseq[nd] = sd.tseq[ns - 1]; }
       __syncwarp();
       *sd.nd = nd + 1; ns--;
     }
-    arr_insert(sd.top, ns, cs, o);
+    arr_insert(sd.top, sd.tseq, ns, cs, o, oseq);
     *sd.ns = ns + 1;
   } else {
     if (nd >= SM->run.db.deep_cap) { h.status = ABIDES_EOVERFLOW; return; }
-    arr_insert(sd.deep, nd, nd - cd, o);                 // logical index cd <-> physical nd - cd (reversed)
+    arr_insert(sd.deep, sd.dseq, nd, nd - cd, o, oseq);  // logical index cd <-> physical nd - cd (reversed)
     *sd.nd = nd + 1;
   }
   int tot = h.n_bids + h.n_asks + h.nd_bids + h.nd_asks;
@@ -717,6 +733,75 @@ __device__ __noinline__ int side_find(const Side& sd, int price, int id, int& id
   return 0;
 }
 
+// ---- OrderBook.history / get_transacted_volume (:401-471) ------------------------------------
+// The reference keeps, per history bucket (one per trade-producing order), the (time, qty) transactions
+// of the orders ENTERED in that bucket, and a volume query unrolls only a window of "recent" buckets.
+// Equivalent device form: every transaction is one TxnRow tagged with the bucket of its record; a query
+// scans the rows logged since the previous query, keeps those whose bucket lies in the window, drops
+// duplicate (time, qty) rows of that batch and appends the rest to the unrolled ring it then sums over.
+__device__ __forceinline__ void txn_log_row(long long t, int q, int seq) {
+  Hot& h = SM->st.hot;
+  long long i = h.log_len;
+  __syncwarp();
+  if (LANE == 0 && SM->run.txn_log) { TxnRow r; r.t = t; r.q = q; r.seq = seq; SM->run.txn_log[i & (TXN_CAP - 1)] = r; }
+  __syncwarp();
+  h.log_len = i + 1;
+}
+__device__ __noinline__ long long book_transacted_volume(long long now, long long lookback) {
+  Hot& h = SM->st.hot;
+  const int SH = SM->run.cfg.stream_history;
+  int B = h.hist_B;
+  int n = (B + 1 < SH + 1) ? B + 1 : SH + 1, p = h.tv_prev_len;
+  int lo = 1, hi = 0;
+  if (p == 0) { lo = B - (n - 1); hi = B; h.tv_prev_len = n; }
+  else if (p != n) { int cnt = n - p - 1; if (cnt > 0) { lo = B - cnt + 1; hi = B; } h.tv_prev_len = n; }
+  long long start = h.log_mark, end = h.log_len;
+  if (end - start > TXN_CAP) { h.status = ABIDES_EOVERFLOW; return 0; }
+  const TxnRow* lg = SM->run.txn_log;
+  TxnRow* un = SM->run.unrolled;
+  long long ulen = h.unr_len;
+  __syncwarp();
+  if (hi >= lo) {
+    for (long long base = start; base < end; base += 32) {
+      long long i = base + LANE;
+      bool keep = false; TxnRow r;
+      if (i < end) {
+        r = lg[i & (TXN_CAP - 1)];
+        keep = r.seq >= lo && r.seq <= hi;
+        if (keep) {                                     // drop_duplicates over this batch (:448-451)
+          for (long long j = i - 1; j >= start; j--) {
+            TxnRow e = lg[j & (TXN_CAP - 1)];
+            if (e.t != r.t) break;
+            if (e.q == r.q && e.seq >= lo && e.seq <= hi) { keep = false; break; }
+          }
+        }
+      }
+      unsigned m = __ballot_sync(FULL, keep);
+      if (keep) un[(ulen + __popc(m & ((1u << LANE) - 1u))) & (UNR_CAP - 1)] = r;
+      ulen += __popc(m);
+    }
+  }
+  __syncwarp();
+  h.unr_len = ulen;
+  h.log_mark = end;
+  __syncwarp();
+  // sum quantities of unrolled rows with time >= now - lookback (rows are in time order)
+  long long thr = now - lookback, sum = 0;
+  long long ul = h.unr_len, floor_i = ul > UNR_CAP ? ul - UNR_CAP : 0;
+  for (long long base = ul; base > floor_i; base -= 32) {
+    long long i = base - 1 - LANE;
+    bool in = false; TxnRow r;
+    if (i >= floor_i) { r = un[i & (UNR_CAP - 1)]; in = r.t >= thr; }
+    sum += in ? r.q : 0;
+    if (__any_sync(FULL, i >= floor_i && !in)) { floor_i = -1; break; }
+  }
+  if (floor_i > 0 && ul > UNR_CAP) {                     // the whole ring lies inside the window: rows were lost
+    h.status = ABIDES_EOVERFLOW;
+  }
+  for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
+  return sum;
+}
+
 // OrderBook.handleLimitOrder (:46-158)
 template <typename Send>
 __device__ __noinline__ void book_handle_limit(Send send, int agent, int id, int price, int qty, bool is_buy) {
@@ -729,9 +814,12 @@ __device__ __noinline__ void book_handle_limit(Send send, int agent, int id, int
     bool match = false; BookOrd top;
     if (*opp.ns > 0) { top = opp.top[0]; match = is_buy ? price >= top.price : price <= top.price; }
     if (match) {                                               // executeOrder (:190-256)
-      int fill;
+      int fill, tseq = opp.tseq[0];
       if (qty >= top.qty) { fill = top.qty; side_pop_front(opp); }
       else { fill = qty; __syncwarp(); if (LANE == 0) opp.top[0].qty = top.qty - qty; __syncwarp(); }
+      // history (:245-253): the aggressor logs its REMAINING quantity, the resting order the fill
+      txn_log_row(h.now, qty, h.hist_B);
+      if (h.hist_B - tseq <= SM->run.cfg.stream_history) txn_log_row(h.now, fill, tseq);
       qty -= fill;
       send(agent, pay_order(ABIDES_MSG_ORDER_EXECUTED, 0, id, price, fill, is_buy, top.price));
       send(top.agent, pay_order(ABIDES_MSG_ORDER_EXECUTED, 0, top.id, top.price, fill, !is_buy, top.price));
@@ -748,6 +836,7 @@ __device__ __noinline__ void book_handle_limit(Send send, int agent, int id, int
   if (executed) {
     h.last_trade = (int)(long long)rint((double)ex_pq / (double)ex_qty);     // int(round(.)) (:130)
     h.has_last_trade = 1;
+    h.hist_B++;                                                                // history.insert(0, {}) (:137)
   }
 }
 // OrderBook.cancelOrder (:300-348)
@@ -760,15 +849,71 @@ __device__ __noinline__ void book_cancel(Send send, int agent, int id, int price
   BookOrd o;
   if (where == 1) {
     o = sd.top[idx];
-    arr_remove(sd.top, *sd.ns, idx);
+    arr_remove(sd.top, sd.tseq, *sd.ns, idx);
     *sd.ns -= 1;
     side_refill(sd);
   } else {
     o = sd.deep[idx];
-    arr_remove(sd.deep, *sd.nd, idx);
+    arr_remove(sd.deep, sd.dseq, *sd.nd, idx);
     *sd.nd -= 1;
   }
   send(agent, pay_order(ABIDES_MSG_ORDER_CANCELLED, 0, o.id, o.price, o.qty, is_buy, -1));
+}
+
+// OrderBook.handleMarketOrder (:160-188): one fresh limit order per opposite level until the quantity is
+// covered.  Each child consumes exactly the level it was sized from, so walking the live book level by
+// level is equivalent to the reference's snapshot walk; an uncovered remainder is dropped.
+template <typename Send>
+__device__ __noinline__ void book_handle_market(Send send, int agent, int qty, bool is_buy) {
+  Hot& h = SM->st.hot;
+  if (qty <= 0) return;
+  int rem = qty;
+  for (;;) {
+    int p, v;
+    side_inside(book_side(!is_buy), p, v);
+    if (p < 0) break;
+    int q = rem <= v ? rem : v;
+    int id = (int)h.next_order_id++;
+    book_handle_limit(send, agent, id, p, q, is_buy);
+    if (rem <= v) break;
+    rem -= v;
+  }
+}
+// OrderBook.modifyOrder (:350-373), including the reference's index-0 overwrite (:359)
+template <typename Send>
+__device__ __noinline__ void book_modify(Send send, int agent, int id, int price, int new_qty, bool is_buy) {
+  Hot& h = SM->st.hot;
+  Side sd = book_side(is_buy);
+  int idx = 0;
+  int where = side_find(sd, price, id, idx);
+  if (where == 0) return;
+  int oseq = where == 1 ? sd.tseq[idx] : sd.dseq[idx];
+  // first entry of that price level = number of entries with a strictly better price
+  int ns = *sd.ns, nd = *sd.nd;
+  int better = 0;
+  __syncwarp();
+  for (int j = LANE; j < ns; j += 32) { int pp = sd.top[j].price; better += (is_buy ? pp > price : pp < price) ? 1 : 0; }
+  for (int j = LANE; j < nd; j += 32) { int pp = sd.deep[j].price; better += (is_buy ? pp > price : pp < price) ? 1 : 0; }
+  better = warp_sum_i(better);
+  BookOrd no; no.price = price; no.qty = new_qty; no.id = id; no.agent = agent;
+  __syncwarp();
+  if (LANE == 0) {
+    if (better < ns) { sd.top[better] = no; sd.tseq[better] = oseq; }
+    else { sd.deep[nd - 1 - (better - ns)] = no; sd.dseq[nd - 1 - (better - ns)] = oseq; }
+  }
+  __syncwarp();
+  if (h.hist_B - oseq <= SM->run.cfg.stream_history)       // one notification per history bucket holding the id
+    send(agent, pay_order(ABIDES_MSG_ORDER_MODIFIED, 0, id, price, new_qty, is_buy, -1));
+}
+__device__ __noinline__ int side_levels(const Side& sd) {                      // number of distinct prices
+  int ns = *sd.ns, nd = *sd.nd, c = 0;
+  __syncwarp();
+  for (int j = LANE; j < ns + nd; j += 32) {
+    int p = j < ns ? sd.top[j].price : sd.deep[nd - 1 - (j - ns)].price;
+    int q = j == 0 ? p - 1 : (j - 1 < ns ? sd.top[j - 1].price : sd.deep[nd - 1 - (j - 1 - ns)].price);
+    c += (j == 0 || p != q) ? 1 : 0;
+  }
+  return warp_sum_i(c);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -803,7 +948,9 @@ __device__ __noinline__ void ta_place_limit(int a, long long qty, bool is_buy, l
   int init_cap = ty.klass == ABIDES_ADAPTIVE_MM ? (int)(2 * ty.num_ticks + 8) : (ty.klass == ABIDES_MOMENTUM ? 16 : 4);
   ord_reserve(A, init_cap);
   if (h.status) return;
+  __syncwarp();
   if (LANE == 0) SM->run.arena[A.ord_off + A.ord_cnt] = oo;
+  __syncwarp();
   A.ord_cnt++;
   agent_send(a, pay_order(ABIDES_MSG_LIMIT_ORDER, a, id, (int)price, (int)qty, is_buy, -1));
   if (ty.log_orders && id == 0) h.next_order_id++;
@@ -1204,14 +1351,24 @@ __device__ __noinline__ void exchange_receive(const EvPay& m) {
       break;
     }
     case ABIDES_MSG_QUERY_TRANSACTED_VOLUME: {
-      h.status = ABIDES_ESTATE;          // transacted-volume history: not yet on device
+      long long lookback = ((long long)(unsigned)m.w[2]) | ((long long)m.w[3] << 32);
+      long long vol = book_transacted_volume(h.now, lookback);
+      EvPay r = pay_zero((ABIDES_MSG_QUERY_TRANSACTED_VOLUME | ABIDES_MSG_REPLY) | cflag);
+      r.w[2] = (int)(unsigned)(vol & 0xffffffffll); r.w[3] = (int)(vol >> 32);
+      send(sender, r);
       break;
     }
     case ABIDES_MSG_LIMIT_ORDER:
       book_handle_limit(send, sender, oid, m.w[3], m.w[4], pay_is_buy(m));
       break;
+    case ABIDES_MSG_MARKET_ORDER:
+      book_handle_market(send, sender, m.w[4], pay_is_buy(m));
+      break;
     case ABIDES_MSG_CANCEL_ORDER:
       book_cancel(send, sender, oid, m.w[3], pay_is_buy(m));
+      break;
+    case ABIDES_MSG_MODIFY_ORDER:
+      book_modify(send, sender, oid, m.w[3], m.w[5], pay_is_buy(m));
       break;
     default: break;
   }
@@ -1425,6 +1582,9 @@ __global__ void __launch_bounds__(32) sim_kernel(DevBatch db, long long until_ti
     r.far_pay = db.far_pay + (size_t)inst * db.far_cap;
     r.arena = db.arena + (size_t)inst * db.arena_cap;
     r.deep = db.deep_book + (size_t)inst * 2 * db.deep_cap;
+    r.deep_seq = db.deep_seq + (size_t)inst * 2 * db.deep_cap;
+    r.txn_log = db.txn_log + (size_t)inst * TXN_CAP;
+    r.unrolled = db.unrolled + (size_t)inst * UNR_CAP;
     r.trace = db.trace_cap > 0 ? db.trace + (size_t)inst * db.trace_cap : nullptr;
     r.aoff = db.cfg[inst].agent_offset; r.inst = inst; r.n_agents = db.cfg[inst].n_agents; r.cur_agent = -1;
   }
@@ -1484,6 +1644,77 @@ __global__ void __launch_bounds__(32) sim_kernel(DevBatch db, long long until_ti
     int4* dst = reinterpret_cast<int4*>(G);
     const int4* src = reinterpret_cast<const int4*>(S);
     for (int i = lane; i < (int)(sizeof(InstShared) / 16); i += 32) dst[i] = src[i];
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// K2 parity harness: replay recorded order tapes into the book, one warp per book
+// ----------------------------------------------------------------------------------------------
+struct ReplaySend {
+  __device__ void operator()(int rcpt, const EvPay& p) const {
+    Run& r = SM->run;
+    int k = r.rp_counts[r.rp_op];
+    __syncwarp();
+    if (LANE == 0) {
+      if (k < r.rp_max) {
+        abides_book_event e;
+        e.op_index = r.rp_op - r.rp_base; e.kind = pay_code(p); e.agent = rcpt; e.is_buy = pay_is_buy(p) ? 1 : 0;
+        e.order_id = p.w[2]; e.price = p.w[3]; e.qty = p.w[4]; e.fill_price = p.w[5];
+        r.rp_events[(size_t)r.rp_op * r.rp_max + k] = e;
+      }
+      r.rp_counts[r.rp_op] = k + 1;
+    }
+    __syncwarp();
+  }
+};
+
+__global__ void __launch_bounds__(32) replay_kernel(int n_books, const long long* op_offset, const abides_book_op* ops,
+                                                    int stream_history, int max_events, abides_book_event* events,
+                                                    int* counts, abides_book_state* states, BookOrd* deep, int* deep_seq,
+                                                    int deep_cap) {
+  int b = blockIdx.x, lane = threadIdx.x;
+  if (b >= n_books) return;
+  for (int i = lane; i < (int)(sizeof(Smem) / 4); i += 32) reinterpret_cast<unsigned*>(SM)[i] = 0;
+  __syncwarp();
+  if (lane == 0) {
+    Run& r = SM->run;
+    r.db.deep_cap = deep_cap;
+    r.cfg.stream_history = stream_history;
+    r.deep = deep + (size_t)b * 2 * deep_cap;
+    r.deep_seq = deep_seq + (size_t)b * 2 * deep_cap;
+    r.txn_log = nullptr;
+    r.rp_events = events; r.rp_counts = counts; r.rp_max = max_events; r.rp_base = (int)op_offset[b];
+    SM->st.hot.next_order_id = 1 << 30;          // ids of market-order children: outside the tape's id space
+  }
+  __syncwarp();
+  Hot& h = SM->st.hot;
+  ReplaySend send;
+  for (long long i = op_offset[b]; i < op_offset[b + 1]; i++) {
+    abides_book_op op = ops[i];
+    __syncwarp();
+    if (lane == 0) { SM->run.rp_op = (int)i; counts[i] = 0; }
+    __syncwarp();
+    h.now = op.time;
+    bool buy = op.is_buy != 0;
+    switch (op.kind) {
+      case ABIDES_MSG_LIMIT_ORDER: book_handle_limit(send, op.agent, (int)op.order_id, (int)op.price, (int)op.qty, buy); break;
+      case ABIDES_MSG_MARKET_ORDER: book_handle_market(send, op.agent, (int)op.qty, buy); break;
+      case ABIDES_MSG_CANCEL_ORDER: book_cancel(send, op.agent, (int)op.order_id, (int)op.price, buy); break;
+      case ABIDES_MSG_MODIFY_ORDER: book_modify(send, op.agent, (int)op.order_id, (int)op.price, (int)op.new_qty, buy); break;
+      default: break;
+    }
+    int bp, bv, ap, av;
+    side_inside(book_side(true), bp, bv);
+    side_inside(book_side(false), ap, av);
+    int nbl = side_levels(book_side(true)), nal = side_levels(book_side(false));
+    if (lane == 0) {
+      abides_book_state st;
+      st.bid = bp; st.bid_vol = bv; st.ask = ap; st.ask_vol = av;
+      st.last_trade = h.has_last_trade ? h.last_trade : -1;
+      st.n_bid_levels = nbl; st.n_ask_levels = nal;
+      states[i] = st;
+    }
+    __syncwarp();
   }
 }
 
@@ -1688,6 +1919,9 @@ int abides_load(abides_handle* h, const abides_batch* b) {
     if ((rc = dev_alloc(h, &d.far_pay, (size_t)ni * d.far_cap))) return rc;
     if ((rc = dev_alloc(h, &d.arena, (size_t)ni * d.arena_cap))) return rc;
     if ((rc = dev_alloc(h, &d.deep_book, (size_t)ni * 2 * d.deep_cap))) return rc;
+    if ((rc = dev_alloc(h, &d.deep_seq, (size_t)ni * 2 * d.deep_cap))) return rc;
+    if ((rc = dev_alloc(h, &d.txn_log, (size_t)ni * TXN_CAP))) return rc;
+    if ((rc = dev_alloc(h, &d.unrolled, (size_t)ni * UNR_CAP))) return rc;
     if ((rc = dev_alloc(h, &d.mom_ring, (size_t)(n_mom > 0 ? n_mom : 1) * MOM_RING))) return rc;
     if ((rc = dev_alloc(h, &d.trace, (size_t)ni * (d.trace_cap > 0 ? d.trace_cap : 0)))) return rc;
     if ((rc = dev_alloc(h, &d.res, (size_t)ni))) return rc;
@@ -1792,9 +2026,52 @@ int abides_read_trace(abides_handle* h, int32_t instance, abides_trace_rec* out,
 int abides_replay_book(abides_handle* h, int32_t n_books, const int64_t* op_offset, const abides_book_op* ops,
                        int32_t stream_history, int32_t max_events_per_op, abides_book_event* events_out,
                        int32_t* event_count_out, abides_book_state* states_out) {
-  (void)h; (void)n_books; (void)op_offset; (void)ops; (void)stream_history; (void)max_events_per_op;
-  (void)events_out; (void)event_count_out; (void)states_out;
-  return fail(ABIDES_ESTATE, "abides_replay_book: not built yet");
+  if (!h || n_books <= 0 || !op_offset || !ops || !events_out || !event_count_out || !states_out || max_events_per_op <= 0)
+    return fail(ABIDES_EINVAL, "abides_replay_book: bad argument");
+  CK(cudaSetDevice(h->device));
+  long long n_ops = op_offset[n_books];
+  if (n_ops <= 0) return 0;
+  long long longest = 0;
+  for (int b = 0; b < n_books; b++) {
+    long long len = op_offset[b + 1] - op_offset[b];
+    if (len < 0) return fail(ABIDES_EINVAL, "abides_replay_book: op_offset must be non-decreasing");
+    if (len > longest) longest = len;
+  }
+  for (long long i = 0; i < n_ops; i++)
+    if (ops[i].price < 0 || ops[i].price > 2000000000ll || ops[i].qty > 2000000000ll || ops[i].order_id >= (1ll << 30))
+      return fail(ABIDES_EINVAL, "abides_replay_book: price / quantity / order id outside the device's int32 range");
+  int deep_cap = (int)(longest + 64);
+  long long* d_off = nullptr; abides_book_op* d_ops = nullptr; abides_book_event* d_ev = nullptr; int* d_cnt = nullptr;
+  abides_book_state* d_st = nullptr; BookOrd* d_deep = nullptr; int* d_seq = nullptr;
+  int rc = 0;
+  auto cleanup = [&]() { cudaFree(d_off); cudaFree(d_ops); cudaFree(d_ev); cudaFree(d_cnt); cudaFree(d_st); cudaFree(d_deep); cudaFree(d_seq); };
+#define RCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return fail(ABIDES_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
+  RCK(cudaMalloc(&d_off, sizeof(long long) * (n_books + 1)));
+  RCK(cudaMalloc(&d_ops, sizeof(abides_book_op) * n_ops));
+  RCK(cudaMalloc(&d_ev, sizeof(abides_book_event) * n_ops * max_events_per_op));
+  RCK(cudaMalloc(&d_cnt, sizeof(int) * n_ops));
+  RCK(cudaMalloc(&d_st, sizeof(abides_book_state) * n_ops));
+  RCK(cudaMalloc(&d_deep, sizeof(BookOrd) * (size_t)n_books * 2 * deep_cap));
+  RCK(cudaMalloc(&d_seq, sizeof(int) * (size_t)n_books * 2 * deep_cap));
+  RCK(cudaMemcpyAsync(d_off, op_offset, sizeof(long long) * (n_books + 1), cudaMemcpyHostToDevice, h->stream));
+  RCK(cudaMemcpyAsync(d_ops, ops, sizeof(abides_book_op) * n_ops, cudaMemcpyHostToDevice, h->stream));
+  RCK(cudaMemsetAsync(d_ev, 0, sizeof(abides_book_event) * n_ops * max_events_per_op, h->stream));
+  RCK(cudaFuncSetAttribute(replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+  RCK(cudaEventRecord(h->ev0, h->stream));
+  replay_kernel<<<n_books, 32, sizeof(Smem), h->stream>>>(n_books, d_off, d_ops, stream_history, max_events_per_op, d_ev, d_cnt,
+                                                         d_st, d_deep, d_seq, deep_cap);
+  RCK(cudaGetLastError());
+  RCK(cudaEventRecord(h->ev1, h->stream));
+  RCK(cudaMemcpyAsync(events_out, d_ev, sizeof(abides_book_event) * n_ops * max_events_per_op, cudaMemcpyDeviceToHost, h->stream));
+  RCK(cudaMemcpyAsync(event_count_out, d_cnt, sizeof(int) * n_ops, cudaMemcpyDeviceToHost, h->stream));
+  RCK(cudaMemcpyAsync(states_out, d_st, sizeof(abides_book_state) * n_ops, cudaMemcpyDeviceToHost, h->stream));
+  RCK(cudaStreamSynchronize(h->stream));
+  RCK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+#undef RCK
+  h->last_launches = 1;
+  cleanup();
+  (void)rc;
+  return 0;
 }
 
 }  // extern "C"

@@ -107,3 +107,39 @@ AGENT_RESULT_DTYPE = np.dtype([("cash", "<i8"), ("holdings", "<i8"), ("marked_to
 assert INSTANCE_RESULT_DTYPE.itemsize == C.sizeof(_abi.InstanceResult)
 assert AGENT_RESULT_DTYPE.itemsize == C.sizeof(_abi.AgentResult)
 assert TRACE_DTYPE.itemsize == C.sizeof(_abi.TraceRec)
+
+
+def make_book_ops(rows):
+    """int64[n,8] rows (kind, agent, order_id, price, qty, is_buy, new_qty, time) -> ctypes abides_book_op array."""
+    n = len(rows)
+    ops = (_abi.BookOp * max(1, n))()
+    for i, r in enumerate(rows):
+        o = ops[i]
+        o.kind, o.agent, o.order_id, o.price, o.qty, o.is_buy, o.new_qty, o.time = [int(x) for x in r]
+    return ops
+
+
+def replay_book(engine, op_offset, rows, stream_history, max_events_per_op=64):
+    """util/OrderBook.py replay on the device (abides_replay_book): returns (events int64[m,8], counts, states int64[n,7])."""
+    n_books = len(op_offset) - 1
+    n = int(op_offset[-1])
+    ops = make_book_ops(rows)
+    ev = (_abi.BookEvent * max(1, n * max_events_per_op))()
+    cnt = np.zeros(max(1, n), np.int32)
+    st = (_abi.BookState * max(1, n))()
+    off = np.ascontiguousarray(op_offset, np.int64)
+    engine._ck(engine._L.abides_replay_book(engine._h, n_books, off.ctypes.data_as(C.POINTER(C.c_int64)), ops,
+                                            int(stream_history), int(max_events_per_op), ev,
+                                            cnt.ctypes.data_as(C.POINTER(C.c_int32)), st), "abides_replay_book")
+    return unpack_replay(ev, cnt[:n], st, n, max_events_per_op)
+
+
+def unpack_replay(ev, cnt, st, n, max_events_per_op):
+    events = []
+    for i in range(n):
+        for k in range(min(int(cnt[i]), max_events_per_op)):
+            e = ev[i * max_events_per_op + k]
+            events.append((i, e.kind, e.agent, e.is_buy, e.order_id, e.price, e.qty, e.fill_price))
+    states = np.array([(s.bid, s.bid_vol, s.ask, s.ask_vol, s.last_trade, s.n_bid_levels, s.n_ask_levels)
+                       for s in st[:n]], np.int64).reshape(-1, 7)
+    return np.array(events, np.int64).reshape(-1, 8), np.asarray(cnt), states

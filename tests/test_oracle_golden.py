@@ -1,32 +1,85 @@
 """CPU: the C oracle (oracle/abides_oracle.c) against golden vectors produced by the unmodified
-reference (tests/golden/gen_golden.py).  Bit-exact: trace, ttl_messages, finals, fundamental log."""
+reference (tests/golden/gen_golden.py).  Bit-exact: dispatch trace, ttl_messages, per-agent finals,
+fundamental log.  The instance inputs come from this repo's own config builders and must hash to the
+inputs the reference's builders produced (spec_sha256)."""
+import hashlib
+import sys
+import os
+
 import numpy as np
 import pytest
 
 import oracle
-from abides_b200 import lowering
-from parity_util import load_golden, load_spec, first_trace_mismatch, describe_mismatch
+from abides_b200 import lowering, runtime
+from parity_util import load_golden, load_spec, first_trace_mismatch, describe_mismatch, GOLDEN
+
+sys.path.insert(0, GOLDEN)
+from gen_golden import spec_digest  # noqa: E402
+
+CASES = {
+    "zi100_s123456789": ("sparse_zi_100", ["-s", "123456789"]),
+    "zi1000_s123456789": ("sparse_zi_1000", ["-s", "123456789"]),
+    "rmsc03_s1234_1000": ("rmsc03", ["-t", "ABM", "-d", "20200603", "-s", "1234", "--end-time", "10:00:00"]),
+}
 
 
-@pytest.mark.parametrize("name", ["zi100_s123456789"])
-def test_oracle_matches_reference_run(name):
-    g, meta = load_golden(name)
-    hb = lowering.HostBatch([load_spec(name)])
-    r = oracle.run_instance(hb, 0, trace_cap=meta["delivered"] + 16, flog_cap=len(g["f_time"]) + 16)
+def build_case(name):
+    cfg, args = CASES[name]
+    return runtime.build_instances(cfg, [args])[0][0]
+
+
+def check_against_golden(r, g, meta, trace=None):
     assert r["status"] == 0
     assert r["ttl_messages"] == meta["ttl_messages"]
     assert r["delivered"] == meta["delivered"]
-    i = first_trace_mismatch(r["trace"], g["trace"])
-    assert i < 0, describe_mismatch(r["trace"], g["trace"], i, ("oracle", "reference"))
+    if trace is not None:
+        if "trace" in g.files:
+            i = first_trace_mismatch(trace, g["trace"])
+            assert i < 0, describe_mismatch(trace, g["trace"], i, ("got", "reference"))
+        assert hashlib.sha256(np.ascontiguousarray(trace, np.int64).tobytes()).hexdigest() == meta["trace_sha256"]
     for k in ("cash", "holdings", "mtm"):
         assert np.array_equal(r[k], g[k]), k
     fv, gfv = r["final_valuation"], g["final_valuation"]
     assert np.array_equal(np.isnan(fv), np.isnan(gfv))
+    # FINAL_VALUATION is a float for Value/Noise agents: north-star tolerance 1e-9 relative (it is in fact exact)
+    assert np.allclose(fv[~np.isnan(fv)], gfv[~np.isnan(gfv)], rtol=1e-9, atol=0)
     assert np.array_equal(fv[~np.isnan(fv)], gfv[~np.isnan(gfv)])
-    assert np.array_equal(r["f_time"], g["f_time"])
-    # oracle floats: fundamental values are integral after int(round(.)); 1e-9 relative bound stated by the north star
-    assert np.allclose(r["f_value"], g["f_value"], rtol=1e-9, atol=0)
-    assert np.array_equal(r["f_value"], g["f_value"])
     assert r["last_trade"] == meta["last_trade"]
     assert r["final_time"] == meta["final_time"]
     assert r["slowest_agent_finish_time"] == meta["slowest_agent_finish_time"]
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_builders_reproduce_reference_inputs(name):
+    _, meta = load_golden(name)
+    assert spec_digest(build_case(name)) == meta["spec_sha256"]
+
+
+def test_stored_spec_equals_built_spec():
+    assert spec_digest(load_spec("zi100_s123456789")) == spec_digest(build_case("zi100_s123456789"))
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_oracle_matches_reference_run(name):
+    g, meta = load_golden(name)
+    hb = lowering.HostBatch([build_case(name)])
+    r = oracle.run_instance(hb, 0, trace_cap=meta["delivered"] + 16, flog_cap=len(g["f_time"]) + 16)
+    check_against_golden(r, g, meta, r["trace"])
+    assert np.array_equal(r["f_time"], g["f_time"])
+    assert np.allclose(r["f_value"], g["f_value"], rtol=1e-9, atol=0)    # oracle floats (integral after round)
+    assert np.array_equal(r["f_value"], g["f_value"])
+
+
+def test_mean_ending_value_by_type_matches_reference_stdout():
+    name = "zi100_s123456789"
+    g, meta = load_golden(name)
+    spec = build_case(name)
+    r = oracle.run_instance(lowering.HostBatch([spec]), 0)
+    sums, counts = {}, {}
+    start = spec.types[spec.agent_type[1]]["starting_cash"]
+    for a in range(1, spec.n_agents):
+        t = spec.agent_type_names[a]
+        sums[t] = sums.get(t, 0) + int(r["mtm"][a]) - start
+        counts[t] = counts.get(t, 0) + 1
+    means = {t: int(round(sums[t] / counts[t])) for t in sums}       # Kernel.py:318-322
+    assert means == meta["means"]
