@@ -19,7 +19,7 @@ NVCC_FLAGS = [
 def build_cuda(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    deps = srcs + [os.path.join(INCLUDE, h) for h in ("abides_b200.h", "abides_dd_math.h")]
+    deps = srcs + [os.path.join(INCLUDE, h) for h in ("abides_b200.h", "abides_dd_math.h", "abides_math_tables.h")]
     if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in deps):
         return OUT
     flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]

@@ -94,7 +94,7 @@ ABM_HD uint64_t abm_double_to_bits(double d) { uint64_t u; memcpy(&u, &d, sizeof
 ABM_HD double abm_pow2i(int k) { return abm_bits_to_double((uint64_t)(k + 1023) << 52); }
 
 /* e^a - 1 for |a| <= 2^-10, Taylor to a^10/10! (truncation < 2^-115 relative). */
-ABM_HD_BIG abm_dd abm_expm1_tiny(abm_dd a) {
+ABM_HD_BIG abm_dd abm_slow_expm1_tiny(abm_dd a) {
   abm_dd p = abm_mk(0x1.27e4fb7789f5cp-22, 0x1.cbbc05b4fa99ap-76);                       /* 1/10! */
   p = abm_dd_add(abm_dd_mul(p, a), abm_mk(0x1.71de3a556c734p-19, -0x1.c154f8ddc6c00p-73)); /* 1/9! */
   p = abm_dd_add(abm_dd_mul(p, a), abm_mk(0x1.a01a01a01a01ap-16, 0x1.a01a01a01a01ap-76));  /* 1/8! */
@@ -110,12 +110,12 @@ ABM_HD_BIG abm_dd abm_expm1_tiny(abm_dd a) {
 
 /* exp of a double-double argument, |a| < 700, as an UNSCALED double-double m and an
  * exponent k with result = m * 2^k, m in [~0.7, ~1.42]. */
-ABM_HD_BIG abm_dd abm_exp_dd_k(abm_dd a, int* kout) {
+ABM_HD_BIG abm_dd abm_slow_exp_dd_k(abm_dd a, int* kout) {
   const abm_dd LN2 = abm_mk(0x1.62e42fefa39efp-1, 0x1.abc9e3b39803fp-56);
   double kf = rint(a.hi * 0x1.71547652b82fep+0);
   abm_dd r = abm_dd_add(a, abm_dd_neg(abm_dd_mul_d(LN2, kf)));
   r = abm_dd_scale2(r, 0x1p-9);                               /* |r| <= ln2/2 / 512 < 2^-10 */
-  abm_dd p = abm_expm1_tiny(r);
+  abm_dd p = abm_slow_expm1_tiny(r);
   for (int i = 0; i < 9; ++i)                                 /* (1+p)^2 - 1 = 2p + p^2 */
     p = abm_dd_add(abm_dd_scale2(p, 2.0), abm_dd_mul(p, p));
   *kout = (int)kf;
@@ -131,16 +131,16 @@ ABM_HD double abm_scale_by_pow2(double m, int k) {
   return m * abm_pow2i(k);
 }
 
-ABM_HD_BIG double abm_exp(double x) {
+ABM_HD_BIG double abm_slow_exp(double x) {
   if (x == 0.0) return 1.0;
   if (x > 709.0) return INFINITY;
   if (x < -708.0) return 0.0;
-  int k; abm_dd m = abm_exp_dd_k(abm_mk(x, 0.0), &k);
+  int k; abm_dd m = abm_slow_exp_dd_k(abm_mk(x, 0.0), &k);
   return abm_scale_by_pow2(m.hi, k);
 }
 
 /* log(x) as a double-double; x > 0, normal. */
-ABM_HD_BIG abm_dd abm_log_dd(double x) {
+ABM_HD_BIG abm_dd abm_slow_log_dd(double x) {
   const abm_dd LN2 = abm_mk(0x1.62e42fefa39efp-1, 0x1.abc9e3b39803fp-56);
   uint64_t bits = abm_double_to_bits(x);
   int e = (int)((bits >> 52) & 0x7ff) - 1023;
@@ -170,7 +170,7 @@ ABM_HD_BIG abm_dd abm_log_dd(double x) {
     q = q * z + 1.0 / 13.0; q = q * z + 1.0 / 11.0; q = q * z + 1.0 / 9.0;  q = q * z + 1.0 / 7.0;
     q = q * z + 1.0 / 5.0;  q = q * z + 1.0 / 3.0;  q = q * z + 1.0;
     double y0 = 2.0 * sh * q;
-    int k; abm_dd em = abm_exp_dd_k(abm_mk(-y0, 0.0), &k);   /* |y0| <= 0.35 => k == 0 or -1/+1 */
+    int k; abm_dd em = abm_slow_exp_dd_k(abm_mk(-y0, 0.0), &k);   /* |y0| <= 0.35 => k == 0 or -1/+1 */
     em = abm_dd_scale2(em, abm_pow2i(k));
     abm_dd t = abm_dd_add_d(abm_dd_mul_d(em, m), -1.0);
     abm_dd t2h = abm_dd_scale2(abm_dd_mul(t, t), 0.5);
@@ -180,29 +180,124 @@ ABM_HD_BIG abm_dd abm_log_dd(double x) {
   return abm_dd_add(abm_dd_mul_d(LN2, (double)e), lm);
 }
 
-ABM_HD double abm_log(double x) { return abm_log_dd(x).hi; }
+ABM_HD double abm_slow_log(double x) { return abm_slow_log_dd(x).hi; }
 
 /* x ** y for x > 0 (C pow semantics for the finite, positive-base cases the reference hits). */
-ABM_HD_BIG double abm_pow(double x, double y) {
+ABM_HD_BIG double abm_slow_pow(double x, double y) {
   if (y == 0.0 || x == 1.0) return 1.0;
   if (y == 1.0) return x;
-  abm_dd l = abm_log_dd(x);
+  abm_dd l = abm_slow_log_dd(x);
   abm_dd p = abm_dd_mul_d(l, y);
   if (p.hi > 709.0) return INFINITY;
   if (p.hi < -708.0) return 0.0;
-  int k; abm_dd m = abm_exp_dd_k(p, &k);
+  int k; abm_dd m = abm_slow_exp_dd_k(p, &k);
   return abm_scale_by_pow2(m.hi, k);
 }
 
-/* x ** y given a precomputed l = abm_log_dd(x): bit-identical to abm_pow(x, y). */
-ABM_HD_BIG double abm_pow_with_log(abm_dd l, double x, double y) {
+/* x ** y given a precomputed l = abm_slow_log_dd(x): bit-identical to abm_slow_pow(x, y). */
+ABM_HD_BIG double abm_slow_pow_with_log(abm_dd l, double x, double y) {
   if (y == 0.0 || x == 1.0) return 1.0;
   if (y == 1.0) return x;
   abm_dd p = abm_dd_mul_d(l, y);
   if (p.hi > 709.0) return INFINITY;
   if (p.hi < -708.0) return 0.0;
-  int k; abm_dd m = abm_exp_dd_k(p, &k);
+  int k; abm_dd m = abm_slow_exp_dd_k(p, &k);
   return abm_scale_by_pow2(m.hi, k);
+}
+
+
+/* ------------------------------------------------------------------------------------------------
+ * Production versions: table-driven, ~40 flops each, relative error before the final rounding
+ * < 2^-66 (log) / 2^-69 (exp), i.e. the correctly rounded result except when the exact value lies
+ * within ~2^-13 ulp of a rounding boundary.  The abm_slow_* functions above (error < 2^-85) are kept
+ * as the cross-check (tests/test_math.py).  Tables: include/abides_math_tables.h (generated).
+ * ---------------------------------------------------------------------------------------------- */
+#include "abides_math_tables.h"
+
+static const double abm_exp_tab_h[2 * ABM_EXP_N] = { ABM_EXP_TAB_VALUES };
+static const double abm_log_tab_h[3 * ABM_LOG_N] = { ABM_LOG_TAB_VALUES };
+#if defined(__CUDACC__)
+static __device__ __constant__ double abm_exp_tab_d[2 * ABM_EXP_N] = { ABM_EXP_TAB_VALUES };
+static __device__ __constant__ double abm_log_tab_d[3 * ABM_LOG_N] = { ABM_LOG_TAB_VALUES };
+#endif
+#if defined(__CUDA_ARCH__)
+#define ABM_EXP_TAB abm_exp_tab_d
+#define ABM_LOG_TAB abm_log_tab_d
+#else
+#define ABM_EXP_TAB abm_exp_tab_h
+#define ABM_LOG_TAB abm_log_tab_h
+#endif
+
+/* log(x) as a double-double; x > 0, normal. */
+ABM_HD_BIG abm_dd abm_log_dd(double x) {
+  uint64_t bits = abm_double_to_bits(x);
+  int e = (int)((bits >> 52) & 0x7ff) - 1023;
+  double z = abm_bits_to_double((bits & 0x000fffffffffffffULL) | 0x3ff0000000000000ULL);  /* [1,2) */
+  if (z >= 1.5) { z *= 0.5; e += 1; }                                                   /* [0.75,1.5) */
+  int i = z < 1.0 ? (int)((z - 0.75) * 256.0) : 64 + (int)((z - 1.0) * 128.0);
+  double invc = ABM_LOG_TAB[3 * i], lch = ABM_LOG_TAB[3 * i + 1], lcl = ABM_LOG_TAB[3 * i + 2];
+  /* r = z * invc - 1 exactly as rh + rl (|r| <= 2^-7; r = z - 1 exactly in the two cells touching 1) */
+  double ph = z * invc, pl = ABM_FMA(z, invc, -ph);
+  abm_dd r = abm_fast_two_sum(ph - 1.0, pl);
+  double h = r.hi;
+  /* log1p(r) = r - r^2/2 + h^3 (1/3 - h/4 + ... + h^8/11) */
+  double sqh = h * h, sql = ABM_FMA(h, h, -sqh);
+  double t2h = -0.5 * sqh, t2l = -0.5 * sql - h * r.lo;
+  double q = 1.0 / 11.0;
+  q = ABM_FMA(q, h, -1.0 / 10.0); q = ABM_FMA(q, h, 1.0 / 9.0); q = ABM_FMA(q, h, -1.0 / 8.0);
+  q = ABM_FMA(q, h, 1.0 / 7.0);   q = ABM_FMA(q, h, -1.0 / 6.0); q = ABM_FMA(q, h, 1.0 / 5.0);
+  q = ABM_FMA(q, h, -1.0 / 4.0);  q = ABM_FMA(q, h, 1.0 / 3.0);
+  q = q * (sqh * h);
+  abm_dd s1 = abm_two_sum(lch, h);
+  abm_dd s2 = abm_two_sum(s1.hi, t2h);
+  double lo = (s1.lo + s2.lo) + (((lcl + r.lo) + t2l) + q);
+  abm_dd res = abm_fast_two_sum(s2.hi, lo);
+  if (e != 0) {
+    double eh = (double)e * ABM_LN2_HI42, el = (double)e * ABM_LN2_LO42;      /* eh exact */
+    abm_dd u = abm_two_sum(eh, res.hi);
+    res = abm_fast_two_sum(u.hi, u.lo + (res.lo + el));
+  }
+  return res;
+}
+
+ABM_HD double abm_log(double x) { return abm_log_dd(x).hi; }
+
+/* exp(ah + al), |ah| < 709, |al| <~ ulp(ah) */
+ABM_HD_BIG double abm_exp_dd(double ah, double al) {
+  double kf = rint(ah * ABM_128_LN2);
+  abm_dd rr = abm_two_sum(ABM_FMA(-kf, ABM_LN2_128_HI, ah) /* exact */, ABM_FMA(-kf, ABM_LN2_128_LO, al));
+  double r = rr.hi, rl = rr.lo;                                /* |r| <= ln2/256, |rl| <= ulp(r)/2 */
+  int k = (int)kf, j = k & (ABM_EXP_N - 1), e = k >> 7;
+  double th = ABM_EXP_TAB[2 * j], tl = ABM_EXP_TAB[2 * j + 1];
+  double p = ABM_FMA(r, 1.0 / 720.0, 1.0 / 120.0);
+  p = ABM_FMA(r, p, 1.0 / 24.0); p = ABM_FMA(r, p, 1.0 / 6.0); p = ABM_FMA(r, p, 0.5);
+  double q = ABM_FMA(r * r, p, rl);                            /* expm1(r + rl) - r */
+  double sh = th * r, sl = ABM_FMA(th, r, -sh);
+  double lo = sl + ABM_FMA(th, q, tl);
+  abm_dd u = abm_fast_two_sum(th, sh);
+  double m = u.hi + (u.lo + lo);
+  return abm_scale_by_pow2(m, e);
+}
+
+ABM_HD double abm_exp(double x) {
+  if (x > 709.0) return INFINITY;
+  if (x < -708.0) return 0.0;
+  return abm_exp_dd(x, 0.0);
+}
+
+/* x ** y given l = abm_log_dd(x), x > 0 (C pow semantics for the finite cases the reference hits). */
+ABM_HD double abm_pow_with_log(abm_dd l, double x, double y) {
+  if (y == 0.0 || x == 1.0) return 1.0;
+  if (y == 1.0) return x;
+  double ph = l.hi * y, pl = ABM_FMA(l.hi, y, -ph) + l.lo * y;
+  if (ph > 709.0) return INFINITY;
+  if (ph < -708.0) return 0.0;
+  return abm_exp_dd(ph, pl);
+}
+ABM_HD double abm_pow(double x, double y) {
+  if (y == 0.0 || x == 1.0) return 1.0;
+  if (y == 1.0) return x;
+  return abm_pow_with_log(abm_log_dd(x), x, y);
 }
 
 /* x ** 3 (model/LatencyModel.py:138): the exact cube in double-double, rounded once. */

@@ -15,7 +15,7 @@ _lib = None
 
 def build(force=False):
     src = os.path.join(_DIR, "abides_oracle.c")
-    hdrs = [os.path.join(_DIR, "..", "include", h) for h in ("abides_b200.h", "abides_dd_math.h")]
+    hdrs = [os.path.join(_DIR, "..", "include", h) for h in ("abides_b200.h", "abides_dd_math.h", "abides_math_tables.h")]
     stale = (not os.path.exists(LIB_PATH)) or any(
         os.path.exists(p) and os.path.getmtime(p) > os.path.getmtime(LIB_PATH) for p in [src] + hdrs)
     if force or stale:
@@ -50,6 +50,9 @@ def lib():
         L.oracle_rng_probe.restype = None
         L.oracle_math_probe.argtypes = [C.c_int, C.c_double, C.c_double]
         L.oracle_math_probe.restype = C.c_double
+        L.oracle_math_probe_n.argtypes = [C.c_int, C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                          C.POINTER(C.c_double)]
+        L.oracle_math_probe_n.restype = None
         _lib = L
     return _lib
 
@@ -73,6 +76,16 @@ def results_to_dict(hb, inst, res, ares):
     d["mtm"] = np.array([ares[o + a].marked_to_market for a in range(n)], np.int64)
     d["final_valuation"] = np.array([ares[o + a].final_valuation for a in range(n)], np.float64)
     return d
+
+
+def math_probe(what, x, y=None):
+    """Vector probe of include/abides_dd_math.h: what = 0 log, 1 exp, 2 pow; +10 = abm_slow_* versions."""
+    x = np.ascontiguousarray(x, np.float64)
+    y = np.ascontiguousarray(np.zeros_like(x) if y is None else y, np.float64)
+    out = np.empty_like(x)
+    dp = C.POINTER(C.c_double)
+    lib().oracle_math_probe_n(int(what), x.size, x.ctypes.data_as(dp), y.ctypes.data_as(dp), out.ctypes.data_as(dp))
+    return out
 
 
 def run_instance(hb, inst=0, trace_cap=0, flog_cap=0):
