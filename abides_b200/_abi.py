@@ -135,11 +135,11 @@ class BookState(C.Structure):
 
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "csrc", "libabides_b200.so")
+LIB_PATH = os.environ.get("ABIDES_B200_LIB") or os.path.join(_PKG_DIR, "csrc", "libabides_b200.so")
 
 EXPORTS = [
     "abides_create", "abides_destroy", "abides_last_error", "abides_version", "abides_load",
-    "abides_reset", "abides_run", "abides_read_results", "abides_read_trace", "abides_last_run_ms", "abides_last_reset_ms",
+    "abides_reset", "abides_run", "abides_read_results", "abides_read_trace", "abides_last_run_ms", "abides_last_reset_ms", "abides_read_profile",
     "abides_replay_book",
 ]
 
@@ -179,6 +179,8 @@ def lib():
     L.abides_last_run_ms.restype = C.c_int
     L.abides_last_reset_ms.argtypes = [H, C.POINTER(C.c_float)]
     L.abides_last_reset_ms.restype = C.c_int
+    L.abides_read_profile.argtypes = [H, C.POINTER(C.c_uint64), C.c_int32]
+    L.abides_read_profile.restype = C.c_int
     L.abides_replay_book.argtypes = [H, C.c_int32, C.POINTER(C.c_int64), C.POINTER(BookOp), C.c_int32,
                                      C.c_int32, C.POINTER(BookEvent), C.POINTER(C.c_int32),
                                      C.POINTER(BookState)]

@@ -7,6 +7,7 @@ _DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_DIR, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_DIR), "include")
 OUT = os.path.join(CSRC, "libabides_b200.so")
+OUT_PROF = os.path.join(CSRC, "libabides_b200_prof.so")     # -DABIDES_PROFILE: per-phase cycle counters (diagnosis only)
 SOURCES = ["engine.cu"]
 
 NVCC_FLAGS = [
@@ -16,18 +17,20 @@ NVCC_FLAGS = [
 ]
 
 
-def build_cuda(force=False, verbose=False):
+def build_cuda(force=False, verbose=False, profile=False):
+    """Compile csrc/engine.cu for sm_100a.  profile=True builds the instrumented variant next to it."""
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
     deps = srcs + [os.path.join(INCLUDE, h) for h in ("abides_b200.h", "abides_dd_math.h", "abides_math_tables.h")]
-    if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in deps):
-        return OUT
-    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
-    cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-I", INCLUDE, "-o", OUT] + srcs
+    out = OUT_PROF if profile else OUT
+    if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
+        return out
+    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + (["-DABIDES_PROFILE"] if profile else [])
+    cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-I", INCLUDE, "-o", out] + srcs
     print(" ".join(cmd), file=sys.stderr)
     subprocess.check_call(cmd)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    build_cuda(force=True, verbose="-v" in sys.argv)
+    build_cuda(force=True, verbose="-v" in sys.argv, profile="--profile" in sys.argv)

@@ -8,15 +8,24 @@
 // the latency models (model/LatencyModel.py:113-145, Kernel.py:378-381) and numpy's legacy
 // MT19937 transforms -- as a single persistent kernel in which every warp owns one instance:
 //
-//   * event queue  : a small "near" tier in shared memory (all events below a moving key limit;
-//                    pop = warp arg-min over <=128 keys) over an unsorted "far" list in HBM that is
-//                    scanned, 32 keys per coalesced load, only when the near tier runs dry;
-//   * order book   : both sides as price-time sorted arrays in shared memory; matching, level
-//                    sums, inserts and cancels are ballot/popc scans and warp-wide shifts;
+//   * event queue  : three tiers ordered by two moving key limits.  "near" (shared memory, every
+//                    event below near_limit; pop = redux arg-min), list A (HBM, events below the
+//                    horizon) and list B (HBM, the rest).  A and B are unsorted append-only lists
+//                    with tombstones, scanned 32 keys per coalesced load only when the tier above
+//                    runs dry: B -> A pulls a few hundred events, A -> near a few dozen, so the
+//                    thousands of long-dated wakeups in B are touched once per few thousand pops;
+//   * order book   : both sides as price-time sorted arrays, the best BOOK_TOP entries per side in
+//                    shared memory, the rest reversed in HBM; matching, level sums, inserts and
+//                    cancels are ballot/popc scans and warp-wide shifts;
 //   * agent state  : one 128-byte record per agent in HBM, moved to/from shared memory with one
-//                    coalesced transaction per dispatch; handler code is warp-uniform;
+//                    coalesced transaction per dispatch (skipped when the same agent is dispatched
+//                    again, e.g. busy re-queues); handler code is warp-uniform;
 //   * RNG          : per-stream MT19937 state in HBM (reference-exact mode, warp-parallel twist)
 //                    or counter-based Philox4x32-10 (throughput mode).
+//
+// The kernel is instruction-fetch / latency bound (profiles/): one warp walks a long serial
+// handler per event, so the code is kept small -- events travel in registers, big bodies are
+// __noinline__ and shared by all call sites, the batch descriptor lives in constant memory.
 //
 // No tensor cores: there is no dense contraction on this path (integer / latency bound).
 #include <cuda_runtime.h>
@@ -37,28 +46,36 @@ namespace {
 
 extern __shared__ __align__(128) unsigned char smem_raw[];
 
-constexpr int NEAR_CAP = 128;
-constexpr int FILL_MAX = 64;
-constexpr int FILL_MIN = 16;
-constexpr int BOOK_TOP = 128;          // orders per side kept in shared memory
+constexpr int NEAR_CAP = 128;           // events in the shared-memory tier
+constexpr int FILL_MAX = 64;            // A -> near pulls at most this many ...
+constexpr int FILL_MIN = 16;            // ... and widens its window when it gets fewer
+constexpr int A_CAP = 4096;             // list A capacity per instance
+constexpr int A_FILL_MAX = 384;         // B -> A pulls
+constexpr int A_FILL_MIN = 96;
+constexpr int A_REBALANCE = 2048;       // live entries in A above which the horizon is pulled in
+constexpr int BOOK_TOP = 128;           // orders per side kept in shared memory
 constexpr int MOM_RING = 64;            // >= 51 prefix sums
 constexpr int TXN_CAP = 1 << 16;        // ring of transaction rows since the last volume query (per instance)
 constexpr int UNR_CAP = 1 << 16;        // ring of de-duplicated rows the volume queries sum over
 constexpr int TRACE_FUNDAMENTAL = 64;   // trace code of an oracle step (time = ts, p0 = value)
+constexpr int SID_AGENT = 4;            // RNG stream id of the agent being dispatched (0..3: ABIDES_STREAM_*)
+constexpr int N_PROF = 16;
 
 struct __align__(16) EvKey { long long t; unsigned long long k2; };   // k2 = rcpt<<33 | wakeup<<32 | uniq
 struct __align__(16) EvPay { int w[8]; };
 struct __align__(16) BookOrd { int price, qty, id, agent; };
 struct __align__(16) OpenOrd { int key, id, price, sqty; };            // sqty > 0 buy, < 0 sell
 struct __align__(16) TxnRow { long long t; int q; int seq; };          // OrderBook.history transaction + bucket of its record
+struct __align__(16) RngState { int pos; unsigned flags; double gauss; };   // flags bit 0: cached gaussian valid
 
 enum : unsigned {
   F_HAS_OPEN = 1u, F_HAS_CLOSE = 2u, F_MKT_CLOSED = 4u, F_HAS_LAST_TRADE = 8u, F_HAS_DAILY_CLOSE = 16u,
-  F_KNOWN_BOOK = 32u, F_TRADING = 64u, F_HAS_PREV_WAKE = 128u, F_HAS_GAUSS = 256u,
+  F_KNOWN_BOOK = 32u, F_TRADING = 64u, F_HAS_PREV_WAKE = 128u,
   F_MM_AWAIT_SPREAD = 512u, F_MM_AWAIT_TV = 1024u, F_HAS_LAST_MID = 2048u, F_HAS_AVG20 = 4096u,
   F_HAS_AVG50 = 8192u, F_STATE_SHIFT = 16u, F_STATE_MASK = 3u << 16
 };
 enum { ST_AWAITING_WAKEUP = 0, ST_INACTIVE = 1, ST_AWAITING_SPREAD = 2, ST_ACTIVE = 3 };
+enum { BID = 0, ASK = 1 };              // book side index; a BUY order rests on BID and matches ASK
 
 struct __align__(128) AgentRec {        // 128 bytes: one coalesced transaction
   long long busy;                       // Kernel.agentCurrentTimes[a]
@@ -68,9 +85,9 @@ struct __align__(128) AgentRec {        // 128 bytes: one coalesced transaction
   int last_trade;
   int bid, bid_vol, ask, ask_vol;       // known_bids[0] / known_asks[0], price -1 = empty
   unsigned flags;
-  int ord_off, ord_cnt, ord_cap;        // open orders: slice of the instance's arena
-  int rng_pos;                          // MT19937 position / Philox word counter
-  double gauss;                         // numpy legacy cached gaussian
+  int ord_off;                          // open orders: slice of the instance's arena
+  unsigned short ord_cnt, ord_cap;
+  RngState rng;                         // MT19937 position / Philox word counter, numpy's cached gaussian
   int size;                             // Noise / Value / Momentum order size
   int type_idx;                         // absolute row in the types table
   union {
@@ -83,36 +100,39 @@ struct __align__(128) AgentRec {        // 128 bytes: one coalesced transaction
 };
 static_assert(sizeof(AgentRec) == 128, "AgentRec must be 128 bytes");
 
-struct RngState { int pos; unsigned flags; double gauss; };
-
 struct Hot {
   long long now, ttl, delivered, n_fills, volume;
   long long exch_busy, exch_cd, exch_cur_time, additional_delay;
   long long or_pt; double or_pv; long long ms_time; double ms_value;
   long long next_order_id;
-  long long near_limit_t; unsigned long long near_limit_k; long long dT;
+  long long lim_t; unsigned long long lim_k;                    // near_limit
+  long long hz_t; unsigned long long hz_k;                      // horizon
+  long long span[2];                                            // adaptive windows: [0] A -> near, [1] B -> A
+  long long sel_t; unsigned long long sel_k;                    // result of choose_limit
   unsigned uniq;
-  int n_near, n_far_total, n_far_live;
-  int n_bids, n_asks, nd_bids, nd_asks, last_trade, has_last_trade;
+  int n_near;
+  int l_total[2], l_live[2];            // list A (0) / B (1): slots used, live entries
+  int n_top[2], n_deep[2];              // book: entries per side in shared memory / in HBM
+  int last_trade, has_last_trade;
   int arena_top, status, n_trace, queue_peak, book_peak_orders, done;
+  int find_idx;                         // result of side_find
   int hist_B, tv_prev_len;              // open history bucket; OrderBook._transacted_volume previous length
   long long log_len, log_mark, unr_len; // transaction rows logged / scanned by the last query / unrolled rows
   RngState rs[ABIDES_EXTRA_STREAMS];
 };
 
-struct __align__(128) InstShared {
-  EvKey nkey[NEAR_CAP];
+struct __align__(128) InstShared {      // persisted per instance between launches (abides_run(until))
+  long long nt[NEAR_CAP];
+  unsigned long long nk[NEAR_CAP];
   EvPay npay[NEAR_CAP];
-  BookOrd bids[BOOK_TOP];
-  BookOrd asks[BOOK_TOP];
-  int bid_seq[BOOK_TOP];                // history bucket in which each resting order was entered
-  int ask_seq[BOOK_TOP];
+  BookOrd top[2][BOOK_TOP];
+  int tseq[2][BOOK_TOP];                // history bucket in which each resting order was entered
   AgentRec ag;
   Hot hot;
 };
 
 struct DevBatch {
-  int n_instances, rng_mode, trace_cap, far_cap, arena_cap, n_types, deep_cap;
+  int n_instances, rng_mode, trace_cap, b_cap, arena_cap, n_types, deep_cap;
   const abides_instance_cfg* cfg;
   const abides_agent_type* types;
   abm_dd* type_log1mk;                  // log(1 - kappa) per type, double-double
@@ -129,8 +149,8 @@ struct DevBatch {
   const double* mt_gauss;
   AgentRec* agents;
   InstShared* state;
-  EvKey* far_keys;
-  EvPay* far_pay;
+  EvKey* a_keys; EvPay* a_pay;          // [n_instances][A_CAP]
+  EvKey* b_keys; EvPay* b_pay;          // [n_instances][b_cap]
   OpenOrd* arena;
   BookOrd* deep_book;                   // [n_instances][2][deep_cap]
   int* deep_seq;                        // [n_instances][2][deep_cap]
@@ -141,54 +161,92 @@ struct DevBatch {
   abides_trace_rec* trace;
   abides_instance_result* res;
   abides_agent_result* ares;
+  unsigned long long* prof;             // [N_PROF] cycle / count accumulators (profiling builds)
 };
 
+__constant__ DevBatch c_db;             // uploaded in-stream before every launch
+
 struct Run {                            // per-launch context, shared memory, not persisted
-  DevBatch db;
   abides_instance_cfg cfg;
-  EvKey* far_keys; EvPay* far_pay; OpenOrd* arena; BookOrd* deep; int* deep_seq; TxnRow* txn_log; TxnRow* unrolled;
+  EvKey* lk[2]; EvPay* lp[2]; int lcap[2];
+  OpenOrd* arena; BookOrd* deep[2]; int* dseq[2]; TxnRow* txn_log; TxnRow* unrolled;
   abides_trace_rec* trace;
+  unsigned* mt0;                        // MT state of this instance's stream 0 (agent 0)
+  const double* lat_to; const double* lat_from;   // this instance's rows
+  AgentRec* agents;
   long long aoff;                       // agent_offset
-  int inst, n_agents;
+  int inst, n_agents, deep_cap;
   int cur_agent;                        // agent whose record sits in st.ag (-1 none)
   int rp_op, rp_max, rp_base;           // order-book replay harness: current op, events per op, first op
   abides_book_event* rp_events; int* rp_counts;
+  unsigned long long prof[N_PROF];
 };
 struct __align__(128) Smem { InstShared st; Run run; };
 #define SM (reinterpret_cast<Smem*>(smem_raw))
+#define ST (SM->st)
+#define HOT (SM->st.hot)
+#define RUN (SM->run)
 #define LANE ((int)threadIdx.x)
+
+#ifdef ABIDES_PROFILE
+#define PROF_T0() long long prof_t0_ = clock64()
+#define PROF_ADD(slot) do { long long c_ = clock64(); RUN.prof[slot] += (unsigned long long)(c_ - prof_t0_); prof_t0_ = c_; } while (0)
+#define PROF_CNT(slot) do { RUN.prof[slot] += 1ull; } while (0)
+#else
+#define PROF_T0() do {} while (0)
+#define PROF_ADD(slot) do {} while (0)
+#define PROF_CNT(slot) do {} while (0)
+#endif
+enum { P_POP = 0, P_REFILL, P_REC, P_EXCH_ORDER, P_EXCH_CANCEL, P_EXCH_QUERY, P_EXCH_OTHER, P_AG_WAKE, P_AG_SPREAD,
+       P_AG_OTHER, P_REQUEUE, P_N_REFILL, P_N_BPULL, P_N_REQUEUE, P_N_RECLOAD, P_TOTAL };
 
 // ----------------------------------------------------------------------------------------------
 // warp helpers
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ long long warp_min_ll(long long v) {
-  for (int o = 16; o; o >>= 1) { long long x = __shfl_xor_sync(FULL, v, o); v = x < v ? x : v; }
-  return v;
+  unsigned hi = (unsigned)((unsigned long long)v >> 32) ^ 0x80000000u;     // order-preserving for signed v
+  unsigned mh = __reduce_min_sync(FULL, hi);
+  unsigned lo = hi == mh ? (unsigned)v : 0xffffffffu;
+  unsigned ml = __reduce_min_sync(FULL, lo);
+  return (long long)(((unsigned long long)(mh ^ 0x80000000u) << 32) | ml);
 }
 __device__ __forceinline__ unsigned long long warp_min_ull(unsigned long long v) {
-  for (int o = 16; o; o >>= 1) { unsigned long long x = __shfl_xor_sync(FULL, v, o); v = x < v ? x : v; }
-  return v;
+  unsigned hi = (unsigned)(v >> 32);
+  unsigned mh = __reduce_min_sync(FULL, hi);
+  unsigned lo = hi == mh ? (unsigned)v : 0xffffffffu;
+  unsigned ml = __reduce_min_sync(FULL, lo);
+  return ((unsigned long long)mh << 32) | ml;
 }
 __device__ __forceinline__ unsigned long long warp_max_ull(unsigned long long v) {
-  for (int o = 16; o; o >>= 1) { unsigned long long x = __shfl_xor_sync(FULL, v, o); v = x > v ? x : v; }
-  return v;
+  unsigned hi = (unsigned)(v >> 32);
+  unsigned mh = __reduce_max_sync(FULL, hi);
+  unsigned lo = hi == mh ? (unsigned)v : 0u;
+  unsigned ml = __reduce_max_sync(FULL, lo);
+  return ((unsigned long long)mh << 32) | ml;
 }
-__device__ __forceinline__ int warp_sum_i(int v) {
-  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-  return v;
-}
+__device__ __forceinline__ int warp_sum_i(int v) { return __reduce_add_sync(FULL, v); }
 __device__ __forceinline__ bool key_less(long long at, unsigned long long ak, long long bt, unsigned long long bk) {
   return at < bt || (at == bt && ak < bk);
 }
 
 // ----------------------------------------------------------------------------------------------
-// RNG: numpy legacy RandomState transforms over MT19937 (HBM-resident state) or Philox4x32-10
+// RNG: numpy legacy RandomState transforms over MT19937 (HBM-resident state) or Philox4x32-10.
+// Streams are named by a small id: 0..3 = the instance's extra streams (state in HOT.rs), SID_AGENT
+// = the stream of the agent record currently in shared memory (state in ST.ag.rng).
 // ----------------------------------------------------------------------------------------------
-struct RngH { unsigned* mt; int* pos; double* gauss; unsigned* flagword; unsigned flagbit; unsigned long long key; };
+__device__ __forceinline__ RngState& rng_state(int sid) {
+  unsigned off = sid == SID_AGENT ? (unsigned)(offsetof(Smem, st) + offsetof(InstShared, ag) + offsetof(AgentRec, rng))
+                                  : (unsigned)(offsetof(Smem, st) + offsetof(InstShared, hot) + offsetof(Hot, rs)) +
+                                        (unsigned)sid * (unsigned)sizeof(RngState);
+  return *reinterpret_cast<RngState*>(smem_raw + off);
+}
+__device__ __forceinline__ int rng_stream(int sid) { return sid == SID_AGENT ? RUN.cur_agent : RUN.n_agents + sid; }
 
-__device__ __noinline__ void mt_twist(unsigned* mt, int lane) {
+__device__ __noinline__ void mt_twist(unsigned* mt) {
   const unsigned U = 0x80000000u, L = 0x7fffffffu, MAG = 0x9908b0dfu;
+  const int lane = LANE;
   __syncwarp();
+#pragma unroll 1
   for (int base = 0; base < 227; base += 32) {
     int k = base + lane; bool act = k < 227; unsigned v = 0;
     if (act) { unsigned y = (mt[k] & U) | (mt[k + 1] & L); v = mt[k + 397] ^ (y >> 1) ^ ((y & 1u) ? MAG : 0u); }
@@ -196,6 +254,7 @@ __device__ __noinline__ void mt_twist(unsigned* mt, int lane) {
     if (act) mt[k] = v;
     __syncwarp();
   }
+#pragma unroll 1
   for (int base = 227; base < 623; base += 32) {
     int k = base + lane; bool act = k < 623; unsigned v = 0;
     if (act) { unsigned y = (mt[k] & U) | (mt[k + 1] & L); v = mt[k - 227] ^ (y >> 1) ^ ((y & 1u) ? MAG : 0u); }
@@ -210,7 +269,7 @@ __device__ __noinline__ void mt_twist(unsigned* mt, int lane) {
 __device__ __forceinline__ void philox4x32_10(unsigned long long ctr, unsigned long long key, unsigned out[4]) {
   unsigned c0 = (unsigned)ctr, c1 = (unsigned)(ctr >> 32), c2 = 0, c3 = 0;
   unsigned k0 = (unsigned)key, k1 = (unsigned)(key >> 32);
-#pragma unroll
+#pragma unroll 1
   for (int i = 0; i < 10; i++) {
     unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
     unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
@@ -220,150 +279,159 @@ __device__ __forceinline__ void philox4x32_10(unsigned long long ctr, unsigned l
   }
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
+__device__ __forceinline__ unsigned long long philox_key(unsigned long long seed, int stream) {
+  return seed * 0x9E3779B97F4A7C15ull + (unsigned long long)stream * 0xD1B54A32D192ED03ull + 0x2545F4914F6CDD1Dull;
+}
 
-__device__ __noinline__ unsigned rng_u32(const RngH& r) {
-  if (SM->run.db.rng_mode == ABIDES_RNG_PHILOX) {
-    unsigned n = (unsigned)*r.pos;
+__device__ __noinline__ unsigned rng_u32(int sid) {
+  RngState& r = rng_state(sid);
+  if (c_db.rng_mode == ABIDES_RNG_PHILOX) {
+    unsigned n = (unsigned)r.pos;
     unsigned o[4];
-    philox4x32_10(n >> 2, r.key, o);
-    *r.pos = (int)(n + 1);
+    philox4x32_10(n >> 2, philox_key(RUN.cfg.seed, rng_stream(sid)), o);
+    r.pos = (int)(n + 1);
     unsigned sel = n & 3u;
     return sel == 0 ? o[0] : sel == 1 ? o[1] : sel == 2 ? o[2] : o[3];
   }
-  int p = *r.pos;
-  if (p >= ABIDES_MT_N) { mt_twist(r.mt, LANE); p = 0; }
-  unsigned y = r.mt[p];
-  *r.pos = p + 1;
+  unsigned* mt = RUN.mt0 + (size_t)rng_stream(sid) * ABIDES_MT_N;
+  int p = r.pos;
+  if (p >= ABIDES_MT_N) { mt_twist(mt); p = 0; }
+  unsigned y = mt[p];
+  r.pos = p + 1;
   y ^= (y >> 11);
   y ^= (y << 7) & 0x9d2c5680u;
   y ^= (y << 15) & 0xefc60000u;
   y ^= (y >> 18);
   return y;
 }
-__device__ double rng_double(const RngH& r) {
-  int a = (int)(rng_u32(r) >> 5), b = (int)(rng_u32(r) >> 6);
+__device__ __noinline__ double rng_double(int sid) {
+  int a = (int)(rng_u32(sid) >> 5), b = (int)(rng_u32(sid) >> 6);
   return (a * 67108864.0 + b) / 9007199254740992.0;
 }
-__device__ __noinline__ double rng_gauss(const RngH& r) {
-  if (*r.flagword & r.flagbit) {
-    double t = *r.gauss;
-    *r.flagword &= ~r.flagbit;
-    *r.gauss = 0.0;
+__device__ __noinline__ double rng_gauss(int sid) {
+  RngState& r = rng_state(sid);
+  if (r.flags & 1u) {
+    double t = r.gauss;
+    r.flags = 0u;
+    r.gauss = 0.0;
     return t;
   }
   double f, x1, x2, r2;
   do {
-    x1 = 2.0 * rng_double(r) - 1.0;
-    x2 = 2.0 * rng_double(r) - 1.0;
+    x1 = 2.0 * rng_double(sid) - 1.0;
+    x2 = 2.0 * rng_double(sid) - 1.0;
     r2 = x1 * x1 + x2 * x2;
   } while (r2 >= 1.0 || r2 == 0.0);
   f = sqrt(-2.0 * abm_log(r2) / r2);
-  *r.gauss = f * x1;
-  *r.flagword |= r.flagbit;
+  r.gauss = f * x1;
+  r.flags = 1u;
   return f * x2;
 }
-__device__ double rng_normal(const RngH& r, double loc, double scale) { return loc + scale * rng_gauss(r); }
-__device__ double rng_exponential(const RngH& r, double scale) {
-  return scale * (-abm_log(1.0 - rng_double(r)));
-}
-__device__ double rng_uniform(const RngH& r, double lo, double hi) { return lo + (hi - lo) * rng_double(r); }
-__device__ long long rng_randint(const RngH& r, long long lo, long long hi) {
+__device__ __forceinline__ double rng_normal(int sid, double loc, double scale) { return loc + scale * rng_gauss(sid); }
+__device__ __forceinline__ double rng_exponential(int sid, double scale) { return scale * (-abm_log(1.0 - rng_double(sid))); }
+__device__ __forceinline__ double rng_uniform(int sid, double lo, double hi) { return lo + (hi - lo) * rng_double(sid); }
+__device__ __noinline__ long long rng_randint(int sid, long long lo, long long hi) {
   unsigned long long rng = (unsigned long long)(hi - 1 - lo);
   if (rng == 0) return lo;
-  if (rng == 0xFFFFFFFFull) return lo + (long long)rng_u32(r);
+  if (rng == 0xFFFFFFFFull) return lo + (long long)rng_u32(sid);
   unsigned mask = (unsigned)rng;
   mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
   unsigned v;
-  while ((v = (rng_u32(r) & mask)) > (unsigned)rng) {}
+  while ((v = (rng_u32(sid) & mask)) > (unsigned)rng) {}
   return lo + (long long)v;
-}
-
-__device__ __forceinline__ unsigned long long philox_key(unsigned long long seed, int stream) {
-  return seed * 0x9E3779B97F4A7C15ull + (unsigned long long)stream * 0xD1B54A32D192ED03ull + 0x2545F4914F6CDD1Dull;
-}
-__device__ __forceinline__ RngH agent_rng() {      // stream of the agent currently in S->ag
-  RngH r;
-  AgentRec& A = SM->st.ag;
-  r.mt = SM->run.db.mt ? SM->run.db.mt + (size_t)(SM->run.aoff + (long long)ABIDES_EXTRA_STREAMS * SM->run.inst + SM->run.cur_agent) * ABIDES_MT_N : nullptr;
-  r.pos = &A.rng_pos; r.gauss = &A.gauss; r.flagword = &A.flags; r.flagbit = F_HAS_GAUSS;
-  r.key = philox_key(SM->run.cfg.seed, SM->run.cur_agent);
-  return r;
-}
-__device__ __forceinline__ RngH extra_rng(int which) {
-  RngH r;
-  RngState& s = SM->st.hot.rs[which];
-  int stream = SM->run.n_agents + which;
-  r.mt = SM->run.db.mt ? SM->run.db.mt + (size_t)(SM->run.aoff + (long long)ABIDES_EXTRA_STREAMS * SM->run.inst + stream) * ABIDES_MT_N : nullptr;
-  r.pos = &s.pos; r.gauss = &s.gauss; r.flagword = &s.flags; r.flagbit = 1u;
-  r.key = philox_key(SM->run.cfg.seed, stream);
-  return r;
 }
 
 // ----------------------------------------------------------------------------------------------
 // trace
 // ----------------------------------------------------------------------------------------------
 __device__ __noinline__ void trace_write(long long time, int agent, int code, long long p0, long long p1, long long p2, long long p3) {
-  Hot& h = SM->st.hot;
-  int i = h.n_trace;
-  h.n_trace = i + 1;
-  if (!SM->run.trace || i >= SM->run.db.trace_cap) return;
+  int i = HOT.n_trace;
+  HOT.n_trace = i + 1;
+  if (!RUN.trace || i >= c_db.trace_cap) return;
   if (LANE == 0) {
     abides_trace_rec r;
     r.time = time; r.agent = agent; r.code = code; r.p0 = p0; r.p1 = p1; r.p2 = p2; r.p3 = p3;
-    SM->run.trace[i] = r;
+    RUN.trace[i] = r;
   }
   __syncwarp();
 }
 
 // ----------------------------------------------------------------------------------------------
-// event queue: near tier (shared memory) over an unsorted far list (HBM)
+// event queue.  Invariants: every near event < near_limit (HOT.lim_*) <= every event of list A and B;
+// every A event < horizon (HOT.hz_*) <= every B event.  Lists are unsorted, append-only, with
+// tombstones (t == LLONG_MAX); which tier an event sits in never changes the pop order.
 // ----------------------------------------------------------------------------------------------
-__device__ __noinline__ void far_compact() {
-  Hot& h = SM->st.hot;
-  int n = h.n_far_total, w = 0;
+__device__ __noinline__ void list_compact(int L) {
+  EvKey* keys = RUN.lk[L]; EvPay* pay = RUN.lp[L];
+  int n = HOT.l_total[L], w = 0;
   __syncwarp();
+#pragma unroll 1
   for (int base = 0; base < n; base += 32) {
     int i = base + LANE;
     bool live = false; EvKey k; EvPay p;
-    if (i < n) { k = SM->run.far_keys[i]; live = k.t != LLONG_MAX; if (live) p = SM->run.far_pay[i]; }
+    if (i < n) { k = keys[i]; live = k.t != LLONG_MAX; if (live) p = pay[i]; }
     unsigned m = __ballot_sync(FULL, live);
     __syncwarp();
     if (live) {
       int j = w + __popc(m & ((1u << LANE) - 1u));
-      if (j != i) { SM->run.far_keys[j] = k; SM->run.far_pay[j] = p; }
+      if (j != i) { keys[j] = k; pay[j] = p; }
     }
     w += __popc(m);
     __syncwarp();
   }
-  h.n_far_total = w;
+  HOT.l_total[L] = w;
 }
 
-__device__ __noinline__ void far_append(const EvKey& k, const EvPay& p) {
-  Hot& h = SM->st.hot;
-  if (h.n_far_total >= SM->run.db.far_cap) {
-    far_compact();
-    if (h.n_far_total >= SM->run.db.far_cap) { h.status = ABIDES_EOVERFLOW; return; }
+__device__ __noinline__ void list_append(int L, long long t, unsigned long long k2, int w0, int w1, int w2, int w3,
+                                         int w4, int w5) {
+  int i = HOT.l_total[L];
+  if (i >= RUN.lcap[L]) {
+    list_compact(L);
+    i = HOT.l_total[L];
+    if (i >= RUN.lcap[L]) { HOT.status = ABIDES_EOVERFLOW; return; }
   }
-  int i = h.n_far_total;
-  if (LANE == 0) SM->run.far_keys[i] = k;
-  else if (LANE == 1) *reinterpret_cast<int4*>(&SM->run.far_pay[i].w[0]) = make_int4(p.w[0], p.w[1], p.w[2], p.w[3]);
-  else if (LANE == 2) *reinterpret_cast<int4*>(&SM->run.far_pay[i].w[4]) = make_int4(p.w[4], p.w[5], p.w[6], p.w[7]);
+  if (LANE == 0) { EvKey k; k.t = t; k.k2 = k2; RUN.lk[L][i] = k; }
+  else if (LANE == 1) *reinterpret_cast<int4*>(&RUN.lp[L][i].w[0]) = make_int4(w0, w1, w2, w3);
+  else if (LANE == 2) *reinterpret_cast<int4*>(&RUN.lp[L][i].w[4]) = make_int4(w4, w5, 0, 0);
   __syncwarp();
-  h.n_far_total = i + 1;
-  h.n_far_live++;
+  HOT.l_total[L] = i + 1;
+  HOT.l_live[L] += 1;
 }
 
-// arg-min (or arg-max) of the near keys; ties broken by slot index so the result is warp-uniform
-__device__ __noinline__ int near_argext(bool want_max) {
-  const InstShared* S = &SM->st;
-  int n = S->hot.n_near;
-  long long bt = 0; unsigned long long bk = 0; int bi = -1;
-  __syncwarp();
+// warp arg-min of the near keys (ties: the lowest lane's candidate; tied keys are identical events)
+__device__ __forceinline__ int near_argmin() {
+  const int n = HOT.n_near;
+  long long bt = LLONG_MAX; unsigned long long bk = ~0ull; int bi = -1;
   for (int i = LANE; i < n; i += 32) {
-    EvKey k = S->nkey[i];
-    bool better = bi < 0 || (want_max ? key_less(bt, bk, k.t, k.k2) : key_less(k.t, k.k2, bt, bk));
-    if (better) { bt = k.t; bk = k.k2; bi = i; }
+    long long t = ST.nt[i]; unsigned long long k = ST.nk[i];
+    if (key_less(t, k, bt, bk) || bi < 0) { bt = t; bk = k; bi = i; }
   }
+  // times are non-negative (ns since the epoch), so unsigned order == signed order
+  unsigned th = (unsigned)((unsigned long long)bt >> 32);
+  unsigned mh = __reduce_min_sync(FULL, th);
+  unsigned tl = th == mh ? (unsigned)bt : 0xffffffffu;
+  unsigned ml = __reduce_min_sync(FULL, tl);
+  bool c = bi >= 0 && th == mh && (unsigned)bt == ml;
+  unsigned m = __ballot_sync(FULL, c);
+  if (__popc(m) > 1) {
+    unsigned kh = c ? (unsigned)(bk >> 32) : 0xffffffffu;
+    unsigned mkh = __reduce_min_sync(FULL, kh);
+    c = c && kh == mkh;
+    unsigned kl = c ? (unsigned)bk : 0xffffffffu;
+    unsigned mkl = __reduce_min_sync(FULL, kl);
+    c = c && kl == mkl;
+    m = __ballot_sync(FULL, c);
+  }
+  return __shfl_sync(FULL, bi, __ffs(m) - 1);
+}
+__device__ __noinline__ int near_argmax() {
+  const int n = HOT.n_near;
+  long long bt = -1; unsigned long long bk = 0; int bi = -1;
+  for (int i = LANE; i < n; i += 32) {
+    long long t = ST.nt[i]; unsigned long long k = ST.nk[i];
+    if (bi < 0 || key_less(bt, bk, t, k)) { bt = t; bk = k; bi = i; }
+  }
+#pragma unroll 1
   for (int o = 16; o; o >>= 1) {
     long long ot = __shfl_xor_sync(FULL, bt, o);
     unsigned long long ok = __shfl_xor_sync(FULL, bk, o);
@@ -372,219 +440,305 @@ __device__ __noinline__ int near_argext(bool want_max) {
     if (oi < 0) better = false;
     else if (bi < 0) better = true;
     else if (ot == bt && ok == bk) better = oi < bi;
-    else better = want_max ? key_less(bt, bk, ot, ok) : key_less(ot, ok, bt, bk);
+    else better = key_less(bt, bk, ot, ok);
     if (better) { bt = ot; bk = ok; bi = oi; }
   }
   return bi;
 }
-
-__device__ __noinline__ void near_remove(int idx) {
-  InstShared* S = &SM->st;
-  int last = S->hot.n_near - 1;
-  if (idx != last) { S->nkey[idx] = S->nkey[last]; S->npay[idx] = S->npay[last]; }
-  S->hot.n_near = last;
+__device__ __forceinline__ void near_remove(int idx) {
+  int last = HOT.n_near - 1;
+  __syncwarp();
+  if (idx != last) {
+    if (LANE == 0) ST.nt[idx] = ST.nt[last];
+    else if (LANE == 1) ST.nk[idx] = ST.nk[last];
+    else if (LANE == 2) *reinterpret_cast<int4*>(&ST.npay[idx].w[0]) = *reinterpret_cast<const int4*>(&ST.npay[last].w[0]);
+    else if (LANE == 3) *reinterpret_cast<int4*>(&ST.npay[idx].w[4]) = *reinterpret_cast<const int4*>(&ST.npay[last].w[4]);
+  }
+  HOT.n_near = last;
+  __syncwarp();
+}
+__device__ __forceinline__ void near_put(int slot, long long t, unsigned long long k2, int w0, int w1, int w2, int w3,
+                                         int w4, int w5) {
+  if (LANE == 0) ST.nt[slot] = t;
+  else if (LANE == 1) ST.nk[slot] = k2;
+  else if (LANE == 2) *reinterpret_cast<int4*>(&ST.npay[slot].w[0]) = make_int4(w0, w1, w2, w3);
+  else if (LANE == 3) *reinterpret_cast<int4*>(&ST.npay[slot].w[4]) = make_int4(w4, w5, 0, 0);
   __syncwarp();
 }
 
-__device__ __noinline__ void q_push(const EvKey& k, const EvPay& p) {
-  InstShared* S = &SM->st;
-  Hot& h = S->hot;
-  if (key_less(k.t, k.k2, h.near_limit_t, h.near_limit_k)) {
-    if (h.n_near == NEAR_CAP) {
-      // near tier full: move its largest key out to the far list and pull the limit down to it
-      int mi = near_argext(true);
-      EvKey mk = S->nkey[mi]; EvPay mp = S->npay[mi];
-      near_remove(mi);
-      far_append(mk, mp);
-      h.near_limit_t = mk.t; h.near_limit_k = mk.k2;
-      if (!key_less(k.t, k.k2, mk.t, mk.k2)) { far_append(k, p); goto done; }
-    }
-    int n = h.n_near;
-    S->nkey[n] = k; S->npay[n] = p;
-    h.n_near = n + 1;
-  } else {
-    far_append(k, p);
-  }
-done:
-  int tot = h.n_near + h.n_far_live;
-  if (tot > h.queue_peak) h.queue_peak = tot;
-}
-
-__device__ __noinline__ int far_count_lt(int n, long long pt, unsigned long long pk) {
+__device__ __noinline__ int list_count_lt(const EvKey* __restrict__ keys, int n, long long pt, unsigned long long pk) {
   int cnt = 0;
+#pragma unroll 4
   for (int i = LANE; i < n; i += 32) {
-    EvKey k = SM->run.far_keys[i];
+    EvKey k = keys[i];
     cnt += key_less(k.t, k.k2, pt, pk) ? 1 : 0;
   }
   return warp_sum_i(cnt);
 }
 
-// near tier is empty: pull the next batch (<= FILL_MAX smallest keys) out of the far list
-__device__ __noinline__ void q_refill() {
-  InstShared* S = &SM->st;
-  Hot& h = S->hot;
-  if (h.n_far_total > 1024 && h.n_far_live * 2 < h.n_far_total) far_compact();
-  int n = h.n_far_total;
+// Pick a key limit for list L such that 1 <= #(entries < limit) <= kmax (aiming at >= kmin), limit <= (ubt, ubk).
+// The window width HOT.span[S] adapts.  More than kmax events on one timestamp are split on the secondary key
+// (recipient, kind, uniq).  Result in HOT.sel_*; returns the count.
+__device__ __noinline__ int choose_limit(int L, int S, int kmax, int kmin, int hard_cap, long long ubt,
+                                         unsigned long long ubk) {
+  const EvKey* keys = RUN.lk[L];
+  const int n = HOT.l_total[L];
   __syncwarp();
   long long tmin = LLONG_MAX;
-  for (int i = LANE; i < n; i += 32) { long long t = SM->run.far_keys[i].t; tmin = t < tmin ? t : tmin; }
+#pragma unroll 2
+  for (int i = LANE; i < n; i += 32) { long long t = keys[i].t; tmin = t < tmin ? t : tmin; }
   tmin = warp_min_ll(tmin);
-  long long dT = h.dT, pt; unsigned long long pk = 0; int cnt;
-  bool burst = false;
+  long long dT = HOT.span[S], pt; unsigned long long pk = 0; int cnt;
+  bool burst = false, clamped = false;
   for (;;) {
-    pt = (tmin > LLONG_MAX - 2 - dT) ? LLONG_MAX - 1 : tmin + dT;
-    cnt = far_count_lt(n, pt, 0);
-    if (cnt <= FILL_MAX) break;
+    pt = (tmin > LLONG_MAX - 2 - dT) ? LLONG_MAX - 1 : tmin + dT; pk = 0;
+    clamped = !key_less(pt, pk, ubt, ubk);
+    if (clamped) { pt = ubt; pk = ubk; }
+    cnt = list_count_lt(keys, n, pt, pk);
+    if (cnt <= kmax) break;
     if (dT <= 1) { burst = true; break; }
     dT >>= 2; if (dT < 1) dT = 1;
   }
   if (burst) {
-    // more than FILL_MAX events share the timestamp tmin: split them on the secondary key
-    // (recipient, kind, uniq).  Interpolate first (recipients are spread evenly), then bisect.
-    unsigned long long kmin = ~0ull, kmax = 0;
+    // more than kmax events share the timestamp tmin: interpolate (recipients are spread evenly), then bisect
+    unsigned long long kmin_k = ~0ull, kmax_k = 0;
+#pragma unroll 1
     for (int i = LANE; i < n; i += 32) {
-      EvKey k = SM->run.far_keys[i];
-      if (k.t == tmin) { kmin = k.k2 < kmin ? k.k2 : kmin; kmax = k.k2 > kmax ? k.k2 : kmax; }
+      EvKey k = keys[i];
+      if (k.t == tmin) { kmin_k = k.k2 < kmin_k ? k.k2 : kmin_k; kmax_k = k.k2 > kmax_k ? k.k2 : kmax_k; }
     }
-    kmin = warp_min_ull(kmin); kmax = warp_max_ull(kmax);
-    unsigned long long lo = kmin, hi = kmax + 1;          // count(<lo) == 0, count(<hi) == cnt > FILL_MAX
+    kmin_k = warp_min_ull(kmin_k); kmax_k = warp_max_ull(kmax_k);
+    unsigned long long lo = kmin_k, hi = kmax_k + 1;         // count(<lo) == 0, count(<hi) == cnt > kmax
     unsigned long long best = 0; int best_cnt = 0;
-    double frac = (double)(FILL_MAX * 3 / 4) / (double)cnt;
-    unsigned long long guess = kmin + (unsigned long long)((double)(kmax - kmin) * frac) + 1;
+    double frac = (double)(kmax * 3 / 4) / (double)cnt;
+    unsigned long long guess = kmin_k + (unsigned long long)((double)(kmax_k - kmin_k) * frac) + 1;
+#pragma unroll 1
     for (int it = 0; it < 80; it++) {
       unsigned long long mid = it == 0 ? guess : lo + (hi - lo) / 2;
       if (mid <= lo) mid = lo + 1;
       if (mid >= hi) break;
-      int cc = far_count_lt(n, tmin, mid);
-      if (cc > FILL_MAX) hi = mid;
-      else { lo = mid; if (cc > best_cnt) { best = mid; best_cnt = cc; } if (cc >= FILL_MIN) break; }
+      int cc = list_count_lt(keys, n, tmin, mid);
+      if (cc > kmax) hi = mid;
+      else { lo = mid; if (cc > best_cnt) { best = mid; best_cnt = cc; } if (cc >= kmin) break; }
     }
-    if (best_cnt == 0) { best = hi; best_cnt = far_count_lt(n, tmin, hi); }   // identical keys
+    if (best_cnt == 0) { best = hi; best_cnt = list_count_lt(keys, n, tmin, hi); }   // identical keys
     pt = tmin; pk = best; cnt = best_cnt;
-    if (cnt > NEAR_CAP) { h.status = ABIDES_EOVERFLOW; cnt = 0; pk = 0; }
+    if (cnt > hard_cap) { HOT.status = ABIDES_EOVERFLOW; cnt = 0; pk = 0; }
+  } else {
+    if (!clamped && cnt < kmin && dT < (1ll << 50)) dT <<= 1;
+    HOT.span[S] = dT;
   }
-  int nn = h.n_near;
+  HOT.sel_t = pt; HOT.sel_k = pk;
+  return cnt;
+}
+
+// list A ran dry: move the next few hundred events of B into it and advance the horizon
+__device__ __noinline__ void b_pull() {
+  PROF_CNT(P_N_BPULL);
+  if (HOT.l_total[1] > 1024 && HOT.l_live[1] * 2 < HOT.l_total[1]) list_compact(1);
+  int cnt = choose_limit(1, 1, A_FILL_MAX, A_FILL_MIN, A_CAP / 2, LLONG_MAX - 1, 0ull);
+  const long long pt = HOT.sel_t; const unsigned long long pk = HOT.sel_k;
+  EvKey* bk = RUN.lk[1]; EvPay* bp = RUN.lp[1]; EvKey* ak = RUN.lk[0]; EvPay* ap = RUN.lp[0];
+  const int n = HOT.l_total[1];
+  int na = 0;
+#pragma unroll 1
   for (int base = 0; base < n; base += 32) {
     int i = base + LANE;
     bool take = false; EvKey k;
-    if (i < n) { k = SM->run.far_keys[i]; take = key_less(k.t, k.k2, pt, pk); }
+    if (i < n) { k = bk[i]; take = key_less(k.t, k.k2, pt, pk); }
+    unsigned m = __ballot_sync(FULL, take);
+    if (m) {
+      if (take) {
+        int pos = na + __popc(m & ((1u << LANE) - 1u));
+        ak[pos] = k; ap[pos] = bp[i];
+        bk[i].t = LLONG_MAX;
+      }
+      na += __popc(m);
+    }
+  }
+  __syncwarp();
+  HOT.l_total[0] = na; HOT.l_live[0] = na;
+  HOT.l_live[1] -= cnt;
+  HOT.hz_t = pt; HOT.hz_k = pk;
+  __syncwarp();
+}
+
+// list A grew past A_REBALANCE (a burst inside the horizon): pull the horizon in and hand the tail back to B
+__device__ __noinline__ void a_rebalance() {
+  list_compact(0);
+  int cnt = choose_limit(0, 1, A_FILL_MAX, A_FILL_MIN, A_CAP / 2, HOT.hz_t, HOT.hz_k);
+  if (HOT.status) return;
+  const long long pt = HOT.sel_t; const unsigned long long pk = HOT.sel_k;
+  const int n = HOT.l_total[0];
+  int moved = n - cnt;
+  if (HOT.l_total[1] + moved > RUN.lcap[1]) {
+    list_compact(1);
+    if (HOT.l_total[1] + moved > RUN.lcap[1]) { HOT.status = ABIDES_EOVERFLOW; return; }
+  }
+  EvKey* bk = RUN.lk[1]; EvPay* bp = RUN.lp[1]; EvKey* ak = RUN.lk[0]; EvPay* ap = RUN.lp[0];
+  int nb = HOT.l_total[1];
+#pragma unroll 1
+  for (int base = 0; base < n; base += 32) {
+    int i = base + LANE;
+    bool take = false; EvKey k;
+    if (i < n) { k = ak[i]; take = !key_less(k.t, k.k2, pt, pk); }
+    unsigned m = __ballot_sync(FULL, take);
+    if (m) {
+      if (take) {
+        int pos = nb + __popc(m & ((1u << LANE) - 1u));
+        bk[pos] = k; bp[pos] = ap[i];
+        ak[i].t = LLONG_MAX;
+      }
+      nb += __popc(m);
+    }
+  }
+  __syncwarp();
+  HOT.l_total[1] = nb; HOT.l_live[1] += moved;
+  HOT.l_live[0] = cnt;
+  HOT.hz_t = pt; HOT.hz_k = pk;
+  __syncwarp();
+  list_compact(0);
+}
+
+__device__ __noinline__ void q_push(long long t, unsigned long long k2, int w0, int w1, int w2, int w3, int w4, int w5) {
+  if (key_less(t, k2, HOT.lim_t, HOT.lim_k)) {
+    bool to_near = true;
+    if (HOT.n_near == NEAR_CAP) {
+      // near tier full: move its largest key out to list A and pull the limit down to it
+      int mi = near_argmax();
+      long long mt = ST.nt[mi]; unsigned long long mk = ST.nk[mi];
+      int4 p0 = *reinterpret_cast<const int4*>(&ST.npay[mi].w[0]);
+      int4 p1 = *reinterpret_cast<const int4*>(&ST.npay[mi].w[4]);
+      near_remove(mi);
+      list_append(0, mt, mk, p0.x, p0.y, p0.z, p0.w, p1.x, p1.y);
+      HOT.lim_t = mt; HOT.lim_k = mk;
+      to_near = key_less(t, k2, mt, mk);
+    }
+    if (to_near) {
+      int n = HOT.n_near;
+      near_put(n, t, k2, w0, w1, w2, w3, w4, w5);
+      HOT.n_near = n + 1;
+    } else {
+      list_append(0, t, k2, w0, w1, w2, w3, w4, w5);
+    }
+  } else if (key_less(t, k2, HOT.hz_t, HOT.hz_k)) {
+    list_append(0, t, k2, w0, w1, w2, w3, w4, w5);
+    if (HOT.l_live[0] > A_REBALANCE) a_rebalance();
+  } else {
+    list_append(1, t, k2, w0, w1, w2, w3, w4, w5);
+  }
+  int tot = HOT.n_near + HOT.l_live[0] + HOT.l_live[1];
+  if (tot > HOT.queue_peak) HOT.queue_peak = tot;
+}
+
+// near tier is empty: pull the next batch (<= FILL_MAX smallest keys) out of list A (refilled from B when dry)
+__device__ __noinline__ void q_refill() {
+  PROF_CNT(P_N_REFILL);
+  if (HOT.l_live[0] == 0) {
+    HOT.l_total[0] = 0;
+    if (HOT.l_live[1] == 0) return;
+    b_pull();
+    if (HOT.status) return;
+  }
+  if (HOT.l_total[0] > 256 && HOT.l_live[0] * 2 < HOT.l_total[0]) list_compact(0);
+  int cnt = choose_limit(0, 0, FILL_MAX, FILL_MIN, NEAR_CAP, HOT.hz_t, HOT.hz_k);
+  const long long pt = HOT.sel_t; const unsigned long long pk = HOT.sel_k;
+  EvKey* keys = RUN.lk[0]; const EvPay* pay = RUN.lp[0];
+  const int n = HOT.l_total[0];
+  int nn = HOT.n_near;
+#pragma unroll 1
+  for (int base = 0; base < n; base += 32) {
+    int i = base + LANE;
+    bool take = false; EvKey k;
+    if (i < n) { k = keys[i]; take = key_less(k.t, k.k2, pt, pk); }
     unsigned m = __ballot_sync(FULL, take);
     if (m) {
       if (take) {
         int pos = nn + __popc(m & ((1u << LANE) - 1u));
-        S->nkey[pos] = k; S->npay[pos] = SM->run.far_pay[i];
-        SM->run.far_keys[i].t = LLONG_MAX;
+        ST.nt[pos] = k.t; ST.nk[pos] = k.k2; ST.npay[pos] = pay[i];
+        keys[i].t = LLONG_MAX;
       }
       nn += __popc(m);
     }
   }
   __syncwarp();
-  h.n_near = nn;
-  h.n_far_live -= cnt;
-  h.near_limit_t = pt; h.near_limit_k = pk;
-  if (!burst) {
-    if (cnt < FILL_MIN && dT < (1ll << 50)) dT <<= 1;
-    h.dT = dT;
-  }
+  HOT.n_near = nn;
+  HOT.l_live[0] -= cnt;
+  HOT.lim_t = pt; HOT.lim_k = pk;
   __syncwarp();
 }
 
 // ----------------------------------------------------------------------------------------------
-// Kernel.sendMessage / setWakeup  (Kernel.py:329-418)
+// Kernel.sendMessage / setWakeup  (Kernel.py:329-418).  Payload words: w0 = code | mkt_closed<<8 | is_buy<<9;
+// order-carrying: w1 sender (to exchange), w2 id, w3 price, w4 qty, w5 fill price / new qty;
+// QUERY_SPREAD reply: w1 bid, w2 bid volume, w3 ask, w4 ask volume, w5 last trade.
 // ----------------------------------------------------------------------------------------------
-__device__ __noinline__ void k_send(int sender, int rcpt, const EvPay& pay, long long delay) {
-  Hot& h = SM->st.hot;
-  const abides_instance_cfg* cfg = &SM->run.cfg;
-  long long cd = sender == 0 ? h.exch_cd : cfg->default_computation_delay;
-  long long sent = h.now + cd + h.additional_delay + delay;
-  int other = sender == 0 ? rcpt : sender;
-  double minlat = sender == 0 ? SM->run.db.lat_from[SM->run.aoff + other] : SM->run.db.lat_to[SM->run.aoff + other];
+__device__ __noinline__ void k_send(int sender, int rcpt, long long delay, int w0, int w1, int w2, int w3, int w4, int w5) {
+  const abides_instance_cfg& cfg = RUN.cfg;
+  double minlat = sender == 0 ? RUN.lat_from[rcpt] : RUN.lat_to[sender];
+  long long cd = sender == 0 ? HOT.exch_cd : cfg.default_computation_delay;
+  long long sent = HOT.now + cd + HOT.additional_delay + delay;
   long long lat;
-  if (cfg->latency_kind == ABIDES_LAT_DETERMINISTIC) {
+  if (cfg.latency_kind == ABIDES_LAT_DETERMINISTIC) {
     lat = (long long)minlat;
-  } else if (cfg->latency_kind == ABIDES_LAT_CUBIC) {
-    double x = rng_uniform(extra_rng(ABIDES_STREAM_LATENCY), cfg->jitter_clip, 1.0);
-    double l = minlat + ((cfg->jitter / abm_cube(x)) * (minlat / cfg->jitter_unit));
+  } else if (cfg.latency_kind == ABIDES_LAT_CUBIC) {
+    double x = rng_uniform(ABIDES_STREAM_LATENCY, cfg.jitter_clip, 1.0);
+    double l = minlat + ((cfg.jitter / abm_cube(x)) * (minlat / cfg.jitter_unit));
     lat = (long long)l;
   } else {
-    long long noise = rng_randint(extra_rng(ABIDES_STREAM_KERNEL), 0, cfg->n_latency_noise);
+    long long noise = rng_randint(ABIDES_STREAM_KERNEL, 0, cfg.n_latency_noise);
     lat = (long long)(minlat + (double)noise);
   }
-  EvKey k;
-  k.t = sent + lat;
-  k.k2 = ((unsigned long long)(unsigned)rcpt << 33) | (unsigned long long)h.uniq;
-  h.uniq++;
-  q_push(k, pay);
+  unsigned u = HOT.uniq;
+  HOT.uniq = u + 1;
+  q_push(sent + lat, ((unsigned long long)(unsigned)rcpt << 33) | (unsigned long long)u, w0, w1, w2, w3, w4, w5);
 }
 __device__ __noinline__ void k_wakeup(int agent, long long t) {
-  Hot& h = SM->st.hot;
-  if (t < h.now) { h.status = ABIDES_EINVAL; return; }
-  EvKey k; k.t = t; k.k2 = ((unsigned long long)(unsigned)agent << 33) | (1ull << 32);
-  EvPay p;
-#pragma unroll
-  for (int i = 0; i < 8; i++) p.w[i] = 0;
-  q_push(k, p);
+  if (t < HOT.now) { HOT.status = ABIDES_EINVAL; return; }
+  q_push(t, ((unsigned long long)(unsigned)agent << 33) | (1ull << 32), 0, 0, 0, 0, 0, 0);
 }
+__device__ __forceinline__ int pay_code(int w0) { return w0 & 0xff; }
+__device__ __forceinline__ bool pay_closed(int w0) { return (w0 >> 8) & 1; }
+__device__ __forceinline__ bool pay_is_buy(int w0) { return (w0 >> 9) & 1; }
+__device__ __forceinline__ int order_w0(int code, bool is_buy) { return code | (is_buy ? 1 << 9 : 0); }
 
 // ----------------------------------------------------------------------------------------------
 // oracle (util/oracle/SparseMeanRevertingOracle.py)
 // ----------------------------------------------------------------------------------------------
 __device__ __noinline__ double oracle_step(long long ts, double v_adj, long long pt, double pv) {
-  const abides_instance_cfg* cfg = &SM->run.cfg;
-  Hot& h = SM->st.hot;
+  const abides_instance_cfg& cfg = RUN.cfg;
   double d = (double)(ts - pt);
-  double mu = cfg->r_bar, gamma = cfg->kappa, theta = cfg->fund_vol;
+  double mu = cfg.r_bar, gamma = cfg.kappa, theta = cfg.fund_vol;
   double e1 = abm_exp(-gamma * d);
   double loc = mu + (pv - mu) * e1;
   double e2 = abm_exp(-2 * gamma * d);
   double scale = (theta / (2 * gamma)) * (1 - e2);
-  double v = rng_normal(extra_rng(ABIDES_STREAM_ORACLE), loc, scale);
+  double v = rng_normal(ABIDES_STREAM_ORACLE, loc, scale);
   v += v_adj;
   if (!(v > 0)) v = 0;
   v = rint(v);
-  h.or_pt = ts; h.or_pv = v;
-  if (SM->run.trace) trace_write(ts, -1, TRACE_FUNDAMENTAL, (long long)v, 0, 0, 0);
+  HOT.or_pt = ts; HOT.or_pv = v;
+  if (RUN.trace) trace_write(ts, -1, TRACE_FUNDAMENTAL, (long long)v, 0, 0, 0);
   return v;
 }
 __device__ __noinline__ double oracle_advance(long long t) {
-  const abides_instance_cfg* cfg = &SM->run.cfg;
-  Hot& h = SM->st.hot;
-  long long pt = h.or_pt; double pv = h.or_pv;
+  const abides_instance_cfg& cfg = RUN.cfg;
+  long long pt = HOT.or_pt; double pv = HOT.or_pv;
   if (t <= pt) return pv;
-  while (h.ms_time < t) {
-    double v = oracle_step(h.ms_time, h.ms_value, pt, pv);
-    pt = h.ms_time; pv = v;
-    double dt = rng_exponential(extra_rng(ABIDES_STREAM_GLOBAL), 1.0 / cfg->megashock_lambda_a);
-    h.ms_time = pt + (long long)dt;
-    double msv = rng_normal(extra_rng(ABIDES_STREAM_ORACLE), cfg->megashock_mean, sqrt(cfg->megashock_var));
-    h.ms_value = rng_randint(extra_rng(ABIDES_STREAM_ORACLE), 0, 2) == 0 ? msv : -msv;
+  while (HOT.ms_time < t) {
+    double v = oracle_step(HOT.ms_time, HOT.ms_value, pt, pv);
+    pt = HOT.ms_time; pv = v;
+    double dt = rng_exponential(ABIDES_STREAM_GLOBAL, 1.0 / cfg.megashock_lambda_a);
+    HOT.ms_time = pt + (long long)dt;
+    double msv = rng_normal(ABIDES_STREAM_ORACLE, cfg.megashock_mean, sqrt(cfg.megashock_var));
+    HOT.ms_value = rng_randint(ABIDES_STREAM_ORACLE, 0, 2) == 0 ? msv : -msv;
   }
   return oracle_step(t, 0.0, pt, pv);
 }
-__device__ __noinline__ long long oracle_observe(long long t, double sigma_n, const RngH& rs) {
-  double r_t = (t >= SM->run.cfg.mkt_close) ? oracle_advance(SM->run.cfg.mkt_close - 1) : oracle_advance(t);
+__device__ __noinline__ long long oracle_observe(long long t, double sigma_n, int sid) {
+  double r_t = (t >= RUN.cfg.mkt_close) ? oracle_advance(RUN.cfg.mkt_close - 1) : oracle_advance(t);
   if (sigma_n == 0) return (long long)r_t;
-  return (long long)rint(rng_normal(rs, r_t, sqrt(sigma_n)));
-}
-
-// ----------------------------------------------------------------------------------------------
-// payload helpers.  w[0] = code | mkt_closed<<8 | is_buy<<9
-// ----------------------------------------------------------------------------------------------
-__device__ __forceinline__ EvPay pay_zero(int code) {
-  EvPay p;
-#pragma unroll
-  for (int i = 0; i < 8; i++) p.w[i] = 0;
-  p.w[0] = code;
-  return p;
-}
-__device__ __forceinline__ int pay_code(const EvPay& p) { return p.w[0] & 0xff; }
-__device__ __forceinline__ bool pay_closed(const EvPay& p) { return (p.w[0] >> 8) & 1; }
-__device__ __forceinline__ bool pay_is_buy(const EvPay& p) { return (p.w[0] >> 9) & 1; }
-// order-carrying payloads: w[1] sender (to exchange), w[2] id, w[3] price, w[4] qty, w[5] fill price / new qty
-__device__ __forceinline__ EvPay pay_order(int code, int sender, int id, int price, int qty, bool is_buy, int fill) {
-  EvPay p = pay_zero(code | (is_buy ? 1 << 9 : 0));
-  p.w[1] = sender; p.w[2] = id; p.w[3] = price; p.w[4] = qty; p.w[5] = fill;
-  return p;
+  return (long long)rint(rng_normal(sid, r_t, sqrt(sigma_n)));
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -592,143 +746,170 @@ __device__ __forceinline__ EvPay pay_order(int code, int sender, int id, int pri
 // price, oldest first).  Its best BOOK_TOP entries live in shared memory; the rest -- the "deep
 // book" -- is spilled to HBM in REVERSE order (deep[nd-1] is the best deep entry), so that moving
 // entries across the boundary is an O(1) push/pop at the array's end and every scan or shift over
-// the deep part is a run of coalesced 512-byte warp transactions.
+// the deep part is a run of coalesced 512-byte warp transactions.  s = BID / ASK.
 // ----------------------------------------------------------------------------------------------
-struct Side { BookOrd* top; int* tseq; int* ns; BookOrd* deep; int* dseq; int* nd; bool is_buy; };
-__device__ __forceinline__ Side book_side(bool is_buy) {
-  Side sd; InstShared* S = &SM->st;
-  sd.top = is_buy ? S->bids : S->asks;
-  sd.tseq = is_buy ? S->bid_seq : S->ask_seq;
-  sd.ns = is_buy ? &S->hot.n_bids : &S->hot.n_asks;
-  sd.deep = SM->run.deep + (is_buy ? 0 : SM->run.db.deep_cap);
-  sd.dseq = SM->run.deep_seq + (is_buy ? 0 : SM->run.db.deep_cap);
-  sd.nd = is_buy ? &S->hot.nd_bids : &S->hot.nd_asks;
-  sd.is_buy = is_buy;
-  return sd;
-}
-// generic warp-parallel single-slot shifts on an (order, bucket) array pair in shared or global memory
-__device__ __noinline__ void arr_remove(BookOrd* s, int* q, int n, int idx) {   // delete slot idx from [0..n)
+__device__ __forceinline__ bool px_better_eq(int s, int p, int price) { return s == BID ? p >= price : p <= price; }
+__device__ __forceinline__ bool px_better(int s, int p, int price) { return s == BID ? p > price : p < price; }
+
+__device__ __noinline__ void top_remove(int s, int n, int idx) {                 // delete slot idx from top[s][0..n)
   __syncwarp();
+#pragma unroll 1
   for (int base = idx; base < n - 1; base += 32) {
     int j = base + LANE; BookOrd t; int tq = 0;
     bool act = j < n - 1;
-    if (act) { t = s[j + 1]; tq = q[j + 1]; }
+    if (act) { t = ST.top[s][j + 1]; tq = ST.tseq[s][j + 1]; }
     __syncwarp();
-    if (act) { s[j] = t; q[j] = tq; }
+    if (act) { ST.top[s][j] = t; ST.tseq[s][j] = tq; }
     __syncwarp();
   }
 }
-__device__ __noinline__ void arr_insert(BookOrd* s, int* q, int n, int idx, const BookOrd& o, int oseq) {
+__device__ __noinline__ void top_insert(int s, int n, int idx, int price, int qty, int id, int agent, int oseq) {
   __syncwarp();
   int cnt = n - idx;
+#pragma unroll 1
   for (int done = 0; done < cnt; done += 32) {
     int j = n - 1 - done - LANE; BookOrd t; int tq = 0;
     bool act = j >= idx;
-    if (act) { t = s[j]; tq = q[j]; }
+    if (act) { t = ST.top[s][j]; tq = ST.tseq[s][j]; }
     __syncwarp();
-    if (act) { s[j + 1] = t; q[j + 1] = tq; }
+    if (act) { ST.top[s][j + 1] = t; ST.tseq[s][j + 1] = tq; }
     __syncwarp();
   }
-  if (LANE == 0) { s[idx] = o; q[idx] = oseq; }
+  if (LANE == 0) { BookOrd o; o.price = price; o.qty = qty; o.id = id; o.agent = agent; ST.top[s][idx] = o; ST.tseq[s][idx] = oseq; }
   __syncwarp();
 }
-// count entries of s[0..n) whose price is better than or equal to `price` for this side
-__device__ __noinline__ int arr_count_better_eq(const BookOrd* s, int n, int price, bool is_buy) {
+__device__ __noinline__ void deep_remove(BookOrd* d, int* q, int n, int idx) {
+  __syncwarp();
+#pragma unroll 1
+  for (int base = idx; base < n - 1; base += 32) {
+    int j = base + LANE; BookOrd t; int tq = 0;
+    bool act = j < n - 1;
+    if (act) { t = d[j + 1]; tq = q[j + 1]; }
+    __syncwarp();
+    if (act) { d[j] = t; q[j] = tq; }
+    __syncwarp();
+  }
+}
+__device__ __noinline__ void deep_insert(BookOrd* d, int* q, int n, int idx, int price, int qty, int id, int agent, int oseq) {
+  __syncwarp();
+  int cnt = n - idx;
+#pragma unroll 1
+  for (int done = 0; done < cnt; done += 32) {
+    int j = n - 1 - done - LANE; BookOrd t; int tq = 0;
+    bool act = j >= idx;
+    if (act) { t = d[j]; tq = q[j]; }
+    __syncwarp();
+    if (act) { d[j + 1] = t; q[j + 1] = tq; }
+    __syncwarp();
+  }
+  if (LANE == 0) { BookOrd o; o.price = price; o.qty = qty; o.id = id; o.agent = agent; d[idx] = o; q[idx] = oseq; }
+  __syncwarp();
+}
+// count entries whose price is better than or equal to `price` for this side
+__device__ __forceinline__ int top_count_better_eq(int s, int n, int price) {
   __syncwarp();
   int cnt = 0;
-  for (int j = LANE; j < n; j += 32) {
-    int p = s[j].price;
-    cnt += (is_buy ? p >= price : p <= price) ? 1 : 0;
-  }
+  for (int j = LANE; j < n; j += 32) cnt += px_better_eq(s, ST.top[s][j].price, price) ? 1 : 0;
+  return warp_sum_i(cnt);
+}
+__device__ __noinline__ int deep_count_better_eq(int s, const BookOrd* __restrict__ d, int n, int price) {
+  __syncwarp();
+  int cnt = 0;
+#pragma unroll 4
+  for (int j = LANE; j < n; j += 32) cnt += px_better_eq(s, d[j].price, price) ? 1 : 0;
   return warp_sum_i(cnt);
 }
 // the shared-memory part ran empty: pull the best entries of the deep book back in
-__device__ __noinline__ void side_refill(const Side& sd) {
-  int nd = *sd.nd, ns = *sd.ns;
+__device__ __noinline__ void side_refill(int s) {
+  int nd = HOT.n_deep[s], ns = HOT.n_top[s];
   if (ns > 0 || nd == 0) return;
   int k = nd < BOOK_TOP / 2 ? nd : BOOK_TOP / 2;
+  const BookOrd* d = RUN.deep[s]; const int* q = RUN.dseq[s];
   __syncwarp();
-  for (int i = LANE; i < k; i += 32) { sd.top[i] = sd.deep[nd - 1 - i]; sd.tseq[i] = sd.dseq[nd - 1 - i]; }
+  for (int i = LANE; i < k; i += 32) { ST.top[s][i] = d[nd - 1 - i]; ST.tseq[s][i] = q[nd - 1 - i]; }
   __syncwarp();
-  *sd.ns = k; *sd.nd = nd - k;
+  HOT.n_top[s] = k; HOT.n_deep[s] = nd - k;
 }
-__device__ __noinline__ void side_pop_front(const Side& sd) {                   // remove the best entry
-  arr_remove(sd.top, sd.tseq, *sd.ns, 0);
-  *sd.ns -= 1;
-  side_refill(sd);
+__device__ __forceinline__ void side_pop_front(int s) {                          // remove the best entry
+  top_remove(s, HOT.n_top[s], 0);
+  HOT.n_top[s] -= 1;
+  if (HOT.n_top[s] == 0) side_refill(s);
 }
 // getInsideBids(1)/getInsideAsks(1) (:378-399): price and total quantity of the best level
-__device__ __noinline__ void side_inside(const Side& sd, int& price, int& vol) {
+__device__ __noinline__ int2 side_inside(int s) {
   __syncwarp();
-  int ns = *sd.ns, nd = *sd.nd;
-  if (ns == 0) { price = -1; vol = 0; return; }
-  int p = sd.top[0].price, v = 0;
+  int ns = HOT.n_top[s], nd = HOT.n_deep[s];
+  if (ns == 0) return make_int2(-1, 0);
+  int p = ST.top[s][0].price, v = 0;
   bool whole = true;                       // does the level run to the end of the shared part?
   for (int base = 0; base < ns; base += 32) {
     int j = base + LANE;
-    bool in = j < ns && sd.top[j].price == p;
-    v += in ? sd.top[j].qty : 0;
+    bool in = j < ns && ST.top[s][j].price == p;
+    v += in ? ST.top[s][j].qty : 0;
     if (__any_sync(FULL, j < ns && !in)) { whole = false; break; }
   }
   if (whole) {
+    const BookOrd* d = RUN.deep[s];
     for (int base = 0; base < nd; base += 32) {
       int j = nd - 1 - base - LANE;
-      bool in = j >= 0 && sd.deep[j].price == p;
-      v += in ? sd.deep[j].qty : 0;
+      bool in = false; int q = 0;
+      if (j >= 0) { BookOrd e = d[j]; in = e.price == p; q = e.qty; }
+      v += in ? q : 0;
       if (__any_sync(FULL, j >= 0 && !in)) break;
     }
   }
-  price = p; vol = warp_sum_i(v);
+  return make_int2(p, warp_sum_i(v));
 }
 // OrderBook.enterOrder (:272-298): position = number of resting orders with better-or-equal price
-__device__ __noinline__ void book_enter(const BookOrd& o, bool is_buy) {
-  Hot& h = SM->st.hot;
-  Side sd = book_side(is_buy);
-  int ns = *sd.ns, nd = *sd.nd;
-  int oseq = h.hist_B;                                   // history[0][order_id] = {...} (:60-64)
-  int cs = arr_count_better_eq(sd.top, ns, o.price, is_buy);
+__device__ __noinline__ void book_enter(int s, int price, int qty, int id, int agent) {
+  int ns = HOT.n_top[s], nd = HOT.n_deep[s];
+  int oseq = HOT.hist_B;                                 // history[0][order_id] = {...} (:60-64)
+  BookOrd* d = RUN.deep[s]; int* dq = RUN.dseq[s];
+  int cs = top_count_better_eq(s, ns, price);
   bool to_top = cs < ns || nd == 0;
   int cd = 0;
   if (!to_top) {
-    cd = arr_count_better_eq(sd.deep, nd, o.price, is_buy);
+    cd = deep_count_better_eq(s, d, nd, price);
     if (cd == 0 && ns < BOOK_TOP) to_top = true;        // worse than all of top, better than all of deep
   }
   if (to_top && ns == BOOK_TOP && cs == ns) to_top = false;   // full shared part and o is its new worst: goes deep
   if (to_top) {
     if (ns == BOOK_TOP) {                                // spill the worst shared entry to the deep book's best end
-      if (nd >= SM->run.db.deep_cap) { h.status = ABIDES_EOVERFLOW; return; }
+      if (nd >= RUN.deep_cap) { HOT.status = ABIDES_EOVERFLOW; return; }
       __syncwarp();
-      if (LANE == 0) { sd.deep[nd] = sd.top[ns - 1]; sd.dseq[nd] = sd.tseq[ns - 1]; }
+      if (LANE == 0) { d[nd] = ST.top[s][ns - 1]; dq[nd] = ST.tseq[s][ns - 1]; }
       __syncwarp();
-      *sd.nd = nd + 1; ns--;
+      HOT.n_deep[s] = nd + 1; ns--;
     }
-    arr_insert(sd.top, sd.tseq, ns, cs, o, oseq);
-    *sd.ns = ns + 1;
+    top_insert(s, ns, cs, price, qty, id, agent, oseq);
+    HOT.n_top[s] = ns + 1;
   } else {
-    if (nd >= SM->run.db.deep_cap) { h.status = ABIDES_EOVERFLOW; return; }
-    arr_insert(sd.deep, sd.dseq, nd, nd - cd, o, oseq);  // logical index cd <-> physical nd - cd (reversed)
-    *sd.nd = nd + 1;
+    if (nd >= RUN.deep_cap) { HOT.status = ABIDES_EOVERFLOW; return; }
+    deep_insert(d, dq, nd, nd - cd, price, qty, id, agent, oseq);   // logical index cd <-> physical nd - cd (reversed)
+    HOT.n_deep[s] = nd + 1;
   }
-  int tot = h.n_bids + h.n_asks + h.nd_bids + h.nd_asks;
-  if (tot > h.book_peak_orders) h.book_peak_orders = tot;
+  int tot = HOT.n_top[0] + HOT.n_top[1] + HOT.n_deep[0] + HOT.n_deep[1];
+  if (tot > HOT.book_peak_orders) HOT.book_peak_orders = tot;
 }
-// find (price, id) on a side; returns 0 = absent, 1 = in the shared part, 2 = in the deep part; idx physical
-__device__ __noinline__ int side_find(const Side& sd, int price, int id, int& idx) {
+// find (price, id) on a side; returns 0 = absent, 1 = in the shared part, 2 = in the deep part; index in HOT.sel_k
+__device__ __noinline__ int side_find(int s, int price, int id) {
   __syncwarp();
-  int ns = *sd.ns, nd = *sd.nd;
+  int ns = HOT.n_top[s], nd = HOT.n_deep[s];
   for (int base = 0; base < ns; base += 32) {
     int j = base + LANE;
-    bool hit = j < ns && sd.top[j].price == price && sd.top[j].id == id;
+    bool hit = false;
+    if (j < ns) { BookOrd e = ST.top[s][j]; hit = e.price == price && e.id == id; }
     unsigned m = __ballot_sync(FULL, hit);
-    if (m) { idx = base + __ffs(m) - 1; return 1; }
+    if (m) { HOT.find_idx = base + __ffs(m) - 1; return 1; }
   }
   // deep part, scanned from its best end (highest physical index) so the FIRST match in book order wins
+  const BookOrd* d = RUN.deep[s];
   for (int base = 0; base < nd; base += 32) {
     int j = nd - 1 - base - LANE;
     bool hit = false;
-    if (j >= 0) { BookOrd e = sd.deep[j]; hit = e.price == price && e.id == id; }
+    if (j >= 0) { BookOrd e = d[j]; hit = e.price == price && e.id == id; }
     unsigned m = __ballot_sync(FULL, hit);
-    if (m) { idx = nd - 1 - base - (__ffs(m) - 1); return 2; }
+    if (m) { HOT.find_idx = nd - 1 - base - (__ffs(m) - 1); return 2; }
   }
   return 0;
 }
@@ -740,16 +921,15 @@ __device__ __noinline__ int side_find(const Side& sd, int price, int id, int& id
 // scans the rows logged since the previous query, keeps those whose bucket lies in the window, drops
 // duplicate (time, qty) rows of that batch and appends the rest to the unrolled ring it then sums over.
 __device__ __forceinline__ void txn_log_row(long long t, int q, int seq) {
-  Hot& h = SM->st.hot;
-  long long i = h.log_len;
+  long long i = HOT.log_len;
   __syncwarp();
-  if (LANE == 0 && SM->run.txn_log) { TxnRow r; r.t = t; r.q = q; r.seq = seq; SM->run.txn_log[i & (TXN_CAP - 1)] = r; }
+  if (LANE == 0 && RUN.txn_log) { TxnRow r; r.t = t; r.q = q; r.seq = seq; RUN.txn_log[i & (TXN_CAP - 1)] = r; }
   __syncwarp();
-  h.log_len = i + 1;
+  HOT.log_len = i + 1;
 }
 __device__ __noinline__ long long book_transacted_volume(long long now, long long lookback) {
-  Hot& h = SM->st.hot;
-  const int SH = SM->run.cfg.stream_history;
+  Hot& h = HOT;
+  const int SH = RUN.cfg.stream_history;
   int B = h.hist_B;
   int n = (B + 1 < SH + 1) ? B + 1 : SH + 1, p = h.tv_prev_len;
   int lo = 1, hi = 0;
@@ -757,8 +937,8 @@ __device__ __noinline__ long long book_transacted_volume(long long now, long lon
   else if (p != n) { int cnt = n - p - 1; if (cnt > 0) { lo = B - cnt + 1; hi = B; } h.tv_prev_len = n; }
   long long start = h.log_mark, end = h.log_len;
   if (end - start > TXN_CAP) { h.status = ABIDES_EOVERFLOW; return 0; }
-  const TxnRow* lg = SM->run.txn_log;
-  TxnRow* un = SM->run.unrolled;
+  const TxnRow* lg = RUN.txn_log;
+  TxnRow* un = RUN.unrolled;
   long long ulen = h.unr_len;
   __syncwarp();
   if (hi >= lo) {
@@ -802,34 +982,56 @@ __device__ __noinline__ long long book_transacted_volume(long long now, long lon
   return sum;
 }
 
+// outbound notification of the book: to the event queue (engine) or to the replay tape (K2 harness)
+__device__ __noinline__ void replay_emit(int rcpt, int code, bool is_buy, int id, int price, int qty, int fill) {
+  Run& r = RUN;
+  int k = r.rp_counts[r.rp_op];
+  __syncwarp();
+  if (LANE == 0) {
+    if (k < r.rp_max) {
+      abides_book_event e;
+      e.op_index = r.rp_op - r.rp_base; e.kind = code; e.agent = rcpt; e.is_buy = is_buy ? 1 : 0;
+      e.order_id = id; e.price = price; e.qty = qty; e.fill_price = fill;
+      r.rp_events[(size_t)r.rp_op * r.rp_max + k] = e;
+    }
+    r.rp_counts[r.rp_op] = k + 1;
+  }
+  __syncwarp();
+}
+template <bool RP>
+__device__ __forceinline__ void book_send(int rcpt, int code, bool is_buy, int id, int price, int qty, int fill) {
+  if (RP) replay_emit(rcpt, code, is_buy, id, price, qty, fill);
+  else k_send(0, rcpt, code == ABIDES_MSG_ORDER_MODIFIED ? 0 : RUN.cfg.exch_pipeline_delay, order_w0(code, is_buy), 0,
+              id, price, qty, fill);        // ORDER_ACCEPTED/CANCELLED/EXECUTED get +pipeline_delay (ExchangeAgent.py:404-407)
+}
+
 // OrderBook.handleLimitOrder (:46-158)
-template <typename Send>
-__device__ __noinline__ void book_handle_limit(Send send, int agent, int id, int price, int qty, bool is_buy) {
-  Hot& h = SM->st.hot;
+template <bool RP>
+__device__ __noinline__ void book_handle_limit(int agent, int id, int price, int qty, bool is_buy) {
+  Hot& h = HOT;
   if (qty <= 0) return;
   long long ex_qty = 0, ex_pq = 0; int executed = 0;
-  Side opp = book_side(!is_buy);
+  const int os = is_buy ? ASK : BID;
   for (;;) {
     __syncwarp();
     bool match = false; BookOrd top;
-    if (*opp.ns > 0) { top = opp.top[0]; match = is_buy ? price >= top.price : price <= top.price; }
+    if (h.n_top[os] > 0) { top = ST.top[os][0]; match = is_buy ? price >= top.price : price <= top.price; }
     if (match) {                                               // executeOrder (:190-256)
-      int fill, tseq = opp.tseq[0];
-      if (qty >= top.qty) { fill = top.qty; side_pop_front(opp); }
-      else { fill = qty; __syncwarp(); if (LANE == 0) opp.top[0].qty = top.qty - qty; __syncwarp(); }
+      int fill, tseq = ST.tseq[os][0];
+      if (qty >= top.qty) { fill = top.qty; side_pop_front(os); }
+      else { fill = qty; __syncwarp(); if (LANE == 0) ST.top[os][0].qty = top.qty - qty; __syncwarp(); }
       // history (:245-253): the aggressor logs its REMAINING quantity, the resting order the fill
       txn_log_row(h.now, qty, h.hist_B);
-      if (h.hist_B - tseq <= SM->run.cfg.stream_history) txn_log_row(h.now, fill, tseq);
+      if (h.hist_B - tseq <= RUN.cfg.stream_history) txn_log_row(h.now, fill, tseq);
       qty -= fill;
-      send(agent, pay_order(ABIDES_MSG_ORDER_EXECUTED, 0, id, price, fill, is_buy, top.price));
-      send(top.agent, pay_order(ABIDES_MSG_ORDER_EXECUTED, 0, top.id, top.price, fill, !is_buy, top.price));
+      book_send<RP>(agent, ABIDES_MSG_ORDER_EXECUTED, is_buy, id, price, fill, top.price);
+      book_send<RP>(top.agent, ABIDES_MSG_ORDER_EXECUTED, !is_buy, top.id, top.price, fill, top.price);
       ex_qty += fill; ex_pq += (long long)top.price * fill; executed++;
       h.n_fills++; h.volume += fill;
       if (qty <= 0) break;
     } else {
-      BookOrd o; o.price = price; o.qty = qty; o.id = id; o.agent = agent;
-      book_enter(o, is_buy);
-      send(agent, pay_order(ABIDES_MSG_ORDER_ACCEPTED, 0, id, price, qty, is_buy, -1));
+      book_enter(is_buy ? BID : ASK, price, qty, id, agent);
+      book_send<RP>(agent, ABIDES_MSG_ORDER_ACCEPTED, is_buy, id, price, qty, -1);
       break;
     }
   }
@@ -840,77 +1042,77 @@ __device__ __noinline__ void book_handle_limit(Send send, int agent, int id, int
   }
 }
 // OrderBook.cancelOrder (:300-348)
-template <typename Send>
-__device__ __noinline__ void book_cancel(Send send, int agent, int id, int price, bool is_buy) {
-  Side sd = book_side(is_buy);
-  int idx = 0;
-  int where = side_find(sd, price, id, idx);
+template <bool RP>
+__device__ __noinline__ void book_cancel(int agent, int id, int price, bool is_buy) {
+  const int s = is_buy ? BID : ASK;
+  int where = side_find(s, price, id);
   if (where == 0) return;
+  int idx = HOT.find_idx;
   BookOrd o;
   if (where == 1) {
-    o = sd.top[idx];
-    arr_remove(sd.top, sd.tseq, *sd.ns, idx);
-    *sd.ns -= 1;
-    side_refill(sd);
+    o = ST.top[s][idx];
+    top_remove(s, HOT.n_top[s], idx);
+    HOT.n_top[s] -= 1;
+    if (HOT.n_top[s] == 0) side_refill(s);
   } else {
-    o = sd.deep[idx];
-    arr_remove(sd.deep, sd.dseq, *sd.nd, idx);
-    *sd.nd -= 1;
+    o = RUN.deep[s][idx];
+    deep_remove(RUN.deep[s], RUN.dseq[s], HOT.n_deep[s], idx);
+    HOT.n_deep[s] -= 1;
   }
-  send(agent, pay_order(ABIDES_MSG_ORDER_CANCELLED, 0, o.id, o.price, o.qty, is_buy, -1));
+  book_send<RP>(agent, ABIDES_MSG_ORDER_CANCELLED, is_buy, o.id, o.price, o.qty, -1);
 }
 
 // OrderBook.handleMarketOrder (:160-188): one fresh limit order per opposite level until the quantity is
 // covered.  Each child consumes exactly the level it was sized from, so walking the live book level by
 // level is equivalent to the reference's snapshot walk; an uncovered remainder is dropped.
-template <typename Send>
-__device__ __noinline__ void book_handle_market(Send send, int agent, int qty, bool is_buy) {
-  Hot& h = SM->st.hot;
+template <bool RP>
+__device__ __noinline__ void book_handle_market(int agent, int qty, bool is_buy) {
   if (qty <= 0) return;
   int rem = qty;
   for (;;) {
-    int p, v;
-    side_inside(book_side(!is_buy), p, v);
+    int2 in = side_inside(is_buy ? ASK : BID);
+    int p = in.x, v = in.y;
     if (p < 0) break;
     int q = rem <= v ? rem : v;
-    int id = (int)h.next_order_id++;
-    book_handle_limit(send, agent, id, p, q, is_buy);
+    int id = (int)HOT.next_order_id++;
+    book_handle_limit<RP>(agent, id, p, q, is_buy);
     if (rem <= v) break;
     rem -= v;
   }
 }
 // OrderBook.modifyOrder (:350-373), including the reference's index-0 overwrite (:359)
-template <typename Send>
-__device__ __noinline__ void book_modify(Send send, int agent, int id, int price, int new_qty, bool is_buy) {
-  Hot& h = SM->st.hot;
-  Side sd = book_side(is_buy);
-  int idx = 0;
-  int where = side_find(sd, price, id, idx);
+template <bool RP>
+__device__ __noinline__ void book_modify(int agent, int id, int price, int new_qty, bool is_buy) {
+  const int s = is_buy ? BID : ASK;
+  int where = side_find(s, price, id);
   if (where == 0) return;
-  int oseq = where == 1 ? sd.tseq[idx] : sd.dseq[idx];
+  int idx = HOT.find_idx;
+  BookOrd* d = RUN.deep[s]; int* dq = RUN.dseq[s];
+  int oseq = where == 1 ? ST.tseq[s][idx] : dq[idx];
   // first entry of that price level = number of entries with a strictly better price
-  int ns = *sd.ns, nd = *sd.nd;
+  int ns = HOT.n_top[s], nd = HOT.n_deep[s];
   int better = 0;
   __syncwarp();
-  for (int j = LANE; j < ns; j += 32) { int pp = sd.top[j].price; better += (is_buy ? pp > price : pp < price) ? 1 : 0; }
-  for (int j = LANE; j < nd; j += 32) { int pp = sd.deep[j].price; better += (is_buy ? pp > price : pp < price) ? 1 : 0; }
+  for (int j = LANE; j < ns; j += 32) better += px_better(s, ST.top[s][j].price, price) ? 1 : 0;
+  for (int j = LANE; j < nd; j += 32) better += px_better(s, d[j].price, price) ? 1 : 0;
   better = warp_sum_i(better);
   BookOrd no; no.price = price; no.qty = new_qty; no.id = id; no.agent = agent;
   __syncwarp();
   if (LANE == 0) {
-    if (better < ns) { sd.top[better] = no; sd.tseq[better] = oseq; }
-    else { sd.deep[nd - 1 - (better - ns)] = no; sd.dseq[nd - 1 - (better - ns)] = oseq; }
+    if (better < ns) { ST.top[s][better] = no; ST.tseq[s][better] = oseq; }
+    else { d[nd - 1 - (better - ns)] = no; dq[nd - 1 - (better - ns)] = oseq; }
   }
   __syncwarp();
-  if (h.hist_B - oseq <= SM->run.cfg.stream_history)       // one notification per history bucket holding the id
-    send(agent, pay_order(ABIDES_MSG_ORDER_MODIFIED, 0, id, price, new_qty, is_buy, -1));
+  if (HOT.hist_B - oseq <= RUN.cfg.stream_history)         // one notification per history bucket holding the id
+    book_send<RP>(agent, ABIDES_MSG_ORDER_MODIFIED, is_buy, id, price, new_qty, -1);
 }
-__device__ __noinline__ int side_levels(const Side& sd) {                      // number of distinct prices
-  int ns = *sd.ns, nd = *sd.nd, c = 0;
+__device__ __noinline__ int side_levels(int s) {                                // number of distinct prices
+  int ns = HOT.n_top[s], nd = HOT.n_deep[s], c = 0;
+  const BookOrd* d = RUN.deep[s];
   __syncwarp();
   for (int j = LANE; j < ns + nd; j += 32) {
-    int p = j < ns ? sd.top[j].price : sd.deep[nd - 1 - (j - ns)].price;
-    int q = j == 0 ? p - 1 : (j - 1 < ns ? sd.top[j - 1].price : sd.deep[nd - 1 - (j - 1 - ns)].price);
+    int p = j < ns ? ST.top[s][j].price : d[nd - 1 - (j - ns)].price;
+    int q = j == 0 ? p - 1 : (j - 1 < ns ? ST.top[s][j - 1].price : d[nd - 1 - (j - 1 - ns)].price);
     c += (j == 0 || p != q) ? 1 : 0;
   }
   return warp_sum_i(c);
@@ -919,64 +1121,71 @@ __device__ __noinline__ int side_levels(const Side& sd) {                      /
 // ----------------------------------------------------------------------------------------------
 // TradingAgent (agent/TradingAgent.py)
 // ----------------------------------------------------------------------------------------------
+struct Msg { int w0, w1, w2, w3, w4, w5; };
+
 __device__ __forceinline__ int ag_state(const AgentRec& A) { return (A.flags & F_STATE_MASK) >> F_STATE_SHIFT; }
 __device__ __forceinline__ void ag_set_state(AgentRec& A, int s) { A.flags = (A.flags & ~F_STATE_MASK) | ((unsigned)s << F_STATE_SHIFT); }
 
-__device__ void agent_send(int a, EvPay p) { p.w[1] = a; k_send(a, 0, p, 0); }
-__device__ void ta_query_spread(int a) { EvPay p = pay_zero(ABIDES_MSG_QUERY_SPREAD); p.w[2] = 1; agent_send(a, p); }
+__device__ __forceinline__ void agent_send(int a, int w0, int w2, int w3, int w4, int w5) { k_send(a, 0, 0, w0, a, w2, w3, w4, w5); }
+__device__ __forceinline__ void ta_query_spread(int a) { agent_send(a, ABIDES_MSG_QUERY_SPREAD, 1, 0, 0, 0); }
 
-__device__ __noinline__ void ord_reserve(AgentRec& A, int initial_cap) {
-  Hot& h = SM->st.hot;
+__device__ __noinline__ void ord_reserve(int initial_cap) {
+  AgentRec& A = ST.ag; Hot& h = HOT;
   if (A.ord_cnt < A.ord_cap) return;
   int ncap = A.ord_cap ? A.ord_cap * 2 : initial_cap;
-  if (h.arena_top + ncap > SM->run.db.arena_cap) { h.status = ABIDES_EOVERFLOW; return; }
+  if (ncap > 65535 || h.arena_top + ncap > c_db.arena_cap) { h.status = ABIDES_EOVERFLOW; return; }
   int noff = h.arena_top;
   h.arena_top += ncap;
   __syncwarp();
-  for (int j = LANE; j < A.ord_cnt; j += 32) SM->run.arena[noff + j] = SM->run.arena[A.ord_off + j];
+  for (int j = LANE; j < A.ord_cnt; j += 32) RUN.arena[noff + j] = RUN.arena[A.ord_off + j];
   __syncwarp();
-  A.ord_off = noff; A.ord_cap = ncap;
+  A.ord_off = noff; A.ord_cap = (unsigned short)ncap;
 }
 // TradingAgent.placeLimitOrder (:295-330), ignore_risk=True
 __device__ __noinline__ void ta_place_limit(int a, long long qty, bool is_buy, long long price) {
-  AgentRec& A = SM->st.ag; Hot& h = SM->st.hot;
-  const abides_agent_type& ty = SM->run.db.types[A.type_idx];
+  AgentRec& A = ST.ag; Hot& h = HOT;
+  const abides_agent_type& ty = c_db.types[A.type_idx];
   int id = (int)h.next_order_id++;
   if (qty <= 0) return;
   OpenOrd oo; oo.key = id; oo.id = id; oo.price = (int)price; oo.sqty = is_buy ? (int)qty : -(int)qty;
   if (id == 0) oo.id = (int)h.next_order_id++;            // deepcopy of order id 0 takes a fresh id (Order.py:29)
   int init_cap = ty.klass == ABIDES_ADAPTIVE_MM ? (int)(2 * ty.num_ticks + 8) : (ty.klass == ABIDES_MOMENTUM ? 16 : 4);
-  ord_reserve(A, init_cap);
+  ord_reserve(init_cap);
   if (h.status) return;
   __syncwarp();
-  if (LANE == 0) SM->run.arena[A.ord_off + A.ord_cnt] = oo;
+  if (LANE == 0) RUN.arena[A.ord_off + A.ord_cnt] = oo;
   __syncwarp();
   A.ord_cnt++;
-  agent_send(a, pay_order(ABIDES_MSG_LIMIT_ORDER, a, id, (int)price, (int)qty, is_buy, -1));
+  agent_send(a, order_w0(ABIDES_MSG_LIMIT_ORDER, is_buy), id, (int)price, (int)qty, -1);
   if (ty.log_orders && id == 0) h.next_order_id++;
 }
 __device__ __noinline__ void ta_cancel_all(int a) {
-  AgentRec& A = SM->st.ag;
+  AgentRec& A = ST.ag;
   __syncwarp();
   for (int i = 0; i < A.ord_cnt; i++) {
-    OpenOrd o = SM->run.arena[A.ord_off + i];
-    agent_send(a, pay_order(ABIDES_MSG_CANCEL_ORDER, a, o.id, o.price, o.sqty < 0 ? -o.sqty : o.sqty, o.sqty > 0, -1));
+    OpenOrd o = RUN.arena[A.ord_off + i];
+    agent_send(a, order_w0(ABIDES_MSG_CANCEL_ORDER, o.sqty > 0), o.id, o.price, o.sqty < 0 ? -o.sqty : o.sqty, -1);
   }
 }
-__device__ __noinline__ int ord_find(const AgentRec& A, int key) {
+__device__ __noinline__ int ord_find(int key) {
+  const AgentRec& A = ST.ag;
+  const int n = A.ord_cnt;
+  const OpenOrd* s = RUN.arena + A.ord_off;
   __syncwarp();
-  for (int base = 0; base < A.ord_cnt; base += 32) {
+  for (int base = 0; base < n; base += 32) {
     int j = base + LANE;
-    bool hit = j < A.ord_cnt && SM->run.arena[A.ord_off + j].key == key;
+    bool hit = j < n && s[j].key == key;
     unsigned m = __ballot_sync(FULL, hit);
     if (m) return base + __ffs(m) - 1;
   }
   return -1;
 }
-__device__ __noinline__ void ord_remove(AgentRec& A, int idx) {
-  OpenOrd* s = SM->run.arena + A.ord_off;
+__device__ __noinline__ void ord_remove(int idx) {
+  AgentRec& A = ST.ag;
+  OpenOrd* s = RUN.arena + A.ord_off;
   int n = A.ord_cnt;
   __syncwarp();
+#pragma unroll 1
   for (int base = idx; base < n - 1; base += 32) {
     int j = base + LANE; OpenOrd t;
     bool act = j < n - 1;
@@ -985,77 +1194,77 @@ __device__ __noinline__ void ord_remove(AgentRec& A, int idx) {
     if (act) s[j] = t;
     __syncwarp();
   }
-  A.ord_cnt = n - 1;
+  A.ord_cnt = (unsigned short)(n - 1);
 }
 // TradingAgent.wakeup (:152-168); returns can_trade
-__device__ bool ta_wakeup(int a) {
-  AgentRec& A = SM->st.ag;
-  A.cur_time = SM->st.hot.now;
+__device__ __forceinline__ bool ta_wakeup(int a) {
+  AgentRec& A = ST.ag;
+  A.cur_time = HOT.now;
   if (!(A.flags & F_HAS_OPEN)) {
-    agent_send(a, pay_zero(ABIDES_MSG_WHEN_MKT_OPEN));
-    agent_send(a, pay_zero(ABIDES_MSG_WHEN_MKT_CLOSE));
+    agent_send(a, ABIDES_MSG_WHEN_MKT_OPEN, 0, 0, 0, 0);
+    agent_send(a, ABIDES_MSG_WHEN_MKT_CLOSE, 0, 0, 0, 0);
   }
   return (A.flags & F_HAS_OPEN) && (A.flags & F_HAS_CLOSE) && !(A.flags & F_MKT_CLOSED);
 }
 // TradingAgent.receiveMessage (:181-264)
-__device__ __noinline__ void ta_receive(int a, const EvPay& m, int klass, const abides_agent_type& ty) {
-  AgentRec& A = SM->st.ag;
-  A.cur_time = SM->st.hot.now;
+__device__ __forceinline__ void ta_receive(int a, const Msg& m, int klass, const abides_agent_type& ty) {
+  AgentRec& A = ST.ag;
+  A.cur_time = HOT.now;
   bool had = (A.flags & F_HAS_OPEN) && (A.flags & F_HAS_CLOSE);
-  int code = pay_code(m) & ~ABIDES_MSG_REPLY;
+  int code = pay_code(m.w0) & ~ABIDES_MSG_REPLY;
   switch (code) {
     case ABIDES_MSG_WHEN_MKT_OPEN: A.flags |= F_HAS_OPEN; break;
     case ABIDES_MSG_WHEN_MKT_CLOSE: A.flags |= F_HAS_CLOSE; break;
     case ABIDES_MSG_ORDER_EXECUTED: {                         // orderExecuted (:390-426)
-      long long q = pay_is_buy(m) ? m.w[4] : -(long long)m.w[4];
+      long long q = pay_is_buy(m.w0) ? m.w4 : -(long long)m.w4;
       A.holdings += q;
-      A.cash -= q * (long long)m.w[5];
-      int idx = ord_find(A, m.w[2]);
+      A.cash -= q * (long long)m.w5;
+      int idx = ord_find(m.w2);
       if (idx >= 0) {
-        OpenOrd o = SM->run.arena[A.ord_off + idx];
+        OpenOrd o = RUN.arena[A.ord_off + idx];
         int oq = o.sqty < 0 ? -o.sqty : o.sqty;
-        if (m.w[4] >= oq) ord_remove(A, idx);
-        else { __syncwarp(); if (LANE == 0) SM->run.arena[A.ord_off + idx].sqty = o.sqty > 0 ? oq - m.w[4] : -(oq - m.w[4]); __syncwarp(); }
+        if (m.w4 >= oq) ord_remove(idx);
+        else { __syncwarp(); if (LANE == 0) RUN.arena[A.ord_off + idx].sqty = o.sqty > 0 ? oq - m.w4 : -(oq - m.w4); __syncwarp(); }
       }
       break;
     }
     case ABIDES_MSG_ORDER_CANCELLED: {
-      int idx = ord_find(A, m.w[2]);
-      if (idx >= 0) ord_remove(A, idx);
+      int idx = ord_find(m.w2);
+      if (idx >= 0) ord_remove(idx);
       break;
     }
     case ABIDES_MSG_MKT_CLOSED: A.flags |= F_MKT_CLOSED; break;
     case ABIDES_MSG_QUERY_LAST_TRADE:
-      if (pay_closed(m)) A.flags |= F_MKT_CLOSED;
-      A.last_trade = m.w[5]; A.flags |= F_HAS_LAST_TRADE;
+      if (pay_closed(m.w0)) A.flags |= F_MKT_CLOSED;
+      A.last_trade = m.w5; A.flags |= F_HAS_LAST_TRADE;
       if (A.flags & F_MKT_CLOSED) A.flags |= F_HAS_DAILY_CLOSE;
       break;
     case ABIDES_MSG_QUERY_SPREAD:                             // querySpread (:482-501)
-      if (pay_closed(m)) A.flags |= F_MKT_CLOSED;
-      A.last_trade = m.w[5]; A.flags |= F_HAS_LAST_TRADE;
+      if (pay_closed(m.w0)) A.flags |= F_MKT_CLOSED;
+      A.last_trade = m.w5; A.flags |= F_HAS_LAST_TRADE;
       if (A.flags & F_MKT_CLOSED) A.flags |= F_HAS_DAILY_CLOSE;
-      A.bid = m.w[1]; A.bid_vol = m.w[2]; A.ask = m.w[3]; A.ask_vol = m.w[4]; A.flags |= F_KNOWN_BOOK;
+      A.bid = m.w1; A.bid_vol = m.w2; A.ask = m.w3; A.ask_vol = m.w4; A.flags |= F_KNOWN_BOOK;
       break;
     case ABIDES_MSG_QUERY_TRANSACTED_VOLUME:
-      if (pay_closed(m)) A.flags |= F_MKT_CLOSED;
+      if (pay_closed(m.w0)) A.flags |= F_MKT_CLOSED;
       if (klass == ABIDES_ADAPTIVE_MM)
-        A.u.mm.transacted_volume = ((long long)(unsigned)m.w[2]) | ((long long)m.w[3] << 32);
+        A.u.mm.transacted_volume = ((long long)(unsigned)m.w2) | ((long long)m.w3 << 32);
       break;
     default: break;
   }
   bool have = (A.flags & F_HAS_OPEN) && (A.flags & F_HAS_CLOSE);
   if (have && !had) {
     long long off;
-    if (klass == ABIDES_ZI || klass == ABIDES_VALUE || klass == ABIDES_NOISE) off = rng_randint(agent_rng(), 0, 100);
+    if (klass == ABIDES_ZI || klass == ABIDES_VALUE || klass == ABIDES_NOISE) off = rng_randint(SID_AGENT, 0, 100);
     else off = ty.wake_up_freq;
-    k_wakeup(a, SM->run.cfg.mkt_open + off);
+    k_wakeup(a, RUN.cfg.mkt_open + off);
   }
 }
 
 // ZI / Value estimator (ZeroIntelligenceAgent.py:163-247, ValueAgent.py:123-186)
 __device__ __noinline__ long long estimator_update(long long obs_t, const abides_agent_type& ty, abm_dd log1mk) {
-  AgentRec& A = SM->st.ag;
-  if (!(A.flags & F_HAS_PREV_WAKE)) { A.u.est.prev_wake = SM->run.cfg.mkt_open; A.flags |= F_HAS_PREV_WAKE; }
+  AgentRec& A = ST.ag;
+  if (!(A.flags & F_HAS_PREV_WAKE)) { A.u.est.prev_wake = RUN.cfg.mkt_open; A.flags |= F_HAS_PREV_WAKE; }
   double base = 1 - ty.kappa;
   double delta = (double)(A.cur_time - A.u.est.prev_wake);
   double pw = abm_pow_with_log(log1mk, base, delta);
@@ -1068,7 +1277,7 @@ __device__ __noinline__ long long estimator_update(long long obs_t, const abides
   r_t += (sigma_tprime / (ty.sigma_n + sigma_tprime)) * (double)obs_t;
   A.u.est.r_t = r_t;
   A.u.est.sigma_t = (ty.sigma_n * A.u.est.sigma_t) / (ty.sigma_n + A.u.est.sigma_t);
-  double d2 = (double)(SM->run.cfg.mkt_close - A.cur_time);
+  double d2 = (double)(RUN.cfg.mkt_close - A.cur_time);
   if (!(d2 > 0)) d2 = 0;
   double pw3 = abm_pow_with_log(log1mk, base, d2);
   double r_T = (1 - pw3) * ty.r_bar;
@@ -1084,20 +1293,19 @@ __device__ __forceinline__ long long round_hundreds(long long hld) {     // int(
 }
 // ZeroIntelligenceAgent.placeOrder (:249-281)
 __device__ __noinline__ void zi_place_order(int a, const abides_agent_type& ty) {
-  AgentRec& A = SM->st.ag;
-  RngH rs = agent_rng();
-  long long obs = oracle_observe(A.cur_time, ty.sigma_n, rs);
+  AgentRec& A = ST.ag;
+  long long obs = oracle_observe(A.cur_time, ty.sigma_n, SID_AGENT);
   long long q = A.holdings / 100;
   bool buy;
   if (q >= ty.q_max) buy = false;
   else if (q <= -ty.q_max) buy = true;
-  else buy = rng_randint(rs, 0, 2) != 0;
-  long long r_T = estimator_update(obs, ty, SM->run.db.type_log1mk[A.type_idx]);
+  else buy = rng_randint(SID_AGENT, 0, 2) != 0;
+  long long r_T = estimator_update(obs, ty, c_db.type_log1mk[A.type_idx]);
   q += ty.q_max - 1;
-  long long row = SM->run.aoff + a;
-  long long theta = SM->run.db.theta[SM->run.cfg.theta_offset + SM->run.db.agent_theta[row] + (buy ? q + 1 : q)];
+  long long row = RUN.aoff + a;
+  long long theta = c_db.theta[RUN.cfg.theta_offset + c_db.agent_theta[row] + (buy ? q + 1 : q)];
   long long v = r_T + theta;
-  long long R = rng_randint(rs, ty.R_min, ty.R_max + 1);
+  long long R = rng_randint(SID_AGENT, ty.R_min, ty.R_max + 1);
   long long p = buy ? v - R : v + R;
   if (buy && A.ask_vol > 0) {
     long long R_ask = v - A.ask;
@@ -1110,11 +1318,11 @@ __device__ __noinline__ void zi_place_order(int a, const abides_agent_type& ty) 
 }
 // ValueAgent.placeOrder (:188-220)
 __device__ __noinline__ void value_place_order(int a, const abides_agent_type& ty) {
-  AgentRec& A = SM->st.ag;
-  long long obs = oracle_observe(A.cur_time, ty.sigma_n, agent_rng());
-  long long r_T = estimator_update(obs, ty, SM->run.db.type_log1mk[A.type_idx]);
+  AgentRec& A = ST.ag;
+  long long obs = oracle_observe(A.cur_time, ty.sigma_n, SID_AGENT);
+  long long r_T = estimator_update(obs, ty, c_db.type_log1mk[A.type_idx]);
   bool buy; long long p;
-  RngH g = extra_rng(ABIDES_STREAM_GLOBAL);
+  const int g = ABIDES_STREAM_GLOBAL;
   if (A.bid > 0 && A.ask > 0) {
     long long mid = (long long)((double)((long long)A.ask + A.bid) / 2);
     long long spread = A.ask > A.bid ? A.ask - A.bid : A.bid - A.ask;
@@ -1131,16 +1339,16 @@ __device__ __noinline__ void value_place_order(int a, const abides_agent_type& t
 }
 // NoiseAgent.placeOrder (:113-123)
 __device__ __noinline__ void noise_place_order(int a) {
-  AgentRec& A = SM->st.ag;
-  bool buy = rng_randint(extra_rng(ABIDES_STREAM_GLOBAL), 0, 2) != 0;
+  AgentRec& A = ST.ag;
+  bool buy = rng_randint(ABIDES_STREAM_GLOBAL, 0, 2) != 0;
   if (buy && A.ask > 0) ta_place_limit(a, A.size, true, A.ask);
   else if (!buy && A.bid > 0) ta_place_limit(a, A.size, false, A.bid);
 }
 // MomentumAgent.placeOrders (:56-66): running prefix sum + ring of the last MOM_RING prefix sums
 __device__ __noinline__ void momentum_place_orders(int a) {
-  AgentRec& A = SM->st.ag;
+  AgentRec& A = ST.ag;
   if (!(A.bid > 0 && A.ask > 0)) return;
-  double* ring = SM->run.db.mom_ring + (size_t)A.u.mom.ring * MOM_RING;
+  double* ring = c_db.mom_ring + (size_t)A.u.mom.ring * MOM_RING;
   double mid = (double)((long long)A.bid + A.ask) / 2;
   double cs = A.u.mom.csum + mid;                         // np.cumsum: sequential float adds
   int n = A.u.mom.n_mids;                                 // index of this mid
@@ -1157,17 +1365,18 @@ __device__ __noinline__ void momentum_place_orders(int a) {
   }
 }
 // AdaptiveMarketMakerAgent (:112-281)
-__device__ void mm_adaptive_update(AgentRec& A, const abides_agent_type& ty) {
+__device__ __forceinline__ void mm_adaptive_update(AgentRec& A, const abides_agent_type& ty) {
   A.u.mm.window_size = A.u.mm.last_spread;
   int t = (int)(long long)rint(ty.level_spacing * A.u.mm.window_size);
   A.u.mm.tick_size = t == 0 ? 1 : t;
 }
-__device__ double sigmoid_stable(double x, double beta) {
+__device__ __noinline__ double sigmoid_stable(double x, double beta) {
   if (x >= 0) { double z = abm_exp(-beta * x); return 1 / (1 + z); }
   double z = abm_exp(beta * x);
   return z / (1 + z);
 }
-__device__ __noinline__ void mm_update_order_size(AgentRec& A, const abides_agent_type& ty) {
+__device__ __noinline__ void mm_update_order_size(const abides_agent_type& ty) {
+  AgentRec& A = ST.ag;
   long long qty = (long long)rint(ty.pov * (double)A.u.mm.transacted_volume);
   if (ty.skew_beta == 0) {
     long long s = qty >= ty.min_order_size ? qty : ty.min_order_size;
@@ -1181,7 +1390,7 @@ __device__ __noinline__ void mm_update_order_size(AgentRec& A, const abides_agen
   }
 }
 __device__ __noinline__ void mm_place_orders(int a, long long mid, const abides_agent_type& ty) {
-  AgentRec& A = SM->st.ag;
+  AgentRec& A = ST.ag;
   long long highest_bid, lowest_ask;
   double w = A.u.mm.window_size;
   if (ty.anchor == 0) { highest_bid = mid - (long long)floor(0.5 * w); lowest_ask = mid + (long long)ceil(0.5 * w); }
@@ -1201,8 +1410,8 @@ __device__ __noinline__ void mm_place_orders(int a, long long mid, const abides_
 }
 
 __device__ __noinline__ void agent_wakeup(int a) {
-  AgentRec& A = SM->st.ag; Hot& h = SM->st.hot;
-  const abides_agent_type& ty = SM->run.db.types[A.type_idx];
+  AgentRec& A = ST.ag; Hot& h = HOT;
+  const abides_agent_type& ty = c_db.types[A.type_idx];
   switch (ty.klass) {
     case ABIDES_ZI: case ABIDES_VALUE: case ABIDES_NOISE: {
       ta_wakeup(a);
@@ -1213,7 +1422,7 @@ __device__ __noinline__ void agent_wakeup(int a) {
       if (ty.klass == ABIDES_NOISE) {
         if (A.u.noise.wakeup_time > h.now) k_wakeup(a, A.u.noise.wakeup_time);
       } else {
-        double dt = rng_exponential(agent_rng(), 1.0 / ty.lambda_a);
+        double dt = rng_exponential(SID_AGENT, 1.0 / ty.lambda_a);
         k_wakeup(a, h.now + (long long)rint(dt));
       }
       if ((A.flags & F_MKT_CLOSED) && !(A.flags & F_HAS_DAILY_CLOSE)) { ta_query_spread(a); ag_set_state(A, ST_AWAITING_SPREAD); return; }
@@ -1230,9 +1439,8 @@ __device__ __noinline__ void agent_wakeup(int a) {
         ta_cancel_all(a);
         h.additional_delay += ty.cancel_limit_delay;
         ta_query_spread(a);
-        EvPay p = pay_zero(ABIDES_MSG_QUERY_TRANSACTED_VOLUME);
-        p.w[2] = (int)(unsigned)(ty.wake_up_freq & 0xffffffffll); p.w[3] = (int)(ty.wake_up_freq >> 32);
-        agent_send(a, p);
+        agent_send(a, ABIDES_MSG_QUERY_TRANSACTED_VOLUME, (int)(unsigned)(ty.wake_up_freq & 0xffffffffll),
+                   (int)(ty.wake_up_freq >> 32), 0, 0);
       }
       return;
     case ABIDES_POV_EXEC:
@@ -1243,10 +1451,11 @@ __device__ __noinline__ void agent_wakeup(int a) {
   }
 }
 
-__device__ __noinline__ void agent_receive(int a, const EvPay& m) {
-  AgentRec& A = SM->st.ag; Hot& h = SM->st.hot;
-  const abides_agent_type& ty = SM->run.db.types[A.type_idx];
-  int code = pay_code(m) & ~ABIDES_MSG_REPLY;
+__device__ __noinline__ void agent_receive(int a, int w0, int w1, int w2, int w3, int w4, int w5) {
+  AgentRec& A = ST.ag; Hot& h = HOT;
+  const abides_agent_type& ty = c_db.types[A.type_idx];
+  Msg m; m.w0 = w0; m.w1 = w1; m.w2 = w2; m.w3 = w3; m.w4 = w4; m.w5 = w5;
+  int code = pay_code(w0) & ~ABIDES_MSG_REPLY;
   ta_receive(a, m, ty.klass, ty);
   switch (ty.klass) {
     case ABIDES_ZI: case ABIDES_VALUE: case ABIDES_NOISE:
@@ -1269,7 +1478,7 @@ __device__ __noinline__ void agent_receive(int a, const EvPay& m) {
       long long mid = A.u.mm.last_mid;
       if (ty.window_size < 0) mm_adaptive_update(A, ty);
       if (code == ABIDES_MSG_QUERY_TRANSACTED_VOLUME && (A.flags & F_MM_AWAIT_TV)) {
-        mm_update_order_size(A, ty);
+        mm_update_order_size(ty);
         A.flags &= ~F_MM_AWAIT_TV;
       }
       if (code == ABIDES_MSG_QUERY_SPREAD && (A.flags & F_MM_AWAIT_SPREAD)) {
@@ -1299,76 +1508,59 @@ __device__ __noinline__ void agent_receive(int a, const EvPay& m) {
 // ----------------------------------------------------------------------------------------------
 // ExchangeAgent (agent/ExchangeAgent.py:113-283, :398-411)
 // ----------------------------------------------------------------------------------------------
-struct ExchSend {
-  __device__ void operator()(int rcpt, const EvPay& p) const {
-    int code = pay_code(p);
-    long long delay = (code == ABIDES_MSG_ORDER_ACCEPTED || code == ABIDES_MSG_ORDER_CANCELLED ||
-                       code == ABIDES_MSG_ORDER_EXECUTED) ? SM->run.cfg.exch_pipeline_delay : 0;
-    k_send(0, rcpt, p, delay);
-  }
-};
-
-__device__ __noinline__ void exchange_receive(const EvPay& m) {
-  Hot& h = SM->st.hot;
-  const abides_instance_cfg* cfg = &SM->run.cfg;
-  ExchSend send;
+__device__ __noinline__ void exchange_receive(int w0, int w1, int w2, int w3, int w4, int w5) {
+  Hot& h = HOT;
+  const abides_instance_cfg& cfg = RUN.cfg;
   h.exch_cur_time = h.now;
-  h.exch_cd = cfg->exch_computation_delay;
-  int code = pay_code(m), sender = m.w[1];
-  bool is_order = code == ABIDES_MSG_LIMIT_ORDER || code == ABIDES_MSG_MARKET_ORDER || code == ABIDES_MSG_CANCEL_ORDER ||
-                  code == ABIDES_MSG_MODIFY_ORDER;
-  bool is_query = code == ABIDES_MSG_QUERY_LAST_TRADE || code == ABIDES_MSG_QUERY_SPREAD ||
-                  code == ABIDES_MSG_QUERY_ORDER_STREAM || code == ABIDES_MSG_QUERY_TRANSACTED_VOLUME;
-  bool closed = h.now > cfg->mkt_close;
-  int cflag = closed ? 1 << 8 : 0;
-  if (closed && !is_query) { send(sender, pay_zero(ABIDES_MSG_MKT_CLOSED)); return; }
-  int oid = m.w[2];
+  h.exch_cd = cfg.exch_computation_delay;
+  const int code = pay_code(w0), sender = w1;
+  const bool is_order = code == ABIDES_MSG_LIMIT_ORDER || code == ABIDES_MSG_MARKET_ORDER || code == ABIDES_MSG_CANCEL_ORDER ||
+                        code == ABIDES_MSG_MODIFY_ORDER;
+  const bool is_query = code == ABIDES_MSG_QUERY_LAST_TRADE || code == ABIDES_MSG_QUERY_SPREAD ||
+                        code == ABIDES_MSG_QUERY_ORDER_STREAM || code == ABIDES_MSG_QUERY_TRANSACTED_VOLUME;
+  const bool closed = h.now > cfg.mkt_close;
+  const int cflag = closed ? 1 << 8 : 0;
+  if (closed && !is_query) { k_send(0, sender, 0, ABIDES_MSG_MKT_CLOSED, 0, 0, 0, 0, 0); return; }
+  int oid = w2;
   if (is_order) {
-    if (cfg->exch_log_orders && oid == 0) h.next_order_id++;
+    if (cfg.exch_log_orders && oid == 0) h.next_order_id++;
     if (oid == 0) oid = (int)h.next_order_id++;
   }
   switch (code) {
     case ABIDES_MSG_WHEN_MKT_OPEN:
       h.exch_cd = 0;
-      send(sender, pay_zero(ABIDES_MSG_WHEN_MKT_OPEN | ABIDES_MSG_REPLY));
+      k_send(0, sender, 0, ABIDES_MSG_WHEN_MKT_OPEN | ABIDES_MSG_REPLY, 0, 0, 0, 0, 0);
       break;
     case ABIDES_MSG_WHEN_MKT_CLOSE:
       h.exch_cd = 0;
-      send(sender, pay_zero(ABIDES_MSG_WHEN_MKT_CLOSE | ABIDES_MSG_REPLY));
+      k_send(0, sender, 0, ABIDES_MSG_WHEN_MKT_CLOSE | ABIDES_MSG_REPLY, 0, 0, 0, 0, 0);
       break;
-    case ABIDES_MSG_QUERY_LAST_TRADE: {
-      EvPay r = pay_zero((ABIDES_MSG_QUERY_LAST_TRADE | ABIDES_MSG_REPLY) | cflag);
-      r.w[5] = h.last_trade;
-      send(sender, r);
+    case ABIDES_MSG_QUERY_LAST_TRADE:
+      k_send(0, sender, 0, (ABIDES_MSG_QUERY_LAST_TRADE | ABIDES_MSG_REPLY) | cflag, 0, 0, 0, 0, h.last_trade);
       break;
-    }
     case ABIDES_MSG_QUERY_SPREAD: {
-      EvPay r = pay_zero((ABIDES_MSG_QUERY_SPREAD | ABIDES_MSG_REPLY) | cflag);
-      side_inside(book_side(true), r.w[1], r.w[2]);
-      side_inside(book_side(false), r.w[3], r.w[4]);
-      r.w[5] = h.last_trade;
-      send(sender, r);
+      int2 b = side_inside(BID), a = side_inside(ASK);
+      k_send(0, sender, 0, (ABIDES_MSG_QUERY_SPREAD | ABIDES_MSG_REPLY) | cflag, b.x, b.y, a.x, a.y, h.last_trade);
       break;
     }
     case ABIDES_MSG_QUERY_TRANSACTED_VOLUME: {
-      long long lookback = ((long long)(unsigned)m.w[2]) | ((long long)m.w[3] << 32);
+      long long lookback = ((long long)(unsigned)w2) | ((long long)w3 << 32);
       long long vol = book_transacted_volume(h.now, lookback);
-      EvPay r = pay_zero((ABIDES_MSG_QUERY_TRANSACTED_VOLUME | ABIDES_MSG_REPLY) | cflag);
-      r.w[2] = (int)(unsigned)(vol & 0xffffffffll); r.w[3] = (int)(vol >> 32);
-      send(sender, r);
+      k_send(0, sender, 0, (ABIDES_MSG_QUERY_TRANSACTED_VOLUME | ABIDES_MSG_REPLY) | cflag, 0,
+             (int)(unsigned)(vol & 0xffffffffll), (int)(vol >> 32), 0, 0);
       break;
     }
     case ABIDES_MSG_LIMIT_ORDER:
-      book_handle_limit(send, sender, oid, m.w[3], m.w[4], pay_is_buy(m));
+      book_handle_limit<false>(sender, oid, w3, w4, pay_is_buy(w0));
       break;
     case ABIDES_MSG_MARKET_ORDER:
-      book_handle_market(send, sender, m.w[4], pay_is_buy(m));
+      book_handle_market<false>(sender, w4, pay_is_buy(w0));
       break;
     case ABIDES_MSG_CANCEL_ORDER:
-      book_cancel(send, sender, oid, m.w[3], pay_is_buy(m));
+      book_cancel<false>(sender, oid, w3, pay_is_buy(w0));
       break;
     case ABIDES_MSG_MODIFY_ORDER:
-      book_modify(send, sender, oid, m.w[3], m.w[5], pay_is_buy(m));
+      book_modify<false>(sender, oid, w3, w5, pay_is_buy(w0));
       break;
     default: break;
   }
@@ -1377,32 +1569,32 @@ __device__ __noinline__ void exchange_receive(const EvPay& m) {
 // ----------------------------------------------------------------------------------------------
 // trace of a dispatched event (layout of include/abides_b200.h: abides_trace_rec)
 // ----------------------------------------------------------------------------------------------
-__device__ __noinline__ void trace_event(const EvKey& k, const EvPay& m) {
-  int rcpt = (int)(k.k2 >> 33);
-  if ((k.k2 >> 32) & 1) { trace_write(k.t, rcpt, 0, 0, 0, 0, 0); return; }
-  int full = pay_code(m), code = full & ~ABIDES_MSG_REPLY;
+__device__ __noinline__ void trace_event(long long t, unsigned long long k2, int w0, int w1, int w2, int w3, int w4, int w5) {
+  int rcpt = (int)(k2 >> 33);
+  if ((k2 >> 32) & 1) { trace_write(t, rcpt, 0, 0, 0, 0, 0); return; }
+  int full = pay_code(w0), code = full & ~ABIDES_MSG_REPLY;
   long long p0 = 0, p1 = 0, p2 = 0, p3 = 0;
   if (rcpt == 0) {
-    p0 = m.w[1];
+    p0 = w1;
     if (code == ABIDES_MSG_LIMIT_ORDER || code == ABIDES_MSG_MARKET_ORDER || code == ABIDES_MSG_CANCEL_ORDER ||
         code == ABIDES_MSG_MODIFY_ORDER) {
-      p1 = m.w[2]; p2 = m.w[3]; p3 = pay_is_buy(m) ? m.w[4] : -(long long)m.w[4];
-      if (code == ABIDES_MSG_CANCEL_ORDER) p3 = pay_is_buy(m) ? 1 : -1;
-    } else if (code == ABIDES_MSG_QUERY_SPREAD) p1 = m.w[2];
+      p1 = w2; p2 = w3; p3 = pay_is_buy(w0) ? w4 : -(long long)w4;
+      if (code == ABIDES_MSG_CANCEL_ORDER) p3 = pay_is_buy(w0) ? 1 : -1;
+    } else if (code == ABIDES_MSG_QUERY_SPREAD) p1 = w2;
   } else {
     switch (code) {
       case ABIDES_MSG_ORDER_ACCEPTED: case ABIDES_MSG_ORDER_EXECUTED: case ABIDES_MSG_ORDER_CANCELLED:
       case ABIDES_MSG_ORDER_MODIFIED:
-        p0 = m.w[2]; p1 = m.w[3]; p2 = pay_is_buy(m) ? m.w[4] : -(long long)m.w[4]; p3 = m.w[5]; break;
-      case ABIDES_MSG_QUERY_SPREAD: p0 = m.w[1]; p1 = m.w[2]; p2 = m.w[3]; p3 = m.w[4]; break;
-      case ABIDES_MSG_WHEN_MKT_OPEN: p0 = SM->run.cfg.mkt_open; break;
-      case ABIDES_MSG_WHEN_MKT_CLOSE: p0 = SM->run.cfg.mkt_close; break;
-      case ABIDES_MSG_QUERY_TRANSACTED_VOLUME: p0 = ((long long)(unsigned)m.w[2]) | ((long long)m.w[3] << 32); break;
-      case ABIDES_MSG_QUERY_LAST_TRADE: p0 = m.w[5]; break;
+        p0 = w2; p1 = w3; p2 = pay_is_buy(w0) ? w4 : -(long long)w4; p3 = w5; break;
+      case ABIDES_MSG_QUERY_SPREAD: p0 = w1; p1 = w2; p2 = w3; p3 = w4; break;
+      case ABIDES_MSG_WHEN_MKT_OPEN: p0 = RUN.cfg.mkt_open; break;
+      case ABIDES_MSG_WHEN_MKT_CLOSE: p0 = RUN.cfg.mkt_close; break;
+      case ABIDES_MSG_QUERY_TRANSACTED_VOLUME: p0 = ((long long)(unsigned)w2) | ((long long)w3 << 32); break;
+      case ABIDES_MSG_QUERY_LAST_TRADE: p0 = w5; break;
       default: break;
     }
   }
-  trace_write(k.t, rcpt, full, p0, p1, p2, p3);
+  trace_write(t, rcpt, full, p0, p1, p2, p3);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -1410,35 +1602,35 @@ __device__ __noinline__ void trace_event(const EvKey& k, const EvPay& m) {
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void rec_load(int a) {
   __syncwarp();
-  const unsigned* src = reinterpret_cast<const unsigned*>(&SM->run.db.agents[SM->run.aoff + a]);
-  reinterpret_cast<unsigned*>(&SM->st.ag)[LANE] = src[LANE];
-  SM->run.cur_agent = a;
+  const unsigned* src = reinterpret_cast<const unsigned*>(&RUN.agents[a]);
+  reinterpret_cast<unsigned*>(&ST.ag)[LANE] = src[LANE];
+  RUN.cur_agent = a;
   __syncwarp();
 }
 __device__ __forceinline__ void rec_store(int a) {
   __syncwarp();
-  unsigned* dst = reinterpret_cast<unsigned*>(&SM->run.db.agents[SM->run.aoff + a]);
-  dst[LANE] = reinterpret_cast<const unsigned*>(&SM->st.ag)[LANE];
+  unsigned* dst = reinterpret_cast<unsigned*>(&RUN.agents[a]);
+  dst[LANE] = reinterpret_cast<const unsigned*>(&ST.ag)[LANE];
   __syncwarp();
 }
 
 // kernelStopping in id order (Kernel.py:289-291; TradingAgent.py:122-147 and subclasses)
 __device__ __noinline__ void finalize() {
-  Hot& h = SM->st.hot;
-  long long slowest = h.exch_busy > SM->run.cfg.start_time ? h.exch_busy : SM->run.cfg.start_time;
-  for (int a = 1; a < SM->run.n_agents; a++) {
+  Hot& h = HOT;
+  long long slowest = h.exch_busy > RUN.cfg.start_time ? h.exch_busy : RUN.cfg.start_time;
+  for (int a = 1; a < RUN.n_agents; a++) {
     rec_load(a);
-    AgentRec& A = SM->st.ag;
-    const abides_agent_type& ty = SM->run.db.types[A.type_idx];
+    AgentRec& A = ST.ag;
+    const abides_agent_type& ty = c_db.types[A.type_idx];
     if (A.busy > slowest) slowest = A.busy;
     long long cash = A.cash;
     if (A.holdings != 0) cash += (long long)A.last_trade * A.holdings;
     double fv = nan("");
     if (ty.klass == ABIDES_ZI) {
       long long H = round_hundreds(A.holdings);
-      long long rT = oracle_observe(A.cur_time, 0, agent_rng());
+      long long rT = oracle_observe(A.cur_time, 0, SID_AGENT);
       long long surplus = 0;
-      const int* th = SM->run.db.theta + SM->run.cfg.theta_offset + SM->run.db.agent_theta[SM->run.aoff + a];
+      const int* th = c_db.theta + RUN.cfg.theta_offset + c_db.agent_theta[RUN.aoff + a];
       if (H > 0) for (long long x = 1; x <= H; x++) surplus += th[x + ty.q_max - 1];
       else if (H < 0) { for (long long x = H + 1; x <= 0; x++) surplus += th[x + ty.q_max - 1]; surplus = -surplus; }
       surplus += rT * H;
@@ -1446,7 +1638,7 @@ __device__ __noinline__ void finalize() {
       fv = (double)surplus;
     } else if (ty.klass == ABIDES_VALUE) {
       long long H = round_hundreds(A.holdings);
-      long long rT = oracle_observe(A.cur_time, 0, agent_rng());
+      long long rT = oracle_observe(A.cur_time, 0, SID_AGENT);
       long long surplus = rT * H + A.cash - ty.starting_cash;
       fv = (double)surplus / (double)ty.starting_cash;
     } else if (ty.klass == ABIDES_NOISE) {
@@ -1461,12 +1653,12 @@ __device__ __noinline__ void finalize() {
     if (LANE == 0) {
       abides_agent_result r;
       r.cash = A.cash; r.holdings = A.holdings; r.marked_to_market = cash; r.final_valuation = fv;
-      SM->run.db.ares[SM->run.aoff + a] = r;
+      c_db.ares[RUN.aoff + a] = r;
     }
   }
   if (LANE == 0) {
     abides_agent_result r; r.cash = 0; r.holdings = 0; r.marked_to_market = 0; r.final_valuation = nan("");
-    SM->run.db.ares[SM->run.aoff] = r;
+    c_db.ares[RUN.aoff] = r;
     abides_instance_result R;
     memset(&R, 0, sizeof R);
     R.ttl_messages = h.ttl; R.delivered = h.delivered; R.final_time = h.now;
@@ -1475,9 +1667,9 @@ __device__ __noinline__ void finalize() {
     R.final_fundamental = (long long)h.or_pv;
     R.n_orders = h.next_order_id; R.n_fills = h.n_fills; R.traded_volume = h.volume;
     R.status = h.status; R.queue_peak = h.queue_peak; R.book_peak_orders = h.book_peak_orders;
-    SM->run.db.res[SM->run.inst] = R;
+    c_db.res[RUN.inst] = R;
   }
-  SM->run.cur_agent = -1;
+  RUN.cur_agent = -1;
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -1485,7 +1677,8 @@ __device__ __noinline__ void finalize() {
 // ----------------------------------------------------------------------------------------------
 
 // one warp per instance: build the initial device state (Kernel.runner prologue, Kernel.py:97-172)
-__global__ void __launch_bounds__(32) init_kernel(DevBatch db) {
+__global__ void __launch_bounds__(32) init_kernel() {
+  const DevBatch& db = c_db;
   int inst = blockIdx.x, lane = threadIdx.x;
   if (inst >= db.n_instances) return;
   const abides_instance_cfg* cfg = &db.cfg[inst];
@@ -1495,8 +1688,8 @@ __global__ void __launch_bounds__(32) init_kernel(DevBatch db) {
   // zero the persistent block
   for (size_t i = lane; i < sizeof(InstShared) / 4; i += 32) reinterpret_cast<unsigned*>(G)[i] = 0;
   __syncwarp();
-  EvKey* fk = db.far_keys + (size_t)inst * db.far_cap;
-  EvPay* fp = db.far_pay + (size_t)inst * db.far_cap;
+  EvKey* fk = db.b_keys + (size_t)inst * db.b_cap;
+  EvPay* fp = db.b_pay + (size_t)inst * db.b_cap;
   for (int a = lane; a < n; a += 32) {
     long long row = aoff + a;
     AgentRec A;
@@ -1509,9 +1702,9 @@ __global__ void __launch_bounds__(32) init_kernel(DevBatch db) {
     A.size = (int)db.size[row];
     long long stream = aoff + (long long)ABIDES_EXTRA_STREAMS * inst + a;
     if (db.rng_mode == ABIDES_RNG_MT19937) {
-      A.rng_pos = db.mt_pos[stream];
-      A.gauss = db.mt_gauss[stream];
-      if (db.mt_has_gauss[stream]) A.flags |= F_HAS_GAUSS;
+      A.rng.pos = db.mt_pos[stream];
+      A.rng.gauss = db.mt_gauss[stream];
+      A.rng.flags = db.mt_has_gauss[stream] ? 1u : 0u;
     }
     switch (ty.klass) {
       case ABIDES_ZI: case ABIDES_VALUE: A.u.est.r_t = ty.r_bar; A.u.est.sigma_t = 0; break;
@@ -1527,7 +1720,7 @@ __global__ void __launch_bounds__(32) init_kernel(DevBatch db) {
       default: break;
     }
     db.agents[row] = A;
-    // Agent.kernelStarting: setWakeup(startTime) (agent/Agent.py:77)
+    // Agent.kernelStarting: setWakeup(startTime) (agent/Agent.py:77) -- all start in list B
     EvKey k; k.t = cfg->start_time; k.k2 = ((unsigned long long)(unsigned)a << 33) | (1ull << 32);
     fk[a] = k;
     EvPay p;
@@ -1543,9 +1736,10 @@ __global__ void __launch_bounds__(32) init_kernel(DevBatch db) {
     h.exch_cur_time = cfg->start_time;
     h.or_pt = cfg->mkt_open; h.or_pv = cfg->r_bar;
     h.ms_time = cfg->megashock_time0; h.ms_value = cfg->megashock_value0;
-    h.near_limit_t = LLONG_MIN; h.near_limit_k = 0;
-    h.dT = 1000000000ll;
-    h.n_far_total = n; h.n_far_live = n; h.queue_peak = n;
+    h.lim_t = LLONG_MIN; h.lim_k = 0;
+    h.hz_t = LLONG_MIN; h.hz_k = 0;
+    h.span[0] = 1000000000ll; h.span[1] = 64000000000ll;
+    h.l_total[1] = n; h.l_live[1] = n; h.queue_peak = n;
     h.last_trade = (int)cfg->r_bar; h.has_last_trade = 1;
     for (int s = 0; s < ABIDES_EXTRA_STREAMS; s++) {
       long long stream = aoff + (long long)ABIDES_EXTRA_STREAMS * inst + n + s;
@@ -1557,81 +1751,118 @@ __global__ void __launch_bounds__(32) init_kernel(DevBatch db) {
   }
 }
 
-__global__ void init_types_kernel(DevBatch db) {
+__global__ void init_types_kernel() {
+  const DevBatch& db = c_db;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= db.n_types) return;
   double base = 1 - db.types[i].kappa;
   db.type_log1mk[i] = (base > 0 && base != 1.0) ? abm_log_dd(base) : abm_mk(0.0, 0.0);
 }
 
+__device__ __forceinline__ void run_setup(int inst) {
+  const DevBatch& db = c_db;
+  Run& r = RUN;
+  r.cfg = db.cfg[inst];
+  r.lk[0] = db.a_keys + (size_t)inst * A_CAP; r.lp[0] = db.a_pay + (size_t)inst * A_CAP; r.lcap[0] = A_CAP;
+  r.lk[1] = db.b_keys + (size_t)inst * db.b_cap; r.lp[1] = db.b_pay + (size_t)inst * db.b_cap; r.lcap[1] = db.b_cap;
+  r.arena = db.arena + (size_t)inst * db.arena_cap;
+  r.deep[BID] = db.deep_book + (size_t)inst * 2 * db.deep_cap; r.deep[ASK] = r.deep[BID] + db.deep_cap;
+  r.dseq[BID] = db.deep_seq + (size_t)inst * 2 * db.deep_cap; r.dseq[ASK] = r.dseq[BID] + db.deep_cap;
+  r.txn_log = db.txn_log + (size_t)inst * TXN_CAP;
+  r.unrolled = db.unrolled + (size_t)inst * UNR_CAP;
+  r.trace = db.trace_cap > 0 ? db.trace + (size_t)inst * db.trace_cap : nullptr;
+  r.deep_cap = db.deep_cap;
+  r.aoff = r.cfg.agent_offset; r.inst = inst; r.n_agents = r.cfg.n_agents; r.cur_agent = -1;
+  r.mt0 = db.mt ? db.mt + (size_t)(r.aoff + (long long)ABIDES_EXTRA_STREAMS * inst) * ABIDES_MT_N : nullptr;
+  r.lat_to = db.lat_to + r.aoff; r.lat_from = db.lat_from + r.aoff;
+  r.agents = db.agents + r.aoff;
+  for (int i = 0; i < N_PROF; i++) r.prof[i] = 0;
+}
+
 // the persistent event loop: Kernel.runner (Kernel.py:190-271), one warp per instance
-__global__ void __launch_bounds__(32) sim_kernel(DevBatch db, long long until_time) {
-  int inst = blockIdx.x, lane = threadIdx.x;
-  if (inst >= db.n_instances) return;
-  InstShared* S = &SM->st;
-  InstShared* G = &db.state[inst];
+__global__ void __launch_bounds__(32) sim_kernel(long long until_time) {
+  const int inst = blockIdx.x, lane = threadIdx.x;
+  if (inst >= c_db.n_instances) return;
+  InstShared* G = &c_db.state[inst];
   {
     const int4* src = reinterpret_cast<const int4*>(G);
-    int4* dst = reinterpret_cast<int4*>(S);
+    int4* dst = reinterpret_cast<int4*>(&ST);
     for (int i = lane; i < (int)(sizeof(InstShared) / 16); i += 32) dst[i] = src[i];
   }
-  if (lane == 0) {
-    Run& r = SM->run;
-    r.db = db; r.cfg = db.cfg[inst];
-    r.far_keys = db.far_keys + (size_t)inst * db.far_cap;
-    r.far_pay = db.far_pay + (size_t)inst * db.far_cap;
-    r.arena = db.arena + (size_t)inst * db.arena_cap;
-    r.deep = db.deep_book + (size_t)inst * 2 * db.deep_cap;
-    r.deep_seq = db.deep_seq + (size_t)inst * 2 * db.deep_cap;
-    r.txn_log = db.txn_log + (size_t)inst * TXN_CAP;
-    r.unrolled = db.unrolled + (size_t)inst * UNR_CAP;
-    r.trace = db.trace_cap > 0 ? db.trace + (size_t)inst * db.trace_cap : nullptr;
-    r.aoff = db.cfg[inst].agent_offset; r.inst = inst; r.n_agents = db.cfg[inst].n_agents; r.cur_agent = -1;
-  }
+  if (lane == 0) run_setup(inst);
   __syncwarp();
-  Hot& h = S->hot;
-  const long long stop_time = SM->run.cfg.stop_time;
-  const long long default_cd = SM->run.cfg.default_computation_delay;
+  Hot& h = HOT;
+  const long long stop_time = RUN.cfg.stop_time;
+  const long long default_cd = RUN.cfg.default_computation_delay;
+  const bool tracing = RUN.trace != nullptr;
+#ifdef ABIDES_PROFILE
+  const long long prof_start = clock64();
+#endif
 
   if (!h.done) {
     bool finished = false;
     for (;;) {
+      PROF_T0();
       if (h.status != 0) { finished = true; break; }
       if (!(h.now <= stop_time)) { finished = true; break; }
       if (h.n_near == 0) {
-        if (h.n_far_live == 0) { finished = true; break; }
+        if (h.l_live[0] + h.l_live[1] == 0) { finished = true; break; }
         q_refill();
+        PROF_ADD(P_REFILL);
         if (h.n_near == 0) { finished = true; break; }
       }
-      int idx = near_argext(false);
-      EvKey k = S->nkey[idx];
-      if (k.t > until_time) break;
-      EvPay m = S->npay[idx];
-      near_remove(idx);
-      h.now = k.t;
+      const int idx = near_argmin();
+      const long long t = ST.nt[idx];
+      const unsigned long long k2 = ST.nk[idx];
+      if (t > until_time) break;
+      h.now = t;
       h.ttl++;
       h.additional_delay = 0;
-      int rcpt = (int)(k.k2 >> 33);
-      bool is_wakeup = (k.k2 >> 32) & 1;
+      const int rcpt = (int)(k2 >> 33);
+      const bool is_wakeup = (k2 >> 32) & 1;
+      PROF_ADD(P_POP);
+      if (rcpt != 0 && rcpt != RUN.cur_agent) { rec_load(rcpt); PROF_CNT(P_N_RECLOAD); PROF_ADD(P_REC); }
+      const long long busy = rcpt == 0 ? h.exch_busy : ST.ag.busy;
+      if (busy > t) {
+        // agent in the future: re-queue at its busy time with the same uniq (Kernel.py:217-223)
+        PROF_CNT(P_N_REQUEUE);
+        if (key_less(busy, k2, h.lim_t, h.lim_k)) {
+          __syncwarp();
+          if (lane == 0) ST.nt[idx] = busy;
+          __syncwarp();
+        } else {
+          const int4 p0 = *reinterpret_cast<const int4*>(&ST.npay[idx].w[0]);
+          const int4 p1 = *reinterpret_cast<const int4*>(&ST.npay[idx].w[4]);
+          near_remove(idx);
+          q_push(busy, k2, p0.x, p0.y, p0.z, p0.w, p1.x, p1.y);
+        }
+        PROF_ADD(P_REQUEUE);
+        continue;
+      }
+      const int4 p0 = *reinterpret_cast<const int4*>(&ST.npay[idx].w[0]);
+      const int4 p1 = *reinterpret_cast<const int4*>(&ST.npay[idx].w[4]);
+      near_remove(idx);
+      h.delivered++;
+      if (tracing) trace_event(t, k2, p0.x, p0.y, p0.z, p0.w, p1.x, p1.y);
       if (rcpt == 0) {
-        if (h.exch_busy > h.now) { k.t = h.exch_busy; q_push(k, m); continue; }
-        h.exch_busy = h.now;
-        h.delivered++;
-        if (SM->run.trace) trace_event(k, m);
-        if (is_wakeup) h.exch_cur_time = h.now;
-        else exchange_receive(m);
+        h.exch_busy = t;
+        if (is_wakeup) h.exch_cur_time = t;
+        else exchange_receive(p0.x, p0.y, p0.z, p0.w, p1.x, p1.y);
         h.exch_busy += h.exch_cd + h.additional_delay;
+#ifdef ABIDES_PROFILE
+        { int c = pay_code(p0.x);
+          PROF_ADD(c == ABIDES_MSG_LIMIT_ORDER ? P_EXCH_ORDER : c == ABIDES_MSG_CANCEL_ORDER ? P_EXCH_CANCEL :
+                   c == ABIDES_MSG_QUERY_SPREAD ? P_EXCH_QUERY : P_EXCH_OTHER); }
+#endif
       } else {
-        rec_load(rcpt);
-        AgentRec& A = S->ag;
-        if (A.busy > h.now) { k.t = A.busy; q_push(k, m); continue; }
-        A.busy = h.now;
-        h.delivered++;
-        if (SM->run.trace) trace_event(k, m);
+        ST.ag.busy = t;
         if (is_wakeup) agent_wakeup(rcpt);
-        else agent_receive(rcpt, m);
-        A.busy += default_cd + h.additional_delay;
+        else agent_receive(rcpt, p0.x, p0.y, p0.z, p0.w, p1.x, p1.y);
+        ST.ag.busy += default_cd + h.additional_delay;
         rec_store(rcpt);
+#ifdef ABIDES_PROFILE
+        PROF_ADD(is_wakeup ? P_AG_WAKE : (pay_code(p0.x) & ~ABIDES_MSG_REPLY) == ABIDES_MSG_QUERY_SPREAD ? P_AG_SPREAD : P_AG_OTHER);
+#endif
       }
     }
     if (finished) {
@@ -1640,9 +1871,16 @@ __global__ void __launch_bounds__(32) sim_kernel(DevBatch db, long long until_ti
     }
   }
   __syncwarp();
+#ifdef ABIDES_PROFILE
+  if (lane == 0) {
+    RUN.prof[P_TOTAL] += (unsigned long long)(clock64() - prof_start);
+    for (int i = 0; i < N_PROF; i++) atomicAdd(&c_db.prof[i], RUN.prof[i]);
+  }
+  __syncwarp();
+#endif
   {
     int4* dst = reinterpret_cast<int4*>(G);
-    const int4* src = reinterpret_cast<const int4*>(S);
+    const int4* src = reinterpret_cast<const int4*>(&ST);
     for (int i = lane; i < (int)(sizeof(InstShared) / 16); i += 32) dst[i] = src[i];
   }
 }
@@ -1650,24 +1888,6 @@ __global__ void __launch_bounds__(32) sim_kernel(DevBatch db, long long until_ti
 // ----------------------------------------------------------------------------------------------
 // K2 parity harness: replay recorded order tapes into the book, one warp per book
 // ----------------------------------------------------------------------------------------------
-struct ReplaySend {
-  __device__ void operator()(int rcpt, const EvPay& p) const {
-    Run& r = SM->run;
-    int k = r.rp_counts[r.rp_op];
-    __syncwarp();
-    if (LANE == 0) {
-      if (k < r.rp_max) {
-        abides_book_event e;
-        e.op_index = r.rp_op - r.rp_base; e.kind = pay_code(p); e.agent = rcpt; e.is_buy = pay_is_buy(p) ? 1 : 0;
-        e.order_id = p.w[2]; e.price = p.w[3]; e.qty = p.w[4]; e.fill_price = p.w[5];
-        r.rp_events[(size_t)r.rp_op * r.rp_max + k] = e;
-      }
-      r.rp_counts[r.rp_op] = k + 1;
-    }
-    __syncwarp();
-  }
-};
-
 __global__ void __launch_bounds__(32) replay_kernel(int n_books, const long long* op_offset, const abides_book_op* ops,
                                                     int stream_history, int max_events, abides_book_event* events,
                                                     int* counts, abides_book_state* states, BookOrd* deep, int* deep_seq,
@@ -1677,39 +1897,36 @@ __global__ void __launch_bounds__(32) replay_kernel(int n_books, const long long
   for (int i = lane; i < (int)(sizeof(Smem) / 4); i += 32) reinterpret_cast<unsigned*>(SM)[i] = 0;
   __syncwarp();
   if (lane == 0) {
-    Run& r = SM->run;
-    r.db.deep_cap = deep_cap;
+    Run& r = RUN;
     r.cfg.stream_history = stream_history;
-    r.deep = deep + (size_t)b * 2 * deep_cap;
-    r.deep_seq = deep_seq + (size_t)b * 2 * deep_cap;
+    r.deep[BID] = deep + (size_t)b * 2 * deep_cap; r.deep[ASK] = r.deep[BID] + deep_cap;
+    r.dseq[BID] = deep_seq + (size_t)b * 2 * deep_cap; r.dseq[ASK] = r.dseq[BID] + deep_cap;
+    r.deep_cap = deep_cap;
     r.txn_log = nullptr;
     r.rp_events = events; r.rp_counts = counts; r.rp_max = max_events; r.rp_base = (int)op_offset[b];
-    SM->st.hot.next_order_id = 1 << 30;          // ids of market-order children: outside the tape's id space
+    HOT.next_order_id = 1 << 30;                 // ids of market-order children: outside the tape's id space
   }
   __syncwarp();
-  Hot& h = SM->st.hot;
-  ReplaySend send;
+  Hot& h = HOT;
   for (long long i = op_offset[b]; i < op_offset[b + 1]; i++) {
     abides_book_op op = ops[i];
     __syncwarp();
-    if (lane == 0) { SM->run.rp_op = (int)i; counts[i] = 0; }
+    if (lane == 0) { RUN.rp_op = (int)i; counts[i] = 0; }
     __syncwarp();
     h.now = op.time;
     bool buy = op.is_buy != 0;
     switch (op.kind) {
-      case ABIDES_MSG_LIMIT_ORDER: book_handle_limit(send, op.agent, (int)op.order_id, (int)op.price, (int)op.qty, buy); break;
-      case ABIDES_MSG_MARKET_ORDER: book_handle_market(send, op.agent, (int)op.qty, buy); break;
-      case ABIDES_MSG_CANCEL_ORDER: book_cancel(send, op.agent, (int)op.order_id, (int)op.price, buy); break;
-      case ABIDES_MSG_MODIFY_ORDER: book_modify(send, op.agent, (int)op.order_id, (int)op.price, (int)op.new_qty, buy); break;
+      case ABIDES_MSG_LIMIT_ORDER: book_handle_limit<true>(op.agent, (int)op.order_id, (int)op.price, (int)op.qty, buy); break;
+      case ABIDES_MSG_MARKET_ORDER: book_handle_market<true>(op.agent, (int)op.qty, buy); break;
+      case ABIDES_MSG_CANCEL_ORDER: book_cancel<true>(op.agent, (int)op.order_id, (int)op.price, buy); break;
+      case ABIDES_MSG_MODIFY_ORDER: book_modify<true>(op.agent, (int)op.order_id, (int)op.price, (int)op.new_qty, buy); break;
       default: break;
     }
-    int bp, bv, ap, av;
-    side_inside(book_side(true), bp, bv);
-    side_inside(book_side(false), ap, av);
-    int nbl = side_levels(book_side(true)), nal = side_levels(book_side(false));
+    int2 bi = side_inside(BID), ai = side_inside(ASK);
+    int nbl = side_levels(BID), nal = side_levels(ASK);
     if (lane == 0) {
       abides_book_state st;
-      st.bid = bp; st.bid_vol = bv; st.ask = ap; st.ask_vol = av;
+      st.bid = bi.x; st.bid_vol = bi.y; st.ask = ai.x; st.ask_vol = ai.y;
       st.last_trade = h.has_last_trade ? h.last_trade : -1;
       st.n_bid_levels = nbl; st.n_ask_levels = nal;
       states[i] = st;
@@ -1800,8 +2017,10 @@ int launch_init(abides_handle* h) {
     CK(cudaMemcpyAsync(d.mt, h->mt_pristine, h->n_streams * ABIDES_MT_N * sizeof(unsigned), cudaMemcpyDeviceToDevice, h->stream));
   CK(cudaMemsetAsync(d.mom_ring, 0, (size_t)(h->n_mom > 0 ? h->n_mom : 1) * MOM_RING * sizeof(double), h->stream));
   CK(cudaMemsetAsync(d.res, 0, (size_t)d.n_instances * sizeof(abides_instance_result), h->stream));
-  init_types_kernel<<<(d.n_types + 63) / 64, 64, 0, h->stream>>>(d);
-  init_kernel<<<d.n_instances, 32, 0, h->stream>>>(d);
+  CK(cudaMemsetAsync(d.prof, 0, N_PROF * sizeof(unsigned long long), h->stream));
+  CK(cudaMemcpyToSymbolAsync(c_db, &d, sizeof(DevBatch), 0, cudaMemcpyHostToDevice, h->stream));
+  init_types_kernel<<<(d.n_types + 63) / 64, 64, 0, h->stream>>>();
+  init_kernel<<<d.n_instances, 32, 0, h->stream>>>();
   CK(cudaGetLastError());
   h->launches_since_load += 2;
   return 0;
@@ -1811,7 +2030,13 @@ int launch_init(abides_handle* h) {
 extern "C" {
 
 const char* abides_last_error(void) { return g_err.c_str(); }
-const char* abides_version(void) { return "abides_b200 0.1 (sm_100a)"; }
+const char* abides_version(void) {
+#ifdef ABIDES_PROFILE
+  return "abides_b200 0.2 (sm_100a, profiling build)";
+#else
+  return "abides_b200 0.2 (sm_100a)";
+#endif
+}
 
 int abides_create(int device, abides_handle** out) {
   if (!out) return fail(ABIDES_EINVAL, "abides_create: out is NULL");
@@ -1887,7 +2112,7 @@ int abides_load(abides_handle* h, const abides_batch* b) {
     free_all(h);
     memset(&d, 0, sizeof d);
     d.n_instances = ni; d.rng_mode = b->rng_mode; d.trace_cap = b->trace_capacity; d.n_types = b->n_types;
-    d.far_cap = 4 * max_agents + 4096;
+    d.b_cap = 4 * max_agents + 4096;
     d.arena_cap = 8 * max_agents + 4096;
     d.deep_cap = 4 * max_agents + 1024;
     abides_instance_cfg* dcfg; abides_agent_type* dty; int* dat; double *dlt, *dlf; long long *dsz, *dwk; int *dath, *dth, *dmi;
@@ -1915,8 +2140,11 @@ int abides_load(abides_handle* h, const abides_batch* b) {
     if ((rc = dev_alloc(h, &d.type_log1mk, (size_t)b->n_types))) return rc;
     if ((rc = dev_alloc(h, &d.agents, (size_t)na))) return rc;
     if ((rc = dev_alloc(h, &d.state, (size_t)ni))) return rc;
-    if ((rc = dev_alloc(h, &d.far_keys, (size_t)ni * d.far_cap))) return rc;
-    if ((rc = dev_alloc(h, &d.far_pay, (size_t)ni * d.far_cap))) return rc;
+    if ((rc = dev_alloc(h, &d.a_keys, (size_t)ni * A_CAP))) return rc;
+    if ((rc = dev_alloc(h, &d.a_pay, (size_t)ni * A_CAP))) return rc;
+    if ((rc = dev_alloc(h, &d.b_keys, (size_t)ni * d.b_cap))) return rc;
+    if ((rc = dev_alloc(h, &d.b_pay, (size_t)ni * d.b_cap))) return rc;
+    if ((rc = dev_alloc(h, &d.prof, (size_t)N_PROF))) return rc;
     if ((rc = dev_alloc(h, &d.arena, (size_t)ni * d.arena_cap))) return rc;
     if ((rc = dev_alloc(h, &d.deep_book, (size_t)ni * 2 * d.deep_cap))) return rc;
     if ((rc = dev_alloc(h, &d.deep_seq, (size_t)ni * 2 * d.deep_cap))) return rc;
@@ -1976,13 +2204,23 @@ int abides_run(abides_handle* h, int64_t until_time) {
   if (!h || !h->loaded) return fail(ABIDES_ESTATE, "abides_run: no batch loaded");
   CK(cudaSetDevice(h->device));
   CK(cudaEventRecord(h->ev0, h->stream));
-  sim_kernel<<<h->n_instances, 32, sizeof(Smem), h->stream>>>(h->db, (long long)until_time);
+  CK(cudaMemcpyToSymbolAsync(c_db, &h->db, sizeof(DevBatch), 0, cudaMemcpyHostToDevice, h->stream));
+  sim_kernel<<<h->n_instances, 32, sizeof(Smem), h->stream>>>((long long)until_time);
   CK(cudaGetLastError());
   CK(cudaEventRecord(h->ev1, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
   h->last_launches = 1;
   h->launches_since_load += 1;
+  return 0;
+}
+
+int abides_read_profile(abides_handle* h, uint64_t* out, int32_t n) {
+  if (!h || !h->loaded || !out) return fail(ABIDES_ESTATE, "abides_read_profile: no batch loaded");
+  CK(cudaSetDevice(h->device));
+  unsigned long long tmp[N_PROF];
+  CK(cudaMemcpy(tmp, h->db.prof, sizeof tmp, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < n; i++) out[i] = i < N_PROF ? tmp[i] : 0;
   return 0;
 }
 

@@ -1,0 +1,7 @@
+#!/bin/bash
+# one GPU round-trip: parity tests, then throughput checks and the phase profile
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q 2>&1 | tail -15
+python scripts/gpu_zi1000.py 1024 sparse_zi_1000 2>&1 | tail -12
+python scripts/gpu_zi1000.py 1024 sparse_zi_100 2>&1 | grep -E "run s|msg/s|mismatch"
+python scripts/gpu_prof.py 1024 sparse_zi_1000 2>&1 | tail -22
