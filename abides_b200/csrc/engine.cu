@@ -8,15 +8,19 @@
 // the latency models (model/LatencyModel.py:113-145, Kernel.py:378-381) and numpy's legacy
 // MT19937 transforms -- as a single persistent kernel in which every warp owns one instance:
 //
-//   * event queue  : three tiers ordered by two moving key limits.  "near" (shared memory, every
-//                    event below near_limit; pop = redux arg-min), list A (HBM, events below the
-//                    horizon) and list B (HBM, the rest).  A and B are unsorted append-only lists
-//                    with tombstones, scanned 32 keys per coalesced load only when the tier above
-//                    runs dry: B -> A pulls a few hundred events, A -> near a few dozen, so the
-//                    thousands of long-dated wakeups in B are touched once per few thousand pops;
-//   * order book   : both sides as price-time sorted arrays, the best BOOK_TOP entries per side in
-//                    shared memory, the rest reversed in HBM; matching, level sums, inserts and
-//                    cancels are ballot/popc scans and warp-wide shifts;
+//   * event queue  : three tiers ordered by two moving key limits.  "near" (shared memory, <= 32 events
+//                    below near_limit kept SORTED, one per lane: pop = read the tail, insert = ballot
+//                    rank + one warp-wide shift), list A (HBM, events below the horizon) and list B
+//                    (HBM, the rest).  A and B are unsorted append-only lists with tombstones, scanned
+//                    32 keys per coalesced load only when the tier above runs dry: B -> A pulls a few
+//                    hundred events, A -> near a couple of dozen, so the thousands of long-dated
+//                    wakeups in B are touched once per few thousand pops;
+//   * order book   : per side the best <= BOOK_TOP orders price-time sorted in shared memory (matching,
+//                    level sums, inserts and cancels are ballot/popc scans and warp-wide shifts) over
+//                    an unsorted "pool" list in HBM in the same key/payload format as the event lists
+//                    (key = price rank, arrival number | order id), so deep inserts are O(1) appends,
+//                    deep cancels one coalesced key scan, and the pool -> top refill reuses the event
+//                    queue's window selection;
 //   * agent state  : one 128-byte record per agent in HBM, moved to/from shared memory with one
 //                    coalesced transaction per dispatch (skipped when the same agent is dispatched
 //                    again, e.g. busy re-queues); handler code is warp-uniform;
@@ -46,14 +50,17 @@ namespace {
 
 extern __shared__ __align__(128) unsigned char smem_raw[];
 
-constexpr int NEAR_CAP = 128;           // events in the shared-memory tier
-constexpr int FILL_MAX = 64;            // A -> near pulls at most this many ...
-constexpr int FILL_MIN = 16;            // ... and widens its window when it gets fewer
+constexpr int NEAR_CAP = 32;            // events in the shared-memory tier (one per lane, sorted)
+constexpr int FILL_MAX = 24;            // A -> near pulls at most this many ...
+constexpr int FILL_MIN = 8;             // ... and widens its window when it gets fewer
 constexpr int A_CAP = 4096;             // list A capacity per instance
 constexpr int A_FILL_MAX = 384;         // B -> A pulls
 constexpr int A_FILL_MIN = 96;
 constexpr int A_REBALANCE = 2048;       // live entries in A above which the horizon is pulled in
-constexpr int BOOK_TOP = 128;           // orders per side kept in shared memory
+constexpr int BOOK_TOP = 64;            // orders per side kept (sorted) in shared memory
+constexpr int TOP_FILL = 32;            // pool -> top pulls at most this many (one per lane) ...
+constexpr int TOP_FILL_MIN = 8;         // ... and widens its price window when it gets fewer
+enum { L_A = 0, L_B = 1, L_POOL = 2, N_LISTS = 4 };   // HBM lists: event lists A, B; book pools L_POOL + side
 constexpr int MOM_RING = 64;            // >= 51 prefix sums
 constexpr int TXN_CAP = 1 << 16;        // ring of transaction rows since the last volume query (per instance)
 constexpr int UNR_CAP = 1 << 16;        // ring of de-duplicated rows the volume queries sum over
@@ -107,12 +114,15 @@ struct Hot {
   long long next_order_id;
   long long lim_t; unsigned long long lim_k;                    // near_limit
   long long hz_t; unsigned long long hz_k;                      // horizon
-  long long span[2];                                            // adaptive windows: [0] A -> near, [1] B -> A
+  long long span[N_LISTS];                                      // adaptive windows: A -> near, B -> A, pool -> top (x2)
   long long sel_t; unsigned long long sel_k;                    // result of choose_limit
   unsigned uniq;
   int n_near;
-  int l_total[2], l_live[2];            // list A (0) / B (1): slots used, live entries
-  int n_top[2], n_deep[2];              // book: entries per side in shared memory / in HBM
+  int l_total[N_LISTS], l_live[N_LISTS];   // per HBM list: slots used, live entries
+  int n_top[2];                         // book: entries per side in shared memory
+  unsigned near_free;                   // free payload slots of the near tier
+  unsigned book_arr;                    // arrival counter of resting orders (time priority)
+  long long pb_t[2]; unsigned long long pb_k[2];   // per side: lower bound of every pool key
   int last_trade, has_last_trade;
   int arena_top, status, n_trace, queue_peak, book_peak_orders, done;
   int find_idx;                         // result of side_find
@@ -122,11 +132,13 @@ struct Hot {
 };
 
 struct __align__(128) InstShared {      // persisted per instance between launches (abides_run(until))
-  long long nt[NEAR_CAP];
+  long long nt[NEAR_CAP];               // sorted DESCENDING by (nt, nk): entry n_near-1 is the next event
   unsigned long long nk[NEAR_CAP];
+  int nslot[NEAR_CAP];                  // payload slot of each entry
   EvPay npay[NEAR_CAP];
-  BookOrd top[2][BOOK_TOP];
+  BookOrd top[2][BOOK_TOP];             // best first
   int tseq[2][BOOK_TOP];                // history bucket in which each resting order was entered
+  int tarr[2][BOOK_TOP];                // arrival number (time priority across top and pool)
   AgentRec ag;
   Hot hot;
 };
@@ -151,9 +163,8 @@ struct DevBatch {
   InstShared* state;
   EvKey* a_keys; EvPay* a_pay;          // [n_instances][A_CAP]
   EvKey* b_keys; EvPay* b_pay;          // [n_instances][b_cap]
+  EvKey* p_keys; EvPay* p_pay;          // [n_instances][2][deep_cap] book pools
   OpenOrd* arena;
-  BookOrd* deep_book;                   // [n_instances][2][deep_cap]
-  int* deep_seq;                        // [n_instances][2][deep_cap]
   TxnRow* txn_log;                      // [n_instances][TXN_CAP]
   TxnRow* unrolled;                     // [n_instances][UNR_CAP]
   double* mom_ring;
@@ -168,14 +179,14 @@ __constant__ DevBatch c_db;             // uploaded in-stream before every launc
 
 struct Run {                            // per-launch context, shared memory, not persisted
   abides_instance_cfg cfg;
-  EvKey* lk[2]; EvPay* lp[2]; int lcap[2];
-  OpenOrd* arena; BookOrd* deep[2]; int* dseq[2]; TxnRow* txn_log; TxnRow* unrolled;
+  EvKey* lk[N_LISTS]; EvPay* lp[N_LISTS]; int lcap[N_LISTS];
+  OpenOrd* arena; TxnRow* txn_log; TxnRow* unrolled;
   abides_trace_rec* trace;
   unsigned* mt0;                        // MT state of this instance's stream 0 (agent 0)
   const double* lat_to; const double* lat_from;   // this instance's rows
   AgentRec* agents;
   long long aoff;                       // agent_offset
-  int inst, n_agents, deep_cap;
+  int inst, n_agents;
   int cur_agent;                        // agent whose record sits in st.ag (-1 none)
   int rp_op, rp_max, rp_base;           // order-book replay harness: current op, events per op, first op
   abides_book_event* rp_events; int* rp_counts;
@@ -283,16 +294,18 @@ __device__ __forceinline__ unsigned long long philox_key(unsigned long long seed
   return seed * 0x9E3779B97F4A7C15ull + (unsigned long long)stream * 0xD1B54A32D192ED03ull + 0x2545F4914F6CDD1Dull;
 }
 
-__device__ __noinline__ unsigned rng_u32(int sid) {
+__device__ __noinline__ unsigned philox_u32(int sid) {
   RngState& r = rng_state(sid);
-  if (c_db.rng_mode == ABIDES_RNG_PHILOX) {
-    unsigned n = (unsigned)r.pos;
-    unsigned o[4];
-    philox4x32_10(n >> 2, philox_key(RUN.cfg.seed, rng_stream(sid)), o);
-    r.pos = (int)(n + 1);
-    unsigned sel = n & 3u;
-    return sel == 0 ? o[0] : sel == 1 ? o[1] : sel == 2 ? o[2] : o[3];
-  }
+  unsigned n = (unsigned)r.pos;
+  unsigned o[4];
+  philox4x32_10(n >> 2, philox_key(RUN.cfg.seed, rng_stream(sid)), o);
+  r.pos = (int)(n + 1);
+  unsigned sel = n & 3u;
+  return sel == 0 ? o[0] : sel == 1 ? o[1] : sel == 2 ? o[2] : o[3];
+}
+__device__ __noinline__ unsigned rng_u32(int sid) {
+  if (c_db.rng_mode == ABIDES_RNG_PHILOX) return philox_u32(sid);
+  RngState& r = rng_state(sid);
   unsigned* mt = RUN.mt0 + (size_t)rng_stream(sid) * ABIDES_MT_N;
   int p = r.pos;
   if (p >= ABIDES_MT_N) { mt_twist(mt); p = 0; }
@@ -398,72 +411,42 @@ __device__ __noinline__ void list_append(int L, long long t, unsigned long long 
   HOT.l_live[L] += 1;
 }
 
-// warp arg-min of the near keys (ties: the lowest lane's candidate; tied keys are identical events)
-__device__ __forceinline__ int near_argmin() {
-  const int n = HOT.n_near;
-  long long bt = LLONG_MAX; unsigned long long bk = ~0ull; int bi = -1;
-  for (int i = LANE; i < n; i += 32) {
-    long long t = ST.nt[i]; unsigned long long k = ST.nk[i];
-    if (key_less(t, k, bt, bk) || bi < 0) { bt = t; bk = k; bi = i; }
-  }
-  // times are non-negative (ns since the epoch), so unsigned order == signed order
-  unsigned th = (unsigned)((unsigned long long)bt >> 32);
-  unsigned mh = __reduce_min_sync(FULL, th);
-  unsigned tl = th == mh ? (unsigned)bt : 0xffffffffu;
-  unsigned ml = __reduce_min_sync(FULL, tl);
-  bool c = bi >= 0 && th == mh && (unsigned)bt == ml;
-  unsigned m = __ballot_sync(FULL, c);
-  if (__popc(m) > 1) {
-    unsigned kh = c ? (unsigned)(bk >> 32) : 0xffffffffu;
-    unsigned mkh = __reduce_min_sync(FULL, kh);
-    c = c && kh == mkh;
-    unsigned kl = c ? (unsigned)bk : 0xffffffffu;
-    unsigned mkl = __reduce_min_sync(FULL, kl);
-    c = c && kl == mkl;
-    m = __ballot_sync(FULL, c);
-  }
-  return __shfl_sync(FULL, bi, __ffs(m) - 1);
-}
-__device__ __noinline__ int near_argmax() {
-  const int n = HOT.n_near;
-  long long bt = -1; unsigned long long bk = 0; int bi = -1;
-  for (int i = LANE; i < n; i += 32) {
-    long long t = ST.nt[i]; unsigned long long k = ST.nk[i];
-    if (bi < 0 || key_less(bt, bk, t, k)) { bt = t; bk = k; bi = i; }
-  }
-#pragma unroll 1
-  for (int o = 16; o; o >>= 1) {
-    long long ot = __shfl_xor_sync(FULL, bt, o);
-    unsigned long long ok = __shfl_xor_sync(FULL, bk, o);
-    int oi = __shfl_xor_sync(FULL, bi, o);
-    bool better;
-    if (oi < 0) better = false;
-    else if (bi < 0) better = true;
-    else if (ot == bt && ok == bk) better = oi < bi;
-    else better = key_less(bt, bk, ot, ok);
-    if (better) { bt = ot; bk = ok; bi = oi; }
-  }
-  return bi;
-}
-__device__ __forceinline__ void near_remove(int idx) {
-  int last = HOT.n_near - 1;
-  __syncwarp();
-  if (idx != last) {
-    if (LANE == 0) ST.nt[idx] = ST.nt[last];
-    else if (LANE == 1) ST.nk[idx] = ST.nk[last];
-    else if (LANE == 2) *reinterpret_cast<int4*>(&ST.npay[idx].w[0]) = *reinterpret_cast<const int4*>(&ST.npay[last].w[0]);
-    else if (LANE == 3) *reinterpret_cast<int4*>(&ST.npay[idx].w[4]) = *reinterpret_cast<const int4*>(&ST.npay[last].w[4]);
-  }
-  HOT.n_near = last;
-  __syncwarp();
-}
-__device__ __forceinline__ void near_put(int slot, long long t, unsigned long long k2, int w0, int w1, int w2, int w3,
-                                         int w4, int w5) {
-  if (LANE == 0) ST.nt[slot] = t;
-  else if (LANE == 1) ST.nk[slot] = k2;
-  else if (LANE == 2) *reinterpret_cast<int4*>(&ST.npay[slot].w[0]) = make_int4(w0, w1, w2, w3);
+// ---- near tier: <= 32 events sorted descending in shared memory, payloads in free-listed slots ----
+__device__ __forceinline__ int near_alloc(int w0, int w1, int w2, int w3, int w4, int w5) {
+  const unsigned fm = HOT.near_free;
+  const int slot = __ffs(fm) - 1;
+  if (LANE == 2) *reinterpret_cast<int4*>(&ST.npay[slot].w[0]) = make_int4(w0, w1, w2, w3);
   else if (LANE == 3) *reinterpret_cast<int4*>(&ST.npay[slot].w[4]) = make_int4(w4, w5, 0, 0);
+  HOT.near_free = fm & ~(1u << slot);
+  return slot;
+}
+// insert (t, k2) -> payload slot; needs n_near < NEAR_CAP
+__device__ __noinline__ void near_insert(long long t, unsigned long long k2, int slot) {
+  const int n = HOT.n_near, lane = LANE;
+  long long et = 0; unsigned long long ek = 0; int es = 0;
+  bool gt = false;
+  if (lane < n) { et = ST.nt[lane]; ek = ST.nk[lane]; es = ST.nslot[lane]; gt = key_less(t, k2, et, ek); }
+  const int pos = __popc(__ballot_sync(FULL, gt));            // entries above the new key keep their place
+  if (lane >= pos && lane < n) { ST.nt[lane + 1] = et; ST.nk[lane + 1] = ek; ST.nslot[lane + 1] = es; }
+  if (lane == 0) { ST.nt[pos] = t; ST.nk[pos] = k2; ST.nslot[pos] = slot; }
+  HOT.n_near = n + 1;
   __syncwarp();
+}
+// near tier full: hand its largest key (entry 0) to list A and pull near_limit down to it
+__device__ __noinline__ void near_spill() {
+  const int lane = LANE;
+  const long long mt = ST.nt[0]; const unsigned long long mk = ST.nk[0]; const int ms = ST.nslot[0];
+  const int4 p0 = *reinterpret_cast<const int4*>(&ST.npay[ms].w[0]);
+  const int4 p1 = *reinterpret_cast<const int4*>(&ST.npay[ms].w[4]);
+  long long et = 0; unsigned long long ek = 0; int es = 0;
+  if (lane >= 1) { et = ST.nt[lane]; ek = ST.nk[lane]; es = ST.nslot[lane]; }
+  __syncwarp();
+  if (lane >= 1) { ST.nt[lane - 1] = et; ST.nk[lane - 1] = ek; ST.nslot[lane - 1] = es; }
+  HOT.n_near = NEAR_CAP - 1;
+  HOT.near_free |= 1u << ms;
+  __syncwarp();
+  list_append(L_A, mt, mk, p0.x, p0.y, p0.z, p0.w, p1.x, p1.y);
+  HOT.lim_t = mt; HOT.lim_k = mk;
 }
 
 __device__ __noinline__ int list_count_lt(const EvKey* __restrict__ keys, int n, long long pt, unsigned long long pk) {
@@ -485,7 +468,7 @@ __device__ __noinline__ int choose_limit(int L, int S, int kmax, int kmin, int h
   const int n = HOT.l_total[L];
   __syncwarp();
   long long tmin = LLONG_MAX;
-#pragma unroll 2
+#pragma unroll 4
   for (int i = LANE; i < n; i += 32) { long long t = keys[i].t; tmin = t < tmin ? t : tmin; }
   tmin = warp_min_ll(tmin);
   long long dT = HOT.span[S], pt; unsigned long long pk = 0; int cnt;
@@ -502,7 +485,6 @@ __device__ __noinline__ int choose_limit(int L, int S, int kmax, int kmin, int h
   if (burst) {
     // more than kmax events share the timestamp tmin: interpolate (recipients are spread evenly), then bisect
     unsigned long long kmin_k = ~0ull, kmax_k = 0;
-#pragma unroll 1
     for (int i = LANE; i < n; i += 32) {
       EvKey k = keys[i];
       if (k.t == tmin) { kmin_k = k.k2 < kmin_k ? k.k2 : kmin_k; kmax_k = k.k2 > kmax_k ? k.k2 : kmax_k; }
@@ -512,7 +494,6 @@ __device__ __noinline__ int choose_limit(int L, int S, int kmax, int kmin, int h
     unsigned long long best = 0; int best_cnt = 0;
     double frac = (double)(kmax * 3 / 4) / (double)cnt;
     unsigned long long guess = kmin_k + (unsigned long long)((double)(kmax_k - kmin_k) * frac) + 1;
-#pragma unroll 1
     for (int it = 0; it < 80; it++) {
       unsigned long long mid = it == 0 ? guess : lo + (hi - lo) / 2;
       if (mid <= lo) mid = lo + 1;
@@ -536,7 +517,7 @@ __device__ __noinline__ int choose_limit(int L, int S, int kmax, int kmin, int h
 __device__ __noinline__ void b_pull() {
   PROF_CNT(P_N_BPULL);
   if (HOT.l_total[1] > 1024 && HOT.l_live[1] * 2 < HOT.l_total[1]) list_compact(1);
-  int cnt = choose_limit(1, 1, A_FILL_MAX, A_FILL_MIN, A_CAP / 2, LLONG_MAX - 1, 0ull);
+  int cnt = choose_limit(L_B, L_B, A_FILL_MAX, A_FILL_MIN, A_CAP / 2, LLONG_MAX - 1, 0ull);
   const long long pt = HOT.sel_t; const unsigned long long pk = HOT.sel_k;
   EvKey* bk = RUN.lk[1]; EvPay* bp = RUN.lp[1]; EvKey* ak = RUN.lk[0]; EvPay* ap = RUN.lp[0];
   const int n = HOT.l_total[1];
@@ -566,7 +547,7 @@ __device__ __noinline__ void b_pull() {
 // list A grew past A_REBALANCE (a burst inside the horizon): pull the horizon in and hand the tail back to B
 __device__ __noinline__ void a_rebalance() {
   list_compact(0);
-  int cnt = choose_limit(0, 1, A_FILL_MAX, A_FILL_MIN, A_CAP / 2, HOT.hz_t, HOT.hz_k);
+  int cnt = choose_limit(L_A, L_B, A_FILL_MAX, A_FILL_MIN, A_CAP / 2, HOT.hz_t, HOT.hz_k);
   if (HOT.status) return;
   const long long pt = HOT.sel_t; const unsigned long long pk = HOT.sel_k;
   const int n = HOT.l_total[0];
@@ -602,50 +583,34 @@ __device__ __noinline__ void a_rebalance() {
 
 __device__ __noinline__ void q_push(long long t, unsigned long long k2, int w0, int w1, int w2, int w3, int w4, int w5) {
   if (key_less(t, k2, HOT.lim_t, HOT.lim_k)) {
-    bool to_near = true;
-    if (HOT.n_near == NEAR_CAP) {
-      // near tier full: move its largest key out to list A and pull the limit down to it
-      int mi = near_argmax();
-      long long mt = ST.nt[mi]; unsigned long long mk = ST.nk[mi];
-      int4 p0 = *reinterpret_cast<const int4*>(&ST.npay[mi].w[0]);
-      int4 p1 = *reinterpret_cast<const int4*>(&ST.npay[mi].w[4]);
-      near_remove(mi);
-      list_append(0, mt, mk, p0.x, p0.y, p0.z, p0.w, p1.x, p1.y);
-      HOT.lim_t = mt; HOT.lim_k = mk;
-      to_near = key_less(t, k2, mt, mk);
-    }
-    if (to_near) {
-      int n = HOT.n_near;
-      near_put(n, t, k2, w0, w1, w2, w3, w4, w5);
-      HOT.n_near = n + 1;
-    } else {
-      list_append(0, t, k2, w0, w1, w2, w3, w4, w5);
-    }
+    if (HOT.n_near == NEAR_CAP) near_spill();
+    if (key_less(t, k2, HOT.lim_t, HOT.lim_k)) near_insert(t, k2, near_alloc(w0, w1, w2, w3, w4, w5));
+    else list_append(L_A, t, k2, w0, w1, w2, w3, w4, w5);
   } else if (key_less(t, k2, HOT.hz_t, HOT.hz_k)) {
-    list_append(0, t, k2, w0, w1, w2, w3, w4, w5);
-    if (HOT.l_live[0] > A_REBALANCE) a_rebalance();
+    list_append(L_A, t, k2, w0, w1, w2, w3, w4, w5);
+    if (HOT.l_live[L_A] > A_REBALANCE) a_rebalance();
   } else {
-    list_append(1, t, k2, w0, w1, w2, w3, w4, w5);
+    list_append(L_B, t, k2, w0, w1, w2, w3, w4, w5);
   }
-  int tot = HOT.n_near + HOT.l_live[0] + HOT.l_live[1];
+  int tot = HOT.n_near + HOT.l_live[L_A] + HOT.l_live[L_B];
   if (tot > HOT.queue_peak) HOT.queue_peak = tot;
 }
 
 // near tier is empty: pull the next batch (<= FILL_MAX smallest keys) out of list A (refilled from B when dry)
 __device__ __noinline__ void q_refill() {
   PROF_CNT(P_N_REFILL);
-  if (HOT.l_live[0] == 0) {
-    HOT.l_total[0] = 0;
-    if (HOT.l_live[1] == 0) return;
+  if (HOT.l_live[L_A] == 0) {
+    HOT.l_total[L_A] = 0;
+    if (HOT.l_live[L_B] == 0) return;
     b_pull();
     if (HOT.status) return;
   }
-  if (HOT.l_total[0] > 256 && HOT.l_live[0] * 2 < HOT.l_total[0]) list_compact(0);
-  int cnt = choose_limit(0, 0, FILL_MAX, FILL_MIN, NEAR_CAP, HOT.hz_t, HOT.hz_k);
+  if (HOT.l_total[L_A] > 256 && HOT.l_live[L_A] * 2 < HOT.l_total[L_A]) list_compact(L_A);
+  const int cnt = choose_limit(L_A, L_A, FILL_MAX, FILL_MIN, NEAR_CAP, HOT.hz_t, HOT.hz_k);
   const long long pt = HOT.sel_t; const unsigned long long pk = HOT.sel_k;
-  EvKey* keys = RUN.lk[0]; const EvPay* pay = RUN.lp[0];
-  const int n = HOT.l_total[0];
-  int nn = HOT.n_near;
+  EvKey* keys = RUN.lk[L_A]; const EvPay* pay = RUN.lp[L_A];
+  const int n = HOT.l_total[L_A];
+  int nn = 0;                                   // the near tier is empty: payload slot i <-> i-th taken event
 #pragma unroll 1
   for (int base = 0; base < n; base += 32) {
     int i = base + LANE;
@@ -662,8 +627,19 @@ __device__ __noinline__ void q_refill() {
     }
   }
   __syncwarp();
+  // rank sort, descending: lane i owns taken event i
+  long long et = 0; unsigned long long ek = 0; int rank = 0;
+  if (LANE < nn) { et = ST.nt[LANE]; ek = ST.nk[LANE]; }
+#pragma unroll 1
+  for (int j = 0; j < nn; j++) {
+    long long ot = ST.nt[j]; unsigned long long ok = ST.nk[j];
+    rank += (key_less(et, ek, ot, ok) || (et == ot && ek == ok && j < LANE)) ? 1 : 0;
+  }
+  __syncwarp();
+  if (LANE < nn) { ST.nt[rank] = et; ST.nk[rank] = ek; ST.nslot[rank] = LANE; }
   HOT.n_near = nn;
-  HOT.l_live[0] -= cnt;
+  HOT.near_free = nn >= 32 ? 0u : ~((1u << nn) - 1u);
+  HOT.l_live[L_A] -= cnt;
   HOT.lim_t = pt; HOT.lim_k = pk;
   __syncwarp();
 }
@@ -742,159 +718,167 @@ __device__ __noinline__ long long oracle_observe(long long t, double sigma_n, in
 }
 
 // ----------------------------------------------------------------------------------------------
-// order book (util/OrderBook.py).  Each side is ONE price-time sorted sequence (index 0 = best
-// price, oldest first).  Its best BOOK_TOP entries live in shared memory; the rest -- the "deep
-// book" -- is spilled to HBM in REVERSE order (deep[nd-1] is the best deep entry), so that moving
-// entries across the boundary is an O(1) push/pop at the array's end and every scan or shift over
-// the deep part is a run of coalesced 512-byte warp transactions.  s = BID / ASK.
+// order book (util/OrderBook.py).  Per side s = BID / ASK the best <= BOOK_TOP resting orders are kept
+// price-time sorted in shared memory (index 0 = best price, oldest first).  Every other resting order
+// sits in the side's unsorted POOL, an HBM list in the event-list format: key.t = price rank (smaller =
+// better), key.k2 = arrival number << 32 | order id, payload = price, qty, id, agent, history bucket,
+// arrival number.  Invariant: every top entry precedes every pool entry in price-time order, and
+// (pb_t, pb_k)[s] is a lower bound of the pool's keys.  Deep inserts are O(1) appends, deep cancels one
+// coalesced scan over 16-byte keys, and the pool -> top refill reuses choose_limit (a price window).
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool px_better_eq(int s, int p, int price) { return s == BID ? p >= price : p <= price; }
-__device__ __forceinline__ bool px_better(int s, int p, int price) { return s == BID ? p > price : p < price; }
+__device__ __forceinline__ long long pool_rank(int s, int price) { return s == ASK ? (long long)price : (long long)(0x7fffffff - price); }
+__device__ __forceinline__ unsigned long long pool_k2(unsigned arr, int id) { return ((unsigned long long)arr << 32) | (unsigned)id; }
 
 __device__ __noinline__ void top_remove(int s, int n, int idx) {                 // delete slot idx from top[s][0..n)
   __syncwarp();
 #pragma unroll 1
   for (int base = idx; base < n - 1; base += 32) {
-    int j = base + LANE; BookOrd t; int tq = 0;
+    int j = base + LANE; BookOrd t; int tq = 0, ta = 0;
     bool act = j < n - 1;
-    if (act) { t = ST.top[s][j + 1]; tq = ST.tseq[s][j + 1]; }
+    if (act) { t = ST.top[s][j + 1]; tq = ST.tseq[s][j + 1]; ta = ST.tarr[s][j + 1]; }
     __syncwarp();
-    if (act) { ST.top[s][j] = t; ST.tseq[s][j] = tq; }
+    if (act) { ST.top[s][j] = t; ST.tseq[s][j] = tq; ST.tarr[s][j] = ta; }
     __syncwarp();
   }
 }
-__device__ __noinline__ void top_insert(int s, int n, int idx, int price, int qty, int id, int agent, int oseq) {
+__device__ __noinline__ void top_insert(int s, int n, int idx, int price, int qty, int id, int agent, int oseq, int arr) {
   __syncwarp();
   int cnt = n - idx;
 #pragma unroll 1
   for (int done = 0; done < cnt; done += 32) {
-    int j = n - 1 - done - LANE; BookOrd t; int tq = 0;
+    int j = n - 1 - done - LANE; BookOrd t; int tq = 0, ta = 0;
     bool act = j >= idx;
-    if (act) { t = ST.top[s][j]; tq = ST.tseq[s][j]; }
+    if (act) { t = ST.top[s][j]; tq = ST.tseq[s][j]; ta = ST.tarr[s][j]; }
     __syncwarp();
-    if (act) { ST.top[s][j + 1] = t; ST.tseq[s][j + 1] = tq; }
-    __syncwarp();
-  }
-  if (LANE == 0) { BookOrd o; o.price = price; o.qty = qty; o.id = id; o.agent = agent; ST.top[s][idx] = o; ST.tseq[s][idx] = oseq; }
-  __syncwarp();
-}
-__device__ __noinline__ void deep_remove(BookOrd* d, int* q, int n, int idx) {
-  __syncwarp();
-#pragma unroll 1
-  for (int base = idx; base < n - 1; base += 32) {
-    int j = base + LANE; BookOrd t; int tq = 0;
-    bool act = j < n - 1;
-    if (act) { t = d[j + 1]; tq = q[j + 1]; }
-    __syncwarp();
-    if (act) { d[j] = t; q[j] = tq; }
+    if (act) { ST.top[s][j + 1] = t; ST.tseq[s][j + 1] = tq; ST.tarr[s][j + 1] = ta; }
     __syncwarp();
   }
-}
-__device__ __noinline__ void deep_insert(BookOrd* d, int* q, int n, int idx, int price, int qty, int id, int agent, int oseq) {
-  __syncwarp();
-  int cnt = n - idx;
-#pragma unroll 1
-  for (int done = 0; done < cnt; done += 32) {
-    int j = n - 1 - done - LANE; BookOrd t; int tq = 0;
-    bool act = j >= idx;
-    if (act) { t = d[j]; tq = q[j]; }
-    __syncwarp();
-    if (act) { d[j + 1] = t; q[j + 1] = tq; }
-    __syncwarp();
+  if (LANE == 0) {
+    BookOrd o; o.price = price; o.qty = qty; o.id = id; o.agent = agent;
+    ST.top[s][idx] = o; ST.tseq[s][idx] = oseq; ST.tarr[s][idx] = arr;
   }
-  if (LANE == 0) { BookOrd o; o.price = price; o.qty = qty; o.id = id; o.agent = agent; d[idx] = o; q[idx] = oseq; }
   __syncwarp();
 }
-// count entries whose price is better than or equal to `price` for this side
+// count top entries whose price is better than or equal to `price` for this side
 __device__ __forceinline__ int top_count_better_eq(int s, int n, int price) {
   __syncwarp();
   int cnt = 0;
   for (int j = LANE; j < n; j += 32) cnt += px_better_eq(s, ST.top[s][j].price, price) ? 1 : 0;
   return warp_sum_i(cnt);
 }
-__device__ __noinline__ int deep_count_better_eq(int s, const BookOrd* __restrict__ d, int n, int price) {
-  __syncwarp();
-  int cnt = 0;
-#pragma unroll 4
-  for (int j = LANE; j < n; j += 32) cnt += px_better_eq(s, d[j].price, price) ? 1 : 0;
-  return warp_sum_i(cnt);
+__device__ __noinline__ void pool_append(int s, int price, int qty, int id, int agent, int hseq, int arr) {
+  const int L = L_POOL + s;
+  const long long kt = pool_rank(s, price); const unsigned long long kk = pool_k2((unsigned)arr, id);
+  if (HOT.l_live[L] == 0 || key_less(kt, kk, HOT.pb_t[s], HOT.pb_k[s])) { HOT.pb_t[s] = kt; HOT.pb_k[s] = kk; }
+  list_append(L, kt, kk, price, qty, id, agent, hseq, arr);
 }
-// the shared-memory part ran empty: pull the best entries of the deep book back in
+// the shared-memory part ran empty: pull the best price levels of the pool back in
 __device__ __noinline__ void side_refill(int s) {
-  int nd = HOT.n_deep[s], ns = HOT.n_top[s];
-  if (ns > 0 || nd == 0) return;
-  int k = nd < BOOK_TOP / 2 ? nd : BOOK_TOP / 2;
-  const BookOrd* d = RUN.deep[s]; const int* q = RUN.dseq[s];
+  const int L = L_POOL + s;
+  if (HOT.n_top[s] > 0 || HOT.l_live[L] == 0) return;
+  if (HOT.l_total[L] > 256 && HOT.l_live[L] * 2 < HOT.l_total[L]) list_compact(L);
+  const int cnt = choose_limit(L, L, TOP_FILL, TOP_FILL_MIN, TOP_FILL, LLONG_MAX - 1, 0ull);
+  if (HOT.status) return;
+  const long long pt = HOT.sel_t; const unsigned long long pk = HOT.sel_k;
+  EvKey* keys = RUN.lk[L]; const EvPay* pay = RUN.lp[L];
+  const int n = HOT.l_total[L];
+  int nn = 0;
+#pragma unroll 1
+  for (int base = 0; base < n; base += 32) {
+    int i = base + LANE;
+    bool take = false; EvKey k;
+    if (i < n) { k = keys[i]; take = key_less(k.t, k.k2, pt, pk); }
+    unsigned m = __ballot_sync(FULL, take);
+    if (m) {
+      if (take) {
+        int pos = nn + __popc(m & ((1u << LANE) - 1u));
+        EvPay p = pay[i];
+        BookOrd o; o.price = p.w[0]; o.qty = p.w[1]; o.id = p.w[2]; o.agent = p.w[3];
+        ST.top[s][pos] = o; ST.tseq[s][pos] = p.w[4]; ST.tarr[s][pos] = p.w[5];
+        keys[i].t = LLONG_MAX;
+      }
+      nn += __popc(m);
+    }
+  }
   __syncwarp();
-  for (int i = LANE; i < k; i += 32) { ST.top[s][i] = d[nd - 1 - i]; ST.tseq[s][i] = q[nd - 1 - i]; }
+  // rank sort (<= TOP_FILL = 32 entries, lane i owns entry i): better price first, then arrival
+  BookOrd e; int eq = 0, ea = 0, rank = 0;
+  if (LANE < nn) { e = ST.top[s][LANE]; eq = ST.tseq[s][LANE]; ea = ST.tarr[s][LANE]; }
+  else { e.price = 0; e.qty = 0; e.id = 0; e.agent = 0; }
+  const long long er = pool_rank(s, e.price);
+#pragma unroll 1
+  for (int j = 0; j < nn; j++) {
+    long long orr = pool_rank(s, ST.top[s][j].price); unsigned oa = (unsigned)ST.tarr[s][j];
+    rank += (orr < er || (orr == er && oa < (unsigned)ea)) ? 1 : 0;
+  }
   __syncwarp();
-  HOT.n_top[s] = k; HOT.n_deep[s] = nd - k;
+  if (LANE < nn) { ST.top[s][rank] = e; ST.tseq[s][rank] = eq; ST.tarr[s][rank] = ea; }
+  HOT.n_top[s] = nn;
+  HOT.l_live[L] -= cnt;
+  HOT.pb_t[s] = pt; HOT.pb_k[s] = pk;
+  __syncwarp();
 }
 __device__ __forceinline__ void side_pop_front(int s) {                          // remove the best entry
   top_remove(s, HOT.n_top[s], 0);
   HOT.n_top[s] -= 1;
   if (HOT.n_top[s] == 0) side_refill(s);
 }
+// sum of quantities resting in the pool at `price` (a level that runs past the shared part)
+__device__ __noinline__ int pool_level_qty(int s, int price) {
+  const int L = L_POOL + s;
+  const EvKey* keys = RUN.lk[L]; const EvPay* pay = RUN.lp[L];
+  const int n = HOT.l_total[L];
+  const long long kt = pool_rank(s, price);
+  int v = 0;
+#pragma unroll 2
+  for (int i = LANE; i < n; i += 32) if (keys[i].t == kt) v += pay[i].w[1];
+  return warp_sum_i(v);
+}
 // getInsideBids(1)/getInsideAsks(1) (:378-399): price and total quantity of the best level
 __device__ __noinline__ int2 side_inside(int s) {
   __syncwarp();
-  int ns = HOT.n_top[s], nd = HOT.n_deep[s];
+  const int ns = HOT.n_top[s];
   if (ns == 0) return make_int2(-1, 0);
-  int p = ST.top[s][0].price, v = 0;
-  bool whole = true;                       // does the level run to the end of the shared part?
-  for (int base = 0; base < ns; base += 32) {
-    int j = base + LANE;
-    bool in = j < ns && ST.top[s][j].price == p;
-    v += in ? ST.top[s][j].qty : 0;
-    if (__any_sync(FULL, j < ns && !in)) { whole = false; break; }
-  }
-  if (whole) {
-    const BookOrd* d = RUN.deep[s];
-    for (int base = 0; base < nd; base += 32) {
-      int j = nd - 1 - base - LANE;
-      bool in = false; int q = 0;
-      if (j >= 0) { BookOrd e = d[j]; in = e.price == p; q = e.qty; }
-      v += in ? q : 0;
-      if (__any_sync(FULL, j >= 0 && !in)) break;
-    }
-  }
-  return make_int2(p, warp_sum_i(v));
+  const int p = ST.top[s][0].price;
+  int v = 0;
+  for (int j = LANE; j < ns; j += 32) { BookOrd e = ST.top[s][j]; v += e.price == p ? e.qty : 0; }
+  v = warp_sum_i(v);
+  // the level may continue in the pool only if it runs to the end of the shared part
+  if (ST.top[s][ns - 1].price == p && HOT.l_live[L_POOL + s] > 0 && HOT.pb_t[s] <= pool_rank(s, p)) v += pool_level_qty(s, p);
+  return make_int2(p, v);
 }
 // OrderBook.enterOrder (:272-298): position = number of resting orders with better-or-equal price
 __device__ __noinline__ void book_enter(int s, int price, int qty, int id, int agent) {
-  int ns = HOT.n_top[s], nd = HOT.n_deep[s];
-  int oseq = HOT.hist_B;                                 // history[0][order_id] = {...} (:60-64)
-  BookOrd* d = RUN.deep[s]; int* dq = RUN.dseq[s];
-  int cs = top_count_better_eq(s, ns, price);
-  bool to_top = cs < ns || nd == 0;
-  int cd = 0;
-  if (!to_top) {
-    cd = deep_count_better_eq(s, d, nd, price);
-    if (cd == 0 && ns < BOOK_TOP) to_top = true;        // worse than all of top, better than all of deep
-  }
-  if (to_top && ns == BOOK_TOP && cs == ns) to_top = false;   // full shared part and o is its new worst: goes deep
+  int ns = HOT.n_top[s];
+  const int oseq = HOT.hist_B;                           // history[0][order_id] = {...} (:60-64)
+  const int arr = (int)HOT.book_arr;
+  HOT.book_arr = (unsigned)arr + 1u;
+  const int cs = top_count_better_eq(s, ns, price);
+  bool to_top = cs < ns;
+  if (!to_top && ns < BOOK_TOP)                          // behind all of top: only if it also precedes all of the pool
+    to_top = HOT.l_live[L_POOL + s] == 0 ||
+             key_less(pool_rank(s, price), pool_k2((unsigned)arr, id), HOT.pb_t[s], HOT.pb_k[s]);
   if (to_top) {
-    if (ns == BOOK_TOP) {                                // spill the worst shared entry to the deep book's best end
-      if (nd >= RUN.deep_cap) { HOT.status = ABIDES_EOVERFLOW; return; }
-      __syncwarp();
-      if (LANE == 0) { d[nd] = ST.top[s][ns - 1]; dq[nd] = ST.tseq[s][ns - 1]; }
-      __syncwarp();
-      HOT.n_deep[s] = nd + 1; ns--;
+    if (ns == BOOK_TOP) {                                // spill the worst shared entry to the pool
+      BookOrd w = ST.top[s][ns - 1];
+      pool_append(s, w.price, w.qty, w.id, w.agent, ST.tseq[s][ns - 1], ST.tarr[s][ns - 1]);
+      if (HOT.status) return;
+      ns--;
     }
-    top_insert(s, ns, cs, price, qty, id, agent, oseq);
+    top_insert(s, ns, cs, price, qty, id, agent, oseq, arr);
     HOT.n_top[s] = ns + 1;
   } else {
-    if (nd >= RUN.deep_cap) { HOT.status = ABIDES_EOVERFLOW; return; }
-    deep_insert(d, dq, nd, nd - cd, price, qty, id, agent, oseq);   // logical index cd <-> physical nd - cd (reversed)
-    HOT.n_deep[s] = nd + 1;
+    pool_append(s, price, qty, id, agent, oseq, arr);
   }
-  int tot = HOT.n_top[0] + HOT.n_top[1] + HOT.n_deep[0] + HOT.n_deep[1];
+  int tot = HOT.n_top[0] + HOT.n_top[1] + HOT.l_live[L_POOL] + HOT.l_live[L_POOL + 1];
   if (tot > HOT.book_peak_orders) HOT.book_peak_orders = tot;
 }
-// find (price, id) on a side; returns 0 = absent, 1 = in the shared part, 2 = in the deep part; index in HOT.sel_k
+// find (price, id) on a side -- the FIRST match in book order; returns 0 = absent, 1 = in the shared part,
+// 2 = in the pool; index in HOT.find_idx
 __device__ __noinline__ int side_find(int s, int price, int id) {
   __syncwarp();
-  int ns = HOT.n_top[s], nd = HOT.n_deep[s];
+  const int ns = HOT.n_top[s];
   for (int base = 0; base < ns; base += 32) {
     int j = base + LANE;
     bool hit = false;
@@ -902,16 +886,22 @@ __device__ __noinline__ int side_find(int s, int price, int id) {
     unsigned m = __ballot_sync(FULL, hit);
     if (m) { HOT.find_idx = base + __ffs(m) - 1; return 1; }
   }
-  // deep part, scanned from its best end (highest physical index) so the FIRST match in book order wins
-  const BookOrd* d = RUN.deep[s];
-  for (int base = 0; base < nd; base += 32) {
-    int j = nd - 1 - base - LANE;
-    bool hit = false;
-    if (j >= 0) { BookOrd e = d[j]; hit = e.price == price && e.id == id; }
-    unsigned m = __ballot_sync(FULL, hit);
-    if (m) { HOT.find_idx = nd - 1 - base - (__ffs(m) - 1); return 2; }
+  const int L = L_POOL + s;
+  if (HOT.l_live[L] == 0) return 0;
+  const EvKey* keys = RUN.lk[L];
+  const int n = HOT.l_total[L];
+  const long long kt = pool_rank(s, price);
+  unsigned long long best = ~0ull; int bi = -1;
+#pragma unroll 4
+  for (int i = LANE; i < n; i += 32) {
+    EvKey k = keys[i];
+    if (k.t == kt && (unsigned)k.k2 == (unsigned)id && k.k2 < best) { best = k.k2; bi = i; }
   }
-  return 0;
+  unsigned long long mb = warp_min_ull(best);
+  if (mb == ~0ull) return 0;
+  unsigned m = __ballot_sync(FULL, best == mb);
+  HOT.find_idx = __shfl_sync(FULL, bi, __ffs(m) - 1);
+  return 2;
 }
 
 // ---- OrderBook.history / get_transacted_volume (:401-471) ------------------------------------
@@ -1048,18 +1038,23 @@ __device__ __noinline__ void book_cancel(int agent, int id, int price, bool is_b
   int where = side_find(s, price, id);
   if (where == 0) return;
   int idx = HOT.find_idx;
-  BookOrd o;
+  int oid, oprice, oqty;
   if (where == 1) {
-    o = ST.top[s][idx];
+    BookOrd o = ST.top[s][idx];
+    oid = o.id; oprice = o.price; oqty = o.qty;
     top_remove(s, HOT.n_top[s], idx);
     HOT.n_top[s] -= 1;
     if (HOT.n_top[s] == 0) side_refill(s);
   } else {
-    o = RUN.deep[s][idx];
-    deep_remove(RUN.deep[s], RUN.dseq[s], HOT.n_deep[s], idx);
-    HOT.n_deep[s] -= 1;
+    const int L = L_POOL + s;
+    const int4 p = *reinterpret_cast<const int4*>(&RUN.lp[L][idx].w[0]);
+    oprice = p.x; oqty = p.y; oid = p.z;
+    __syncwarp();
+    if (LANE == 0) RUN.lk[L][idx].t = LLONG_MAX;
+    __syncwarp();
+    HOT.l_live[L] -= 1;
   }
-  book_send<RP>(agent, ABIDES_MSG_ORDER_CANCELLED, is_buy, o.id, o.price, o.qty, -1);
+  book_send<RP>(agent, ABIDES_MSG_ORDER_CANCELLED, is_buy, oid, oprice, oqty, -1);
 }
 
 // OrderBook.handleMarketOrder (:160-188): one fresh limit order per opposite level until the quantity is
@@ -1080,40 +1075,72 @@ __device__ __noinline__ void book_handle_market(int agent, int qty, bool is_buy)
     rem -= v;
   }
 }
-// OrderBook.modifyOrder (:350-373), including the reference's index-0 overwrite (:359)
+// OrderBook.modifyOrder (:350-373), including the reference's index-0 overwrite (:359): the modified order
+// replaces the FIRST order of its price level (which keeps its queue position), not the matched one.
 template <bool RP>
 __device__ __noinline__ void book_modify(int agent, int id, int price, int new_qty, bool is_buy) {
   const int s = is_buy ? BID : ASK;
+  const int L = L_POOL + s;
   int where = side_find(s, price, id);
   if (where == 0) return;
   int idx = HOT.find_idx;
-  BookOrd* d = RUN.deep[s]; int* dq = RUN.dseq[s];
-  int oseq = where == 1 ? ST.tseq[s][idx] : dq[idx];
-  // first entry of that price level = number of entries with a strictly better price
-  int ns = HOT.n_top[s], nd = HOT.n_deep[s];
-  int better = 0;
+  const int oseq = where == 1 ? ST.tseq[s][idx] : RUN.lp[L][idx].w[4];
+  // first entry of that price level
+  const int ns = HOT.n_top[s];
+  int first = -1;
   __syncwarp();
-  for (int j = LANE; j < ns; j += 32) better += px_better(s, ST.top[s][j].price, price) ? 1 : 0;
-  for (int j = LANE; j < nd; j += 32) better += px_better(s, d[j].price, price) ? 1 : 0;
-  better = warp_sum_i(better);
-  BookOrd no; no.price = price; no.qty = new_qty; no.id = id; no.agent = agent;
-  __syncwarp();
-  if (LANE == 0) {
-    if (better < ns) { ST.top[s][better] = no; ST.tseq[s][better] = oseq; }
-    else { d[nd - 1 - (better - ns)] = no; dq[nd - 1 - (better - ns)] = oseq; }
+  for (int base = 0; base < ns && first < 0; base += 32) {
+    int j = base + LANE;
+    unsigned m = __ballot_sync(FULL, j < ns && ST.top[s][j].price == price);
+    if (m) first = base + __ffs(m) - 1;
   }
-  __syncwarp();
+  if (first >= 0) {
+    __syncwarp();
+    if (LANE == 0) {
+      BookOrd no; no.price = price; no.qty = new_qty; no.id = id; no.agent = agent;
+      ST.top[s][first] = no; ST.tseq[s][first] = oseq;
+    }
+    __syncwarp();
+  } else {
+    // the whole level sits in the pool: its first order is the one with the smallest arrival number
+    EvKey* keys = RUN.lk[L];
+    const int n = HOT.l_total[L];
+    const long long kt = pool_rank(s, price);
+    unsigned long long best = ~0ull; int bi = -1;
+    for (int i = LANE; i < n; i += 32) {
+      EvKey k = keys[i];
+      if (k.t == kt && k.k2 < best) { best = k.k2; bi = i; }
+    }
+    unsigned long long mb = warp_min_ull(best);
+    unsigned m = __ballot_sync(FULL, best == mb);
+    bi = __shfl_sync(FULL, bi, __ffs(m) - 1);
+    __syncwarp();
+    if (LANE == 0) {
+      keys[bi].k2 = (mb & 0xffffffff00000000ull) | (unsigned)id;
+      EvPay p = RUN.lp[L][bi];
+      p.w[0] = price; p.w[1] = new_qty; p.w[2] = id; p.w[3] = agent; p.w[4] = oseq;
+      RUN.lp[L][bi] = p;
+    }
+    __syncwarp();
+  }
   if (HOT.hist_B - oseq <= RUN.cfg.stream_history)         // one notification per history bucket holding the id
     book_send<RP>(agent, ABIDES_MSG_ORDER_MODIFIED, is_buy, id, price, new_qty, -1);
 }
-__device__ __noinline__ int side_levels(int s) {                                // number of distinct prices
-  int ns = HOT.n_top[s], nd = HOT.n_deep[s], c = 0;
-  const BookOrd* d = RUN.deep[s];
+// number of distinct prices on a side (replay harness only)
+__device__ __noinline__ int side_levels(int s) {
+  const int L = L_POOL + s;
+  const int ns = HOT.n_top[s], n = HOT.l_total[L];
+  const EvKey* keys = RUN.lk[L];
+  int c = 0;
   __syncwarp();
-  for (int j = LANE; j < ns + nd; j += 32) {
-    int p = j < ns ? ST.top[s][j].price : d[nd - 1 - (j - ns)].price;
-    int q = j == 0 ? p - 1 : (j - 1 < ns ? ST.top[s][j - 1].price : d[nd - 1 - (j - 1 - ns)].price);
-    c += (j == 0 || p != q) ? 1 : 0;
+  for (int j = LANE; j < ns; j += 32) c += (j == 0 || ST.top[s][j].price != ST.top[s][j - 1].price) ? 1 : 0;
+  const long long worst = ns > 0 ? pool_rank(s, ST.top[s][ns - 1].price) : -1;
+  for (int i = LANE; i < n; i += 32) {
+    EvKey k = keys[i];
+    if (k.t == LLONG_MAX || k.t == worst) continue;
+    bool firstOfLevel = true;                              // no other pool entry of this price arrived earlier
+    for (int j = 0; j < n; j++) { EvKey o = keys[j]; if (o.t == k.t && o.k2 < k.k2) { firstOfLevel = false; break; } }
+    c += firstOfLevel ? 1 : 0;
   }
   return warp_sum_i(c);
 }
@@ -1185,7 +1212,6 @@ __device__ __noinline__ void ord_remove(int idx) {
   OpenOrd* s = RUN.arena + A.ord_off;
   int n = A.ord_cnt;
   __syncwarp();
-#pragma unroll 1
   for (int base = idx; base < n - 1; base += 32) {
     int j = base + LANE; OpenOrd t;
     bool act = j < n - 1;
@@ -1409,28 +1435,30 @@ __device__ __noinline__ void mm_place_orders(int a, long long mid, const abides_
   for (long long i = 0; i <= last_ask; i++) ta_place_limit(a, A.u.mm.sell_size, false, lowest_ask + i * tick);
 }
 
-__device__ __noinline__ void agent_wakeup(int a) {
+// wakeup() of ZeroIntelligence / Value / Noise agents (ZeroIntelligenceAgent.py:96-160, ValueAgent.py:82-121,
+// NoiseAgent.py:77-111)
+__device__ __noinline__ void zvn_wakeup(int a, const abides_agent_type& ty) {
   AgentRec& A = ST.ag; Hot& h = HOT;
-  const abides_agent_type& ty = c_db.types[A.type_idx];
+  ta_wakeup(a);
+  ag_set_state(A, ST_INACTIVE);
+  if (!(A.flags & F_HAS_OPEN) || !(A.flags & F_HAS_CLOSE)) return;
+  A.flags |= F_TRADING;
+  if ((A.flags & F_MKT_CLOSED) && (A.flags & F_HAS_DAILY_CLOSE)) return;
+  if (ty.klass == ABIDES_NOISE) {
+    if (A.u.noise.wakeup_time > h.now) k_wakeup(a, A.u.noise.wakeup_time);
+  } else {
+    double dt = rng_exponential(SID_AGENT, 1.0 / ty.lambda_a);
+    k_wakeup(a, h.now + (long long)rint(dt));
+  }
+  if ((A.flags & F_MKT_CLOSED) && !(A.flags & F_HAS_DAILY_CLOSE)) { ta_query_spread(a); ag_set_state(A, ST_AWAITING_SPREAD); return; }
+  if (ty.klass != ABIDES_NOISE) ta_cancel_all(a);
+  ta_query_spread(a);
+  ag_set_state(A, ST_AWAITING_SPREAD);
+}
+// wakeup() of Momentum / AdaptiveMarketMaker / POV-heartbeat agents
+__device__ __noinline__ void other_wakeup(int a, const abides_agent_type& ty) {
+  AgentRec& A = ST.ag; Hot& h = HOT;
   switch (ty.klass) {
-    case ABIDES_ZI: case ABIDES_VALUE: case ABIDES_NOISE: {
-      ta_wakeup(a);
-      ag_set_state(A, ST_INACTIVE);
-      if (!(A.flags & F_HAS_OPEN) || !(A.flags & F_HAS_CLOSE)) return;
-      A.flags |= F_TRADING;
-      if ((A.flags & F_MKT_CLOSED) && (A.flags & F_HAS_DAILY_CLOSE)) return;
-      if (ty.klass == ABIDES_NOISE) {
-        if (A.u.noise.wakeup_time > h.now) k_wakeup(a, A.u.noise.wakeup_time);
-      } else {
-        double dt = rng_exponential(SID_AGENT, 1.0 / ty.lambda_a);
-        k_wakeup(a, h.now + (long long)rint(dt));
-      }
-      if ((A.flags & F_MKT_CLOSED) && !(A.flags & F_HAS_DAILY_CLOSE)) { ta_query_spread(a); ag_set_state(A, ST_AWAITING_SPREAD); return; }
-      if (ty.klass != ABIDES_NOISE) ta_cancel_all(a);
-      ta_query_spread(a);
-      ag_set_state(A, ST_AWAITING_SPREAD);
-      return;
-    }
     case ABIDES_MOMENTUM:
       if (ta_wakeup(a)) { ta_query_spread(a); ag_set_state(A, ST_AWAITING_SPREAD); }
       return;
@@ -1450,23 +1478,16 @@ __device__ __noinline__ void agent_wakeup(int a) {
     default: return;
   }
 }
+__device__ __forceinline__ void agent_wakeup(int a) {
+  const abides_agent_type& ty = c_db.types[ST.ag.type_idx];
+  if (ty.klass <= ABIDES_NOISE) zvn_wakeup(a, ty);
+  else other_wakeup(a, ty);
+}
 
-__device__ __noinline__ void agent_receive(int a, int w0, int w1, int w2, int w3, int w4, int w5) {
+// receiveMessage() tails of Momentum / AdaptiveMarketMaker agents
+__device__ __noinline__ void other_receive(int a, int code, const abides_agent_type& ty) {
   AgentRec& A = ST.ag; Hot& h = HOT;
-  const abides_agent_type& ty = c_db.types[A.type_idx];
-  Msg m; m.w0 = w0; m.w1 = w1; m.w2 = w2; m.w3 = w3; m.w4 = w4; m.w5 = w5;
-  int code = pay_code(w0) & ~ABIDES_MSG_REPLY;
-  ta_receive(a, m, ty.klass, ty);
   switch (ty.klass) {
-    case ABIDES_ZI: case ABIDES_VALUE: case ABIDES_NOISE:
-      if (ag_state(A) == ST_AWAITING_SPREAD && code == ABIDES_MSG_QUERY_SPREAD) {
-        if (A.flags & F_MKT_CLOSED) return;
-        if (ty.klass == ABIDES_ZI) zi_place_order(a, ty);
-        else if (ty.klass == ABIDES_VALUE) value_place_order(a, ty);
-        else noise_place_order(a);
-        ag_set_state(A, ST_AWAITING_WAKEUP);
-      }
-      return;
     case ABIDES_MOMENTUM:
       if (ag_state(A) == ST_AWAITING_SPREAD && code == ABIDES_MSG_QUERY_SPREAD) {
         momentum_place_orders(a);
@@ -1503,6 +1524,26 @@ __device__ __noinline__ void agent_receive(int a, int w0, int w1, int w2, int w3
     }
     default: return;
   }
+}
+
+__device__ __noinline__ void agent_receive(int a, int w0, int w1, int w2, int w3, int w4, int w5) {
+  AgentRec& A = ST.ag;
+  const abides_agent_type& ty = c_db.types[A.type_idx];
+  Msg m; m.w0 = w0; m.w1 = w1; m.w2 = w2; m.w3 = w3; m.w4 = w4; m.w5 = w5;
+  const int code = pay_code(w0) & ~ABIDES_MSG_REPLY;
+  const int klass = ty.klass;
+  ta_receive(a, m, klass, ty);
+  if (klass <= ABIDES_NOISE) {
+    if (ag_state(A) == ST_AWAITING_SPREAD && code == ABIDES_MSG_QUERY_SPREAD) {
+      if (A.flags & F_MKT_CLOSED) return;
+      if (klass == ABIDES_ZI) zi_place_order(a, ty);
+      else if (klass == ABIDES_VALUE) value_place_order(a, ty);
+      else noise_place_order(a);
+      ag_set_state(A, ST_AWAITING_WAKEUP);
+    }
+    return;
+  }
+  other_receive(a, code, ty);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -1738,8 +1779,10 @@ __global__ void __launch_bounds__(32) init_kernel() {
     h.ms_time = cfg->megashock_time0; h.ms_value = cfg->megashock_value0;
     h.lim_t = LLONG_MIN; h.lim_k = 0;
     h.hz_t = LLONG_MIN; h.hz_k = 0;
-    h.span[0] = 1000000000ll; h.span[1] = 64000000000ll;
-    h.l_total[1] = n; h.l_live[1] = n; h.queue_peak = n;
+    h.span[L_A] = 1000000000ll; h.span[L_B] = 64000000000ll;
+    h.span[L_POOL + BID] = 64; h.span[L_POOL + ASK] = 64;
+    h.near_free = 0xffffffffu;
+    h.l_total[L_B] = n; h.l_live[L_B] = n; h.queue_peak = n;
     h.last_trade = (int)cfg->r_bar; h.has_last_trade = 1;
     for (int s = 0; s < ABIDES_EXTRA_STREAMS; s++) {
       long long stream = aoff + (long long)ABIDES_EXTRA_STREAMS * inst + n + s;
@@ -1759,19 +1802,21 @@ __global__ void init_types_kernel() {
   db.type_log1mk[i] = (base > 0 && base != 1.0) ? abm_log_dd(base) : abm_mk(0.0, 0.0);
 }
 
-__device__ __forceinline__ void run_setup(int inst) {
+__device__ __noinline__ void run_setup(int inst) {
   const DevBatch& db = c_db;
   Run& r = RUN;
   r.cfg = db.cfg[inst];
-  r.lk[0] = db.a_keys + (size_t)inst * A_CAP; r.lp[0] = db.a_pay + (size_t)inst * A_CAP; r.lcap[0] = A_CAP;
-  r.lk[1] = db.b_keys + (size_t)inst * db.b_cap; r.lp[1] = db.b_pay + (size_t)inst * db.b_cap; r.lcap[1] = db.b_cap;
+  r.lk[L_A] = db.a_keys + (size_t)inst * A_CAP; r.lp[L_A] = db.a_pay + (size_t)inst * A_CAP; r.lcap[L_A] = A_CAP;
+  r.lk[L_B] = db.b_keys + (size_t)inst * db.b_cap; r.lp[L_B] = db.b_pay + (size_t)inst * db.b_cap; r.lcap[L_B] = db.b_cap;
+  for (int s = 0; s < 2; s++) {
+    r.lk[L_POOL + s] = db.p_keys + ((size_t)inst * 2 + s) * db.deep_cap;
+    r.lp[L_POOL + s] = db.p_pay + ((size_t)inst * 2 + s) * db.deep_cap;
+    r.lcap[L_POOL + s] = db.deep_cap;
+  }
   r.arena = db.arena + (size_t)inst * db.arena_cap;
-  r.deep[BID] = db.deep_book + (size_t)inst * 2 * db.deep_cap; r.deep[ASK] = r.deep[BID] + db.deep_cap;
-  r.dseq[BID] = db.deep_seq + (size_t)inst * 2 * db.deep_cap; r.dseq[ASK] = r.dseq[BID] + db.deep_cap;
   r.txn_log = db.txn_log + (size_t)inst * TXN_CAP;
   r.unrolled = db.unrolled + (size_t)inst * UNR_CAP;
   r.trace = db.trace_cap > 0 ? db.trace + (size_t)inst * db.trace_cap : nullptr;
-  r.deep_cap = db.deep_cap;
   r.aoff = r.cfg.agent_offset; r.inst = inst; r.n_agents = r.cfg.n_agents; r.cur_agent = -1;
   r.mt0 = db.mt ? db.mt + (size_t)(r.aoff + (long long)ABIDES_EXTRA_STREAMS * inst) * ABIDES_MT_N : nullptr;
   r.lat_to = db.lat_to + r.aoff; r.lat_from = db.lat_from + r.aoff;
@@ -1787,6 +1832,7 @@ __global__ void __launch_bounds__(32) sim_kernel(long long until_time) {
   {
     const int4* src = reinterpret_cast<const int4*>(G);
     int4* dst = reinterpret_cast<int4*>(&ST);
+#pragma unroll 1
     for (int i = lane; i < (int)(sizeof(InstShared) / 16); i += 32) dst[i] = src[i];
   }
   if (lane == 0) run_setup(inst);
@@ -1811,10 +1857,12 @@ __global__ void __launch_bounds__(32) sim_kernel(long long until_time) {
         PROF_ADD(P_REFILL);
         if (h.n_near == 0) { finished = true; break; }
       }
-      const int idx = near_argmin();
-      const long long t = ST.nt[idx];
-      const unsigned long long k2 = ST.nk[idx];
+      const int top_i = h.n_near - 1;
+      const long long t = ST.nt[top_i];
+      const unsigned long long k2 = ST.nk[top_i];
+      const int slot = ST.nslot[top_i];
       if (t > until_time) break;
+      h.n_near = top_i;
       h.now = t;
       h.ttl++;
       h.additional_delay = 0;
@@ -1827,21 +1875,21 @@ __global__ void __launch_bounds__(32) sim_kernel(long long until_time) {
         // agent in the future: re-queue at its busy time with the same uniq (Kernel.py:217-223)
         PROF_CNT(P_N_REQUEUE);
         if (key_less(busy, k2, h.lim_t, h.lim_k)) {
-          __syncwarp();
-          if (lane == 0) ST.nt[idx] = busy;
-          __syncwarp();
+          near_insert(busy, k2, slot);
         } else {
-          const int4 p0 = *reinterpret_cast<const int4*>(&ST.npay[idx].w[0]);
-          const int4 p1 = *reinterpret_cast<const int4*>(&ST.npay[idx].w[4]);
-          near_remove(idx);
+          const int4 p0 = *reinterpret_cast<const int4*>(&ST.npay[slot].w[0]);
+          const int4 p1 = *reinterpret_cast<const int4*>(&ST.npay[slot].w[4]);
+          h.near_free |= 1u << slot;
+          __syncwarp();
           q_push(busy, k2, p0.x, p0.y, p0.z, p0.w, p1.x, p1.y);
         }
         PROF_ADD(P_REQUEUE);
         continue;
       }
-      const int4 p0 = *reinterpret_cast<const int4*>(&ST.npay[idx].w[0]);
-      const int4 p1 = *reinterpret_cast<const int4*>(&ST.npay[idx].w[4]);
-      near_remove(idx);
+      const int4 p0 = *reinterpret_cast<const int4*>(&ST.npay[slot].w[0]);
+      const int4 p1 = *reinterpret_cast<const int4*>(&ST.npay[slot].w[4]);
+      h.near_free |= 1u << slot;
+      __syncwarp();
       h.delivered++;
       if (tracing) trace_event(t, k2, p0.x, p0.y, p0.z, p0.w, p1.x, p1.y);
       if (rcpt == 0) {
@@ -1881,6 +1929,7 @@ __global__ void __launch_bounds__(32) sim_kernel(long long until_time) {
   {
     int4* dst = reinterpret_cast<int4*>(G);
     const int4* src = reinterpret_cast<const int4*>(&ST);
+#pragma unroll 1
     for (int i = lane; i < (int)(sizeof(InstShared) / 16); i += 32) dst[i] = src[i];
   }
 }
@@ -1890,7 +1939,7 @@ __global__ void __launch_bounds__(32) sim_kernel(long long until_time) {
 // ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32) replay_kernel(int n_books, const long long* op_offset, const abides_book_op* ops,
                                                     int stream_history, int max_events, abides_book_event* events,
-                                                    int* counts, abides_book_state* states, BookOrd* deep, int* deep_seq,
+                                                    int* counts, abides_book_state* states, EvKey* pool_keys, EvPay* pool_pay,
                                                     int deep_cap) {
   int b = blockIdx.x, lane = threadIdx.x;
   if (b >= n_books) return;
@@ -1899,9 +1948,12 @@ __global__ void __launch_bounds__(32) replay_kernel(int n_books, const long long
   if (lane == 0) {
     Run& r = RUN;
     r.cfg.stream_history = stream_history;
-    r.deep[BID] = deep + (size_t)b * 2 * deep_cap; r.deep[ASK] = r.deep[BID] + deep_cap;
-    r.dseq[BID] = deep_seq + (size_t)b * 2 * deep_cap; r.dseq[ASK] = r.dseq[BID] + deep_cap;
-    r.deep_cap = deep_cap;
+    for (int s = 0; s < 2; s++) {
+      r.lk[L_POOL + s] = pool_keys + ((size_t)b * 2 + s) * deep_cap;
+      r.lp[L_POOL + s] = pool_pay + ((size_t)b * 2 + s) * deep_cap;
+      r.lcap[L_POOL + s] = deep_cap;
+      HOT.span[L_POOL + s] = 64;
+    }
     r.txn_log = nullptr;
     r.rp_events = events; r.rp_counts = counts; r.rp_max = max_events; r.rp_base = (int)op_offset[b];
     HOT.next_order_id = 1 << 30;                 // ids of market-order children: outside the tape's id space
@@ -2146,8 +2198,8 @@ int abides_load(abides_handle* h, const abides_batch* b) {
     if ((rc = dev_alloc(h, &d.b_pay, (size_t)ni * d.b_cap))) return rc;
     if ((rc = dev_alloc(h, &d.prof, (size_t)N_PROF))) return rc;
     if ((rc = dev_alloc(h, &d.arena, (size_t)ni * d.arena_cap))) return rc;
-    if ((rc = dev_alloc(h, &d.deep_book, (size_t)ni * 2 * d.deep_cap))) return rc;
-    if ((rc = dev_alloc(h, &d.deep_seq, (size_t)ni * 2 * d.deep_cap))) return rc;
+    if ((rc = dev_alloc(h, &d.p_keys, (size_t)ni * 2 * d.deep_cap))) return rc;
+    if ((rc = dev_alloc(h, &d.p_pay, (size_t)ni * 2 * d.deep_cap))) return rc;
     if ((rc = dev_alloc(h, &d.txn_log, (size_t)ni * TXN_CAP))) return rc;
     if ((rc = dev_alloc(h, &d.unrolled, (size_t)ni * UNR_CAP))) return rc;
     if ((rc = dev_alloc(h, &d.mom_ring, (size_t)(n_mom > 0 ? n_mom : 1) * MOM_RING))) return rc;
@@ -2280,7 +2332,7 @@ int abides_replay_book(abides_handle* h, int32_t n_books, const int64_t* op_offs
       return fail(ABIDES_EINVAL, "abides_replay_book: price / quantity / order id outside the device's int32 range");
   int deep_cap = (int)(longest + 64);
   long long* d_off = nullptr; abides_book_op* d_ops = nullptr; abides_book_event* d_ev = nullptr; int* d_cnt = nullptr;
-  abides_book_state* d_st = nullptr; BookOrd* d_deep = nullptr; int* d_seq = nullptr;
+  abides_book_state* d_st = nullptr; EvKey* d_deep = nullptr; EvPay* d_seq = nullptr;
   int rc = 0;
   auto cleanup = [&]() { cudaFree(d_off); cudaFree(d_ops); cudaFree(d_ev); cudaFree(d_cnt); cudaFree(d_st); cudaFree(d_deep); cudaFree(d_seq); };
 #define RCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return fail(ABIDES_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
@@ -2289,8 +2341,8 @@ int abides_replay_book(abides_handle* h, int32_t n_books, const int64_t* op_offs
   RCK(cudaMalloc(&d_ev, sizeof(abides_book_event) * n_ops * max_events_per_op));
   RCK(cudaMalloc(&d_cnt, sizeof(int) * n_ops));
   RCK(cudaMalloc(&d_st, sizeof(abides_book_state) * n_ops));
-  RCK(cudaMalloc(&d_deep, sizeof(BookOrd) * (size_t)n_books * 2 * deep_cap));
-  RCK(cudaMalloc(&d_seq, sizeof(int) * (size_t)n_books * 2 * deep_cap));
+  RCK(cudaMalloc(&d_deep, sizeof(EvKey) * (size_t)n_books * 2 * deep_cap));
+  RCK(cudaMalloc(&d_seq, sizeof(EvPay) * (size_t)n_books * 2 * deep_cap));
   RCK(cudaMemcpyAsync(d_off, op_offset, sizeof(long long) * (n_books + 1), cudaMemcpyHostToDevice, h->stream));
   RCK(cudaMemcpyAsync(d_ops, ops, sizeof(abides_book_op) * n_ops, cudaMemcpyHostToDevice, h->stream));
   RCK(cudaMemsetAsync(d_ev, 0, sizeof(abides_book_event) * n_ops * max_events_per_op, h->stream));
