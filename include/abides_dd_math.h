@@ -286,7 +286,7 @@ ABM_HD double abm_exp(double x) {
 }
 
 /* x ** y given l = abm_log_dd(x), x > 0 (C pow semantics for the finite cases the reference hits). */
-ABM_HD double abm_pow_with_log(abm_dd l, double x, double y) {
+ABM_HD_BIG double abm_pow_with_log(abm_dd l, double x, double y) {
   if (y == 0.0 || x == 1.0) return 1.0;
   if (y == 1.0) return x;
   double ph = l.hi * y, pl = ABM_FMA(l.hi, y, -ph) + l.lo * y;
