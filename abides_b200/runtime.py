@@ -200,3 +200,36 @@ def run_config_batch(config, arg_lists, device=0, write=True):
         for i, k in enumerate(kernels):
             write_back(k, out, i)
     return out, kernels
+
+
+# ---- multi-GPU: instances shard by contiguous ranges, one final gather of summaries (SURVEY 8e) ----
+def shard_bounds(n_instances, world, rank):
+    """[lo, hi) of the instances rank `rank` owns: n // world each, the remainder to the low ranks."""
+    base, rem = divmod(int(n_instances), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def gather_summaries(res, dist=None, device=None):
+    """All-gather the per-instance result records (numpy structured array of engine.INSTANCE_RESULT_DTYPE) of
+    every rank, in instance order.  `dist` is torch.distributed (NCCL on the GPUs, gloo in the CPU tests) or
+    None for a single process.  This is the path's only collective."""
+    import torch
+    from .engine import INSTANCE_RESULT_DTYPE
+    res = np.ascontiguousarray(res)
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return res.copy()
+    world = dist.get_world_size()
+    words = INSTANCE_RESULT_DTYPE.itemsize // 8
+    n_local = torch.tensor([len(res)], dtype=torch.int64, device=device)
+    counts = [torch.zeros_like(n_local) for _ in range(world)]
+    dist.all_gather(counts, n_local)
+    counts = [int(c.item()) for c in counts]
+    pad = max(counts)
+    buf = np.zeros(pad * words, np.int64)
+    buf[:len(res) * words] = np.frombuffer(res.tobytes(), dtype=np.int64)
+    t = torch.from_numpy(buf).to(device) if device is not None else torch.from_numpy(buf)
+    out = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(out, t)
+    parts = [o.cpu().numpy()[:c * words] for o, c in zip(out, counts)]
+    return np.frombuffer(np.concatenate(parts).tobytes(), dtype=INSTANCE_RESULT_DTYPE).copy()

@@ -65,6 +65,35 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def ncu_traffic(workload, instances):
+    """DRAM bytes per sim_kernel launch from the committed ncu capture of the same workload (profiles/), or None."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r1_roofline.json")))
+        e = t.get("%s_x%d" % (workload, instances))
+        return float(e["dram_bytes_per_launch"]) if e else None
+    except Exception:
+        return None
+
+
+def pin_host_batch(hb):
+    """Page-lock the big host tables so the e2e leg copies from pinned memory (done once, outside the timed region)."""
+    import torch
+    rt = torch.cuda.cudart()
+    n = 0
+    for a in (hb.mt_key, hb.lat_to, hb.lat_from, hb.size, hb.wakeup_time, hb.agent_type, hb.agent_theta, hb.theta):
+        if a is not None and a.nbytes >= (1 << 20):
+            if int(rt.cudaHostRegister(a.ctypes.data, a.nbytes, 0)) == 0:
+                n += a.nbytes
+    return n
+
+
 def measured_hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -111,7 +140,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     from abides_b200 import _abi, runtime
     rng_mode = _abi.RNG_MT19937 if args.rng == "mt" else _abi.RNG_PHILOX
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     config = {"workload": "%s x %d seeds per GPU, one market day each (09:30-16:00, kernel 00:00-17:00)"
                           % (args.workload, args.instances),
               "instances_per_gpu": args.instances, "rng": args.rng,
@@ -121,7 +150,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        n_sample = args.cpu_sample or min(args.instances, max(cores, 8) * 4)
+        n_sample = args.cpu_sample or args.instances        # one full batch per step: a few core-seconds per thread
         seeds = runtime.parallel_seeds(args.seed, n_sample)
         hb, build_s = build_batch(args.workload, seeds, _abi.RNG_MT19937)
         for _ in range(min(args.warmup, 1)):
@@ -169,12 +198,7 @@ def main():
 
     def gather_summaries(res):
         """K6: the final gather of per-instance summary records (the path's only collective)."""
-        t = torch.from_numpy(np.frombuffer(res.tobytes(), dtype=np.int64).copy()).cuda()
-        if dist is None:
-            return t
-        out = [torch.empty_like(t) for _ in range(world)]
-        dist.all_gather(out, t)
-        return torch.cat(out)
+        return runtime.gather_summaries(res, dist, device=torch.device("cuda", local_rank))
 
     for _ in range(args.warmup):
         eng.reset()
@@ -202,6 +226,7 @@ def main():
     clocks = sampler.stop()
 
     # e2e: host buffers -> abides_load (H2D) -> abides_run -> abides_read_results (D2H)
+    pinned = pin_host_batch(hb)
     barrier()
     t1 = time.perf_counter()
     for _ in range(args.e2e_steps):
@@ -239,16 +264,21 @@ def main():
         "messages_per_step": msgs_total, "wall_ms_per_step": wall_ms / args.steps, "host_build_s": build_s,
         "clocks": clocks,
         "e2e": {"value": msgs_total * args.e2e_steps / (e2e_ms / 1e3), "unit": "messages/s",
-                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": args.e2e_steps},
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
+                "pinned_host_bytes": pinned,
+                "path": "Engine.load (abides_load, H2D of every table) -> Engine.run (abides_run) -> "
+                        "Engine.results_arrays (abides_read_results, D2H) -> summary gather"},
         "gpu_launches": 3 * args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src,
+                     "traffic": ncu_traffic(args.workload, args.instances), "peak_source": peak_src,
+                     "kernel_ms_per_launch": kern_ms / args.steps,
                      "note": "dominant kernel sim_kernel: %d B algorithmic per message x messages per launch / "
-                             "CUDA-event time of the launch; the path is latency/divergence bound (SURVEY 8d)"
+                             "CUDA-event time of the launch (events on the library's launch stream). The kernel is "
+                             "instruction-fetch bound, not HBM bound: see DESIGN.md and profiles/"
                              % ALGO_BYTES_PER_MESSAGE},
     }
     if world == 1:
-        n_sample = args.cpu_sample or min(args.instances, max(cores, 8) * 4)
+        n_sample = args.cpu_sample or args.instances        # the whole batch once (~2-3 s wall, tens of core-seconds)
         m, dt = cpu_baseline(hb, n_sample, cores)
         line["cpu_baseline"] = {"value": m / dt, "unit": "messages/s", "cores": cores, "kind": "port",
                                 "sample": "first %d instances of the same batch on %d host threads, %.1f s "
