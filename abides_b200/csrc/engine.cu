@@ -101,7 +101,7 @@ struct __align__(128) AgentRec {        // 128 bytes: one coalesced transaction
   int size;                             // Noise / Value / Momentum order size
   int type_idx;                         // absolute row in the types table
   union {
-    struct { double r_t, sigma_t; long long prev_wake; } est;                     // ZI / Value
+    struct { double r_t, sigma_t; long long prev_wake; int hint_id, hint; } est;   // ZI / Value (+ pool slot of the last accepted order)
     struct { long long wakeup_time; } noise;
     struct { double csum; int n_mids; int ring; double avg20, avg50; } mom;
     struct { double last_spread, window_size; long long transacted_volume;
@@ -124,6 +124,8 @@ struct Hot {
   int l_total[N_LISTS], l_live[N_LISTS];   // per HBM list: slots used, live entries
   int n_top[2];                         // book: entries per side in shared memory
   unsigned near_free;                   // free payload slots of the near tier
+  int n_pfree[2];                       // book pools: free (tombstoned) slots available for reuse
+  int last_hint;                        // pool slot + 1 of the order book_enter just placed (0: shared part)
   unsigned book_arr;                    // arrival counter of resting orders (time priority)
   long long pb_t[2]; unsigned long long pb_k[2];   // per side: lower bound of every pool key
   int last_trade, has_last_trade;
@@ -168,6 +170,7 @@ struct DevBatch {
   EvKey* a_keys; EvPay* a_pay;          // [n_instances][A_CAP]
   EvKey* b_keys; EvPay* b_pay;          // [n_instances][b_cap]
   EvKey* p_keys; EvPay* p_pay;          // [n_instances][2][deep_cap] book pools
+  int* p_free;                          // [n_instances][2][deep_cap] free-slot stacks of the pools
   OpenOrd* arena;
   TxnRow* txn_log;                      // [n_instances][TXN_CAP]
   TxnRow* unrolled;                     // [n_instances][UNR_CAP]
@@ -185,6 +188,7 @@ struct Run {                            // per-launch context, shared memory, no
   abides_instance_cfg cfg;
   EvKey* lk[N_LISTS]; EvPay* lp[N_LISTS]; int lcap[N_LISTS];
   OpenOrd* arena; TxnRow* txn_log; TxnRow* unrolled;
+  int* pfree[2];
   abides_trace_rec* trace;
   unsigned* mt0;                        // MT state of this instance's stream 0 (agent 0)
   const double* lat_to; const double* lat_from;   // this instance's rows
@@ -778,18 +782,40 @@ __device__ __noinline__ void pool_append(int s, int price, int qty, int id, int 
   const int L = L_POOL + s;
   const long long kt = pool_rank(s, price); const unsigned long long kk = pool_k2((unsigned)arr, id);
   if (HOT.l_live[L] == 0 || key_less(kt, kk, HOT.pb_t[s], HOT.pb_k[s])) { HOT.pb_t[s] = kt; HOT.pb_k[s] = kk; }
-  list_append(L, kt, kk, price, qty, id, agent, hseq, arr);
+  // slots never move (no compaction): a tombstoned slot is reused, so the slot handed back as a hint stays valid
+  int i;
+  const int nf = HOT.n_pfree[s];
+  if (nf > 0) { i = RUN.pfree[s][nf - 1]; HOT.n_pfree[s] = nf - 1; }
+  else {
+    i = HOT.l_total[L];
+    if (i >= RUN.lcap[L]) { HOT.status = ABIDES_EOVERFLOW; HOT.last_hint = 0; return; }
+    HOT.l_total[L] = i + 1;
+  }
+  if (LANE == 0) { EvKey k; k.t = kt; k.k2 = kk; RUN.lk[L][i] = k; }
+  else if (LANE == 1) *reinterpret_cast<int4*>(&RUN.lp[L][i].w[0]) = make_int4(price, qty, id, agent);
+  else if (LANE == 2) *reinterpret_cast<int4*>(&RUN.lp[L][i].w[4]) = make_int4(hseq, arr, 0, 0);
+  __syncwarp();
+  HOT.l_live[L] += 1;
+  HOT.last_hint = i + 1;
+}
+__device__ __forceinline__ void pool_free_slot(int s, int i) {                  // tombstone slot i (all lanes call)
+  const int nf = HOT.n_pfree[s];
+  __syncwarp();
+  if (LANE == 0) { RUN.lk[L_POOL + s][i].t = LLONG_MAX; RUN.pfree[s][nf] = i; }
+  __syncwarp();
+  HOT.n_pfree[s] = nf + 1;
+  HOT.l_live[L_POOL + s] -= 1;
 }
 // the shared-memory part ran empty: pull the best price levels of the pool back in
 __device__ __noinline__ void side_refill(int s) {
   const int L = L_POOL + s;
   if (HOT.n_top[s] > 0 || HOT.l_live[L] == 0) return;
-  if (HOT.l_total[L] > 256 && HOT.l_live[L] * 2 < HOT.l_total[L]) list_compact(L);
   const int cnt = choose_limit(L, L, TOP_FILL, TOP_FILL_MIN, TOP_FILL, LLONG_MAX - 1, 0ull);
   if (HOT.status) return;
   const long long pt = HOT.sel_t; const unsigned long long pk = HOT.sel_k;
   EvKey* keys = RUN.lk[L]; const EvPay* pay = RUN.lp[L];
-  const int n = HOT.l_total[L];
+  int* fr = RUN.pfree[s];
+  const int n = HOT.l_total[L], nf = HOT.n_pfree[s];
   int nn = 0;
 #pragma unroll 1
   for (int base = 0; base < n; base += 32) {
@@ -804,10 +830,12 @@ __device__ __noinline__ void side_refill(int s) {
         BookOrd o; o.price = p.w[0]; o.qty = p.w[1]; o.id = p.w[2]; o.agent = p.w[3];
         ST.top[s][pos] = o; ST.tseq[s][pos] = p.w[4]; ST.tarr[s][pos] = p.w[5];
         keys[i].t = LLONG_MAX;
+        fr[nf + pos] = i;
       }
       nn += __popc(m);
     }
   }
+  HOT.n_pfree[s] = nf + nn;
   __syncwarp();
   // rank sort (<= TOP_FILL = 32 entries, lane i owns entry i): better price first, then arrival
   BookOrd e; int eq = 0, ea = 0, rank = 0;
@@ -875,6 +903,7 @@ __device__ __noinline__ void book_enter(int s, int price, int qty, int id, int a
     }
     top_insert(s, ns, cs, price, qty, id, agent, oseq, arr);
     HOT.n_top[s] = ns + 1;
+    HOT.last_hint = 0;
   } else {
     pool_append(s, price, qty, id, agent, oseq, arr);
   }
@@ -996,9 +1025,9 @@ __device__ __noinline__ void replay_emit(int rcpt, int code, bool is_buy, int id
   __syncwarp();
 }
 template <bool RP>
-__device__ __forceinline__ void book_send(int rcpt, int code, bool is_buy, int id, int price, int qty, int fill) {
+__device__ __forceinline__ void book_send(int rcpt, int code, bool is_buy, int id, int price, int qty, int fill, int w1 = 0) {
   if (RP) replay_emit(rcpt, code, is_buy, id, price, qty, fill);
-  else k_send(0, rcpt, code == ABIDES_MSG_ORDER_MODIFIED ? 0 : RUN.cfg.exch_pipeline_delay, order_w0(code, is_buy), 0,
+  else k_send(0, rcpt, code == ABIDES_MSG_ORDER_MODIFIED ? 0 : RUN.cfg.exch_pipeline_delay, order_w0(code, is_buy), w1,
               id, price, qty, fill);        // ORDER_ACCEPTED/CANCELLED/EXECUTED get +pipeline_delay (ExchangeAgent.py:404-407)
 }
 
@@ -1028,7 +1057,7 @@ __device__ __noinline__ void book_handle_limit(int agent, int id, int price, int
       if (qty <= 0) break;
     } else {
       book_enter(is_buy ? BID : ASK, price, qty, id, agent);
-      book_send<RP>(agent, ABIDES_MSG_ORDER_ACCEPTED, is_buy, id, price, qty, -1);
+      book_send<RP>(agent, ABIDES_MSG_ORDER_ACCEPTED, is_buy, id, price, qty, -1, HOT.last_hint);   // w1: pool slot hint
       break;
     }
   }
@@ -1040,11 +1069,18 @@ __device__ __noinline__ void book_handle_limit(int agent, int id, int price, int
 }
 // OrderBook.cancelOrder (:300-348)
 template <bool RP>
-__device__ __noinline__ void book_cancel(int agent, int id, int price, bool is_buy) {
+__device__ __noinline__ void book_cancel(int agent, int id, int price, bool is_buy, int hint) {
   const int s = is_buy ? BID : ASK;
-  int where = side_find(s, price, id);
-  if (where == 0) return;
-  int idx = HOT.find_idx;
+  int where = 0, idx = 0;
+  if (hint > 0 && hint <= HOT.l_total[L_POOL + s]) {       // the slot the exchange reported when it accepted the order
+    const EvKey k = RUN.lk[L_POOL + s][hint - 1];
+    if (k.t == pool_rank(s, price) && (unsigned)k.k2 == (unsigned)id) { where = 2; idx = hint - 1; }
+  }
+  if (where == 0) {
+    where = side_find(s, price, id);
+    if (where == 0) return;
+    idx = HOT.find_idx;
+  }
   int oid, oprice, oqty;
   if (where == 1) {
     BookOrd o = ST.top[s][idx];
@@ -1056,10 +1092,7 @@ __device__ __noinline__ void book_cancel(int agent, int id, int price, bool is_b
     const int L = L_POOL + s;
     const int4 p = *reinterpret_cast<const int4*>(&RUN.lp[L][idx].w[0]);
     oprice = p.x; oqty = p.y; oid = p.z;
-    __syncwarp();
-    if (LANE == 0) RUN.lk[L][idx].t = LLONG_MAX;
-    __syncwarp();
-    HOT.l_live[L] -= 1;
+    pool_free_slot(s, idx);
   }
   book_send<RP>(agent, ABIDES_MSG_ORDER_CANCELLED, is_buy, oid, oprice, oqty, -1);
 }
@@ -1195,10 +1228,14 @@ __device__ __noinline__ void ta_place_limit(int a, long long qty, bool is_buy, l
 }
 __device__ __noinline__ void ta_cancel_all(int a) {
   AgentRec& A = ST.ag;
+  const int klass = c_db.types[A.type_idx].klass;
+  const bool hinted = klass == ABIDES_ZI || klass == ABIDES_VALUE;
   __syncwarp();
   for (int i = 0; i < A.ord_cnt; i++) {
     OpenOrd o = RUN.arena[A.ord_off + i];
-    agent_send(a, order_w0(ABIDES_MSG_CANCEL_ORDER, o.sqty > 0), o.id, o.price, o.sqty < 0 ? -o.sqty : o.sqty, -1);
+    int hint = -1;                                       // w5 of a CANCEL_ORDER: pool slot hint (not part of the reference message)
+    if (hinted && o.id == A.u.est.hint_id && A.u.est.hint > 0) hint = A.u.est.hint;
+    agent_send(a, order_w0(ABIDES_MSG_CANCEL_ORDER, o.sqty > 0), o.id, o.price, o.sqty < 0 ? -o.sqty : o.sqty, hint);
   }
 }
 __device__ __noinline__ int ord_find(int key) {
@@ -1261,6 +1298,9 @@ __device__ __forceinline__ void ta_receive(int a, const Msg& m, int klass, const
       }
       break;
     }
+    case ABIDES_MSG_ORDER_ACCEPTED:                           // (not in the reference) remember where the order rests
+      if (klass == ABIDES_ZI || klass == ABIDES_VALUE) { A.u.est.hint_id = m.w2; A.u.est.hint = m.w1; }
+      break;
     case ABIDES_MSG_ORDER_CANCELLED: {
       int idx = ord_find(m.w2);
       if (idx >= 0) ord_remove(idx);
@@ -1605,7 +1645,7 @@ __device__ __noinline__ void exchange_receive(int w0, int w1, int w2, int w3, in
       book_handle_market<false>(sender, w4, pay_is_buy(w0));
       break;
     case ABIDES_MSG_CANCEL_ORDER:
-      book_cancel<false>(sender, oid, w3, pay_is_buy(w0));
+      book_cancel<false>(sender, oid, w3, pay_is_buy(w0), w5 > 0 ? w5 : 0);
       break;
     case ABIDES_MSG_MODIFY_ORDER:
       book_modify<false>(sender, oid, w3, w5, pay_is_buy(w0));
@@ -1821,6 +1861,7 @@ __device__ __noinline__ void run_setup(int inst) {
     r.lk[L_POOL + s] = db.p_keys + ((size_t)inst * 2 + s) * db.deep_cap;
     r.lp[L_POOL + s] = db.p_pay + ((size_t)inst * 2 + s) * db.deep_cap;
     r.lcap[L_POOL + s] = db.deep_cap;
+    r.pfree[s] = db.p_free + ((size_t)inst * 2 + s) * db.deep_cap;
   }
   r.arena = db.arena + (size_t)inst * db.arena_cap;
   r.txn_log = db.txn_log + (size_t)inst * TXN_CAP;
@@ -1949,7 +1990,7 @@ __global__ void __launch_bounds__(32) sim_kernel(long long until_time) {
 __global__ void __launch_bounds__(32) replay_kernel(int n_books, const long long* op_offset, const abides_book_op* ops,
                                                     int stream_history, int max_events, abides_book_event* events,
                                                     int* counts, abides_book_state* states, EvKey* pool_keys, EvPay* pool_pay,
-                                                    int deep_cap) {
+                                                    int* pool_free, int deep_cap) {
   int b = blockIdx.x, lane = threadIdx.x;
   if (b >= n_books) return;
   for (int i = lane; i < (int)(sizeof(Smem) / 4); i += 32) reinterpret_cast<unsigned*>(SM)[i] = 0;
@@ -1961,6 +2002,7 @@ __global__ void __launch_bounds__(32) replay_kernel(int n_books, const long long
       r.lk[L_POOL + s] = pool_keys + ((size_t)b * 2 + s) * deep_cap;
       r.lp[L_POOL + s] = pool_pay + ((size_t)b * 2 + s) * deep_cap;
       r.lcap[L_POOL + s] = deep_cap;
+      r.pfree[s] = pool_free + ((size_t)b * 2 + s) * deep_cap;
       HOT.span[L_POOL + s] = 64;
     }
     r.txn_log = nullptr;
@@ -1979,7 +2021,7 @@ __global__ void __launch_bounds__(32) replay_kernel(int n_books, const long long
     switch (op.kind) {
       case ABIDES_MSG_LIMIT_ORDER: book_handle_limit<true>(op.agent, (int)op.order_id, (int)op.price, (int)op.qty, buy); break;
       case ABIDES_MSG_MARKET_ORDER: book_handle_market<true>(op.agent, (int)op.qty, buy); break;
-      case ABIDES_MSG_CANCEL_ORDER: book_cancel<true>(op.agent, (int)op.order_id, (int)op.price, buy); break;
+      case ABIDES_MSG_CANCEL_ORDER: book_cancel<true>(op.agent, (int)op.order_id, (int)op.price, buy, 0); break;
       case ABIDES_MSG_MODIFY_ORDER: book_modify<true>(op.agent, (int)op.order_id, (int)op.price, (int)op.new_qty, buy); break;
       default: break;
     }
@@ -2210,6 +2252,7 @@ int abides_load(abides_handle* h, const abides_batch* b) {
     if ((rc = dev_alloc(h, &d.arena, (size_t)ni * d.arena_cap))) return rc;
     if ((rc = dev_alloc(h, &d.p_keys, (size_t)ni * 2 * d.deep_cap))) return rc;
     if ((rc = dev_alloc(h, &d.p_pay, (size_t)ni * 2 * d.deep_cap))) return rc;
+    if ((rc = dev_alloc(h, &d.p_free, (size_t)ni * 2 * d.deep_cap))) return rc;
     if ((rc = dev_alloc(h, &d.txn_log, (size_t)ni * TXN_CAP))) return rc;
     if ((rc = dev_alloc(h, &d.unrolled, (size_t)ni * UNR_CAP))) return rc;
     if ((rc = dev_alloc(h, &d.mom_ring, (size_t)(n_mom > 0 ? n_mom : 1) * MOM_RING))) return rc;
@@ -2342,9 +2385,9 @@ int abides_replay_book(abides_handle* h, int32_t n_books, const int64_t* op_offs
       return fail(ABIDES_EINVAL, "abides_replay_book: price / quantity / order id outside the device's int32 range");
   int deep_cap = (int)(longest + 64);
   long long* d_off = nullptr; abides_book_op* d_ops = nullptr; abides_book_event* d_ev = nullptr; int* d_cnt = nullptr;
-  abides_book_state* d_st = nullptr; EvKey* d_deep = nullptr; EvPay* d_seq = nullptr;
+  abides_book_state* d_st = nullptr; EvKey* d_deep = nullptr; EvPay* d_seq = nullptr; int* d_free = nullptr;
   int rc = 0;
-  auto cleanup = [&]() { cudaFree(d_off); cudaFree(d_ops); cudaFree(d_ev); cudaFree(d_cnt); cudaFree(d_st); cudaFree(d_deep); cudaFree(d_seq); };
+  auto cleanup = [&]() { cudaFree(d_off); cudaFree(d_ops); cudaFree(d_ev); cudaFree(d_cnt); cudaFree(d_st); cudaFree(d_deep); cudaFree(d_seq); cudaFree(d_free); };
 #define RCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return fail(ABIDES_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
   RCK(cudaMalloc(&d_off, sizeof(long long) * (n_books + 1)));
   RCK(cudaMalloc(&d_ops, sizeof(abides_book_op) * n_ops));
@@ -2353,13 +2396,14 @@ int abides_replay_book(abides_handle* h, int32_t n_books, const int64_t* op_offs
   RCK(cudaMalloc(&d_st, sizeof(abides_book_state) * n_ops));
   RCK(cudaMalloc(&d_deep, sizeof(EvKey) * (size_t)n_books * 2 * deep_cap));
   RCK(cudaMalloc(&d_seq, sizeof(EvPay) * (size_t)n_books * 2 * deep_cap));
+  RCK(cudaMalloc(&d_free, sizeof(int) * (size_t)n_books * 2 * deep_cap));
   RCK(cudaMemcpyAsync(d_off, op_offset, sizeof(long long) * (n_books + 1), cudaMemcpyHostToDevice, h->stream));
   RCK(cudaMemcpyAsync(d_ops, ops, sizeof(abides_book_op) * n_ops, cudaMemcpyHostToDevice, h->stream));
   RCK(cudaMemsetAsync(d_ev, 0, sizeof(abides_book_event) * n_ops * max_events_per_op, h->stream));
   RCK(cudaFuncSetAttribute(replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
   RCK(cudaEventRecord(h->ev0, h->stream));
   replay_kernel<<<n_books, 32, sizeof(Smem), h->stream>>>(n_books, d_off, d_ops, stream_history, max_events_per_op, d_ev, d_cnt,
-                                                         d_st, d_deep, d_seq, deep_cap);
+                                                         d_st, d_deep, d_seq, d_free, deep_cap);
   RCK(cudaGetLastError());
   RCK(cudaEventRecord(h->ev1, h->stream));
   RCK(cudaMemcpyAsync(events_out, d_ev, sizeof(abides_book_event) * n_ops * max_events_per_op, cudaMemcpyDeviceToHost, h->stream));
