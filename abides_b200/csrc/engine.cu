@@ -432,7 +432,7 @@ __device__ __forceinline__ int near_alloc(int w0, int w1, int w2, int w3, int w4
   return slot;
 }
 // insert (t, k2) -> payload slot; needs n_near < NEAR_CAP
-__device__ __noinline__ void near_insert(long long t, unsigned long long k2, int slot) {
+__device__ __forceinline__ void near_insert_body(long long t, unsigned long long k2, int slot) {
   const int n = HOT.n_near, lane = LANE;
   long long et = 0; unsigned long long ek = 0; int es = 0;
   bool gt = false;
@@ -443,6 +443,7 @@ __device__ __noinline__ void near_insert(long long t, unsigned long long k2, int
   HOT.n_near = n + 1;
   __syncwarp();
 }
+__device__ __noinline__ void near_insert(long long t, unsigned long long k2, int slot) { near_insert_body(t, k2, slot); }
 // near tier full: hand its largest key (entry 0) to list A and pull near_limit down to it
 __device__ __noinline__ void near_spill() {
   const int lane = LANE;
@@ -603,6 +604,8 @@ __device__ __noinline__ void q_push(long long t, unsigned long long k2, int w0, 
   } else {
     list_append(L_B, t, k2, w0, w1, w2, w3, w4, w5);
   }
+}
+__device__ __forceinline__ void track_queue_peak() {      // sampled at refills (diagnostic only)
   int tot = HOT.n_near + HOT.l_live[L_A] + HOT.l_live[L_B];
   if (tot > HOT.queue_peak) HOT.queue_peak = tot;
 }
@@ -610,6 +613,7 @@ __device__ __noinline__ void q_push(long long t, unsigned long long k2, int w0, 
 // near tier is empty: pull the next batch (<= FILL_MAX smallest keys) out of list A (refilled from B when dry)
 __device__ __noinline__ void q_refill() {
   PROF_CNT(P_N_REFILL);
+  track_queue_peak();
   if (HOT.l_live[L_A] == 0) {
     HOT.l_total[L_A] = 0;
     if (HOT.l_live[L_B] == 0) return;
@@ -662,23 +666,35 @@ __device__ __noinline__ void q_refill() {
 // ----------------------------------------------------------------------------------------------
 __device__ __noinline__ void k_send(int sender, int rcpt, long long delay, int w0, int w1, int w2, int w3, int w4, int w5) {
   const abides_instance_cfg& cfg = RUN.cfg;
-  double minlat = sender == 0 ? RUN.lat_from[rcpt] : RUN.lat_to[sender];
-  long long cd = sender == 0 ? HOT.exch_cd : cfg.default_computation_delay;
-  long long sent = HOT.now + cd + HOT.additional_delay + delay;
+  const double minlat = sender == 0 ? RUN.lat_from[rcpt] : RUN.lat_to[sender];
+  const long long cd = sender == 0 ? HOT.exch_cd : cfg.default_computation_delay;
+  const long long sent = HOT.now + cd + HOT.additional_delay + delay;
+  const int kind = cfg.latency_kind;
   long long lat;
-  if (cfg.latency_kind == ABIDES_LAT_DETERMINISTIC) {
+  if (kind == ABIDES_LAT_LEGACY_NOISE) {
+    // random_state.choice(len(noise), 1, noise) == randint(0, len(noise)) (Kernel.py:380): masked rejection
+    const unsigned rng = (unsigned)(cfg.n_latency_noise - 1);
+    unsigned v = 0;
+    if (rng != 0) {
+      unsigned mask = rng;
+      mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+      while ((v = (rng_u32(ABIDES_STREAM_KERNEL) & mask)) > rng) {}
+    }
+    lat = (long long)(minlat + (double)(long long)v);
+  } else if (kind == ABIDES_LAT_DETERMINISTIC) {
     lat = (long long)minlat;
-  } else if (cfg.latency_kind == ABIDES_LAT_CUBIC) {
+  } else {
     double x = rng_uniform(ABIDES_STREAM_LATENCY, cfg.jitter_clip, 1.0);
     double l = minlat + (fdiv(cfg.jitter, abm_cube(x)) * fdiv(minlat, cfg.jitter_unit));
     lat = (long long)l;
-  } else {
-    long long noise = rng_randint(ABIDES_STREAM_KERNEL, 0, cfg.n_latency_noise);
-    lat = (long long)(minlat + (double)noise);
   }
-  unsigned u = HOT.uniq;
+  const unsigned u = HOT.uniq;
   HOT.uniq = u + 1;
-  q_push(sent + lat, ((unsigned long long)(unsigned)rcpt << 33) | (unsigned long long)u, w0, w1, w2, w3, w4, w5);
+  const long long t = sent + lat;
+  const unsigned long long k2 = ((unsigned long long)(unsigned)rcpt << 33) | (unsigned long long)u;
+  // fast path: straight into the sorted shared-memory tier
+  if (key_less(t, k2, HOT.lim_t, HOT.lim_k) && HOT.n_near < NEAR_CAP) near_insert_body(t, k2, near_alloc(w0, w1, w2, w3, w4, w5));
+  else q_push(t, k2, w0, w1, w2, w3, w4, w5);
 }
 __device__ __noinline__ void k_wakeup(int agent, long long t) {
   if (t < HOT.now) { HOT.status = ABIDES_EINVAL; return; }
