@@ -25,6 +25,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+CPU_TTL = []
 ALGO_BYTES_PER_MESSAGE = 160          # pop 16 + payload 16 + agent state r/w 80 + emit 32 + book 16
 BASELINE_PUBLISHED = {"sparse_zi_1000": 3100.4, "sparse_zi_100": 3585.4}   # BASELINE.md section 1 (1 core i7)
 WORKLOADS = {
@@ -32,6 +33,9 @@ WORKLOADS = {
     "sparse_zi_1000": ("sparse_zi_1000", []),
     "rmsc03": ("rmsc03", ["-t", "ABM", "-d", "20200603", "--end-time", "16:00:00"]),
     "rmsc03_2h": ("rmsc03", ["-t", "ABM", "-d", "20200603"]),
+    # BASELINE configs[2] "rmsc01: value + noise agents + market maker", from the supported classes
+    "rmsc01": ("rmsc03", ["-t", "ABM", "-d", "20200603", "--end-time", "16:00:00", "--num-noise", "50",
+                          "--num-value", "25", "--num-momentum", "24"]),
 }
 
 
@@ -117,7 +121,9 @@ def cpu_baseline(hb, n_sample, threads):
     t0 = time.perf_counter()
     res, _ = oracle.run_batch(hb, n_threads=threads, first=0, count=n_sample)
     dt = time.perf_counter() - t0
-    msgs = sum(res[i].ttl_messages for i in range(n_sample))
+    global CPU_TTL
+    CPU_TTL = [int(res[i].ttl_messages) for i in range(n_sample)]      # also a parity spot check against the device
+    msgs = sum(CPU_TTL)
     return msgs, dt
 
 
@@ -280,6 +286,7 @@ def main():
     if world == 1:
         n_sample = args.cpu_sample or args.instances        # the whole batch once (~2-3 s wall, tens of core-seconds)
         m, dt = cpu_baseline(hb, n_sample, cores)
+        line["cpu_sample_ttl_messages_match"] = bool(CPU_TTL == [int(x) for x in res["ttl_messages"][:n_sample]])
         line["cpu_baseline"] = {"value": m / dt, "unit": "messages/s", "cores": cores, "kind": "port",
                                 "sample": "first %d instances of the same batch on %d host threads, %.1f s "
                                           "(oracle/abides_oracle.c)" % (n_sample, cores, dt)}

@@ -36,6 +36,8 @@ def main():
     ap.add_argument("--spec", action="store_true", help="store the full lowered spec")
     ap.add_argument("--trace", action="store_true", help="store the full dispatch trace")
     ap.add_argument("--out", default=os.path.join(REPO, "tests", "golden"))
+    ap.add_argument("--config-path", default=None,
+                    help="run this config FILE (written against the reference API) instead of config.<name>")
     ap.add_argument("ref_args", nargs=argparse.REMAINDER)
     args = ap.parse_args()
     ref_args = [a for a in args.ref_args if a != "--"]
@@ -135,7 +137,12 @@ def main():
     buf = io.StringIO()
     import importlib
     with redirect_stdout(buf):
-        importlib.import_module("config." + cfg)
+        if args.config_path:
+            import runpy
+            runpy.run_path(os.path.join(REPO, args.config_path) if not os.path.isabs(args.config_path)
+                           else args.config_path, run_name="__abides_config__")
+        else:
+            importlib.import_module("config." + cfg)
     out = buf.getvalue()
     m = re.search(r"messages: (\d+), messages per second", out)
     ttl = int(m.group(1))

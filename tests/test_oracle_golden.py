@@ -20,6 +20,10 @@ CASES = {
     "zi100_s123456789": ("sparse_zi_100", ["-s", "123456789"]),
     "zi1000_s123456789": ("sparse_zi_1000", ["-s", "123456789"]),
     "rmsc03_s1234_1000": ("rmsc03", ["-t", "ABM", "-d", "20200603", "-s", "1234", "--end-time", "10:00:00"]),
+    # BASELINE configs[2] "rmsc01: value + noise agents + market maker" from the supported classes: the rmsc03
+    # population at rmsc01 scale (103 agents), one full market day; reference side: tests/golden/refcfg/rmsc_small.py
+    "rmsc01s_s77": ("rmsc03", ["-t", "ABM", "-d", "20200603", "-s", "77", "--end-time", "16:00:00",
+                               "--num-noise", "50", "--num-value", "25", "--num-momentum", "24"]),
 }
 
 
