@@ -178,7 +178,7 @@ def main():
                                  "sample": "%d instances of %s per step on %d host threads (C restatement of the "
                                            "reference, oracle/abides_oracle.c)" % (n_sample, args.workload, cores)},
                 "e2e": {"value": v, "unit": "messages/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
         return 0
 
     # ---- our arm: build the host batch BEFORE touching CUDA (the builder forks a process pool) ----
@@ -295,7 +295,7 @@ def main():
         line["cpu_baseline"] = {"value": m / dt, "unit": "messages/s", "cores": cores, "kind": "port",
                                 "sample": "first %d instances of the same batch on %d host threads, %.1f s "
                                           "(oracle/abides_oracle.c)" % (n_sample, cores, dt)}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
     return 0
