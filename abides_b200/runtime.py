@@ -233,3 +233,19 @@ def gather_summaries(res, dist=None, device=None):
     dist.all_gather(out, t)
     parts = [o.cpu().numpy()[:c * words] for o, c in zip(out, counts)]
     return np.frombuffer(np.concatenate(parts).tobytes(), dtype=INSTANCE_RESULT_DTYPE).copy()
+
+
+def grid_arg_lists(base_args, grid, seeds):
+    """Cartesian parameter grid x seeds as config argument lists (the reference's util/make_grid.py and
+    scripts/market_maker sweeps launch one process per point; here every point is one instance of ONE batch).
+    `grid` maps a config flag (e.g. "--mm-pov") to its list of values."""
+    import itertools
+    keys = list(grid)
+    out = []
+    for combo in itertools.product(*[grid[k] for k in keys]):
+        for s in seeds:
+            args = list(base_args) + ["-s", s]
+            for k, v in zip(keys, combo):
+                args += [k, v]
+            out.append(args)
+    return out

@@ -88,3 +88,22 @@ def test_reset_reruns_identically():
     assert np.array_equal(res["ttl_messages"], res2["ttl_messages"])
     assert np.array_equal(ares["cash"], ares2["cash"])
     assert res2["ttl_messages"][0] == 21799
+
+
+def test_device_parameter_grid_matches_oracle():
+    """BASELINE configs[4]: an rmsc03 parameter grid is ONE heterogeneous batch (instances differ in agent counts,
+    market-maker parameters and seeds)."""
+    grid = {"--num-noise": [40, 80], "--mm-num-ticks": [5, 10], "--mm-pov": [0.01, 0.05]}
+    args = runtime.grid_arg_lists(["-t", "ABM", "-d", "20200603", "--end-time", "09:45:00", "--num-value", "10",
+                                   "--num-momentum", "5"], grid, runtime.parallel_seeds(5, 2))
+    specs = runtime.build_specs_parallel("rmsc03", args)
+    assert len(specs) == 16 and len(set(s.n_agents for s in specs)) == 2
+    hb = lowering.HostBatch(specs)
+    eng, res, ares = device_run(hb)
+    ok = res["status"] == 0
+    ores, oares = oracle.run_batch(hb)
+    for i in range(hb.n_instances):
+        assert res["status"][i] == ores[i].status                 # incl. instances where the reference would raise
+        for f in ("ttl_messages", "delivered", "n_orders", "n_fills", "traded_volume", "last_trade"):
+            assert res[f][i] == getattr(ores[i], f), (i, f)
+    assert ok.sum() >= 12
