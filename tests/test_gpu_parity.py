@@ -107,3 +107,68 @@ def test_device_parameter_grid_matches_oracle():
         for f in ("ttl_messages", "delivered", "n_orders", "n_fills", "traded_volume", "last_trade"):
             assert res[f][i] == getattr(ores[i], f), (i, f)
     assert ok.sum() >= 12
+
+
+def test_pause_and_resume_equals_one_run():
+    """abides_run(until_time) parks the batch in HBM mid-day; resuming gives the same day as one uninterrupted run."""
+    spec = load_spec("zi100_s123456789")
+    hb = lowering.HostBatch([spec] * 2)
+    eng, res, ares = device_run(hb)
+    from abides_b200.engine import Engine
+    e2 = Engine(0)
+    e2.load(hb)
+    mid = (hb.instances[0].mkt_open + hb.instances[0].mkt_close) // 2
+    e2.run(until_time=hb.instances[0].mkt_open)          # before the first trade
+    e2.run(until_time=mid)
+    e2.run(until_time=mid)                                # idempotent: nothing left below `mid`
+    e2.run()
+    r2, a2 = e2.results_arrays()
+    for f in ("ttl_messages", "delivered", "n_fills", "traded_volume", "last_trade", "final_time"):
+        assert np.array_equal(res[f], r2[f]), f
+    assert np.array_equal(ares["cash"], a2["cash"]) and np.array_equal(ares["holdings"], a2["holdings"])
+
+
+def test_full_size_batch_invariants():
+    """BASELINE configs[1] at full size (1024 x sparse_zi_1000): size-independent properties of a closed market,
+    plus the oracle on a subset.  Cash only moves between agents and shares are only exchanged, so per instance
+    sum(cash - starting_cash) == 0 and sum(holdings) == 0; every fill is reported to two agents."""
+    n = 1024
+    seeds = runtime.parallel_seeds(20261019, n)
+    specs = runtime.build_specs_parallel("sparse_zi_1000", [["-s", s] for s in seeds])
+    hb = lowering.HostBatch(specs)
+    eng, res, ares = device_run(hb)
+    assert (res["status"] == 0).all()
+    assert (res["ttl_messages"] >= res["delivered"]).all() and (res["delivered"] > 100000).all()
+    start = specs[0].types[specs[0].agent_type[1]]["starting_cash"]
+    cash = ares["cash"].reshape(n, -1)[:, 1:]
+    hold = ares["holdings"].reshape(n, -1)[:, 1:]
+    assert ((cash - start).sum(axis=1) == 0).all()
+    assert (hold.sum(axis=1) == 0).all()
+    assert (np.abs(hold) % 100 == 0).all()                 # ZI agents trade 100-share lots
+    assert (res["traded_volume"] == 100 * res["n_fills"]).all()
+    # identical re-run after reset (no host traffic)
+    eng.reset(); eng.run()
+    r2, a2 = eng.results_arrays()
+    assert np.array_equal(res["ttl_messages"], r2["ttl_messages"]) and np.array_equal(ares["cash"], a2["cash"])
+    # the first 32 instances against the CPU oracle
+    sub = lowering.HostBatch(specs[:32])
+    ores, oares = oracle.run_batch(sub)
+    assert [int(ores[i].ttl_messages) for i in range(32)] == [int(x) for x in res["ttl_messages"][:32]]
+    o = np.frombuffer(oares, dtype=ares.dtype)
+    assert np.array_equal(o["cash"], ares["cash"][:len(o)])
+
+
+def test_load_rejects_malformed_batches():
+    from abides_b200.engine import Engine, EngineError
+    spec = load_spec("zi100_s123456789")
+    hb = lowering.HostBatch([spec])
+    hb.agent_type[0] = 1                                    # agent 0 must be the exchange
+    eng = Engine(0)
+    with pytest.raises(EngineError, match="exchange"):
+        eng.load(hb)
+    hb = lowering.HostBatch([spec])
+    hb.c.n_agents_total += 1
+    with pytest.raises(EngineError, match="n_agents_total"):
+        eng.load(hb)
+    with pytest.raises(EngineError, match="no batch loaded"):
+        Engine(0).run()
