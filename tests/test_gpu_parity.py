@@ -172,3 +172,20 @@ def test_load_rejects_malformed_batches():
         eng.load(hb)
     with pytest.raises(EngineError, match="no batch loaded"):
         Engine(0).run()
+
+
+def test_philox_throughput_mode_matches_oracle():
+    """Counter-based Philox4x32-10 streams keyed by (instance seed, stream): no RNG state is uploaded; device and
+    oracle implement the same keyed streams, so the runs are still bit-identical to each other (they are
+    statistically, not bit-wise, equivalent to the reference's MT19937 runs)."""
+    from abides_b200 import _abi
+    seeds = runtime.parallel_seeds(21, 12)
+    specs = runtime.build_specs_parallel("sparse_zi_100", [["-s", s] for s in seeds])
+    hb = lowering.HostBatch(specs, rng_mode=_abi.RNG_PHILOX)
+    assert hb.mt_key is None and hb.h2d_bytes() < 200000
+    eng, res, ares = device_run(hb)
+    _compare_with_oracle(hb, res, ares)
+    mt = lowering.HostBatch(specs)
+    _, res_mt, _ = device_run(mt)
+    assert not np.array_equal(res["ttl_messages"], res_mt["ttl_messages"])          # different streams ...
+    assert abs(res["ttl_messages"].mean() / res_mt["ttl_messages"].mean() - 1) < 0.05   # ... same market
