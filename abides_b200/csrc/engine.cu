@@ -18,21 +18,24 @@
 //   * order book   : per side the best <= BOOK_TOP orders price-time sorted in shared memory (matching,
 //                    level sums, inserts and cancels are ballot/popc scans and warp-wide shifts) over
 //                    an unsorted "pool" list in HBM in the same key/payload format as the event lists
-//                    (key = price rank, arrival number | order id), so deep inserts are O(1) appends,
-//                    deep cancels one coalesced key scan, and the pool -> top refill reuses the event
-//                    queue's window selection;
+//                    (key = price rank, arrival number | order id).  Pool slots never move (tombstones
+//                    are reused), the slot is reported with ORDER_ACCEPTED and handed back with the
+//                    cancel, so deep inserts and deep cancels are O(1); the pool -> top refill reuses
+//                    the event queue's window selection;
 //   * agent state  : one 128-byte record per agent in HBM, moved to/from shared memory with one
 //                    coalesced transaction per dispatch (skipped when the same agent is dispatched
 //                    again, e.g. busy re-queues); handler code is warp-uniform;
 //   * RNG          : per-stream MT19937 state in HBM (reference-exact mode, warp-parallel twist)
 //                    or counter-based Philox4x32-10 (throughput mode).
 //
-// The kernel is bound by INSTRUCTION FETCH (profiles/): one warp walks ~750 mostly cold instructions per
-// event, the per-SM instruction cache holds 32 KB (scripts/microbench/icache*.cu), the hot set of the engine
-// is larger, and ncu shows the GPC-level instruction cache ~90 % busy in every version of this kernel
-// (run time == its request count / 7e9 per second).  So the code is kept small: events travel in
-// registers, big bodies are __noinline__ and shared by all call sites, the four HBM lists (event lists A/B,
-// two book pools) share one implementation, the batch descriptor lives in constant memory.
+// The kernel is bound by INSTRUCTION FETCH (profiles/): one warp walks ~670 mostly cold
+// instructions per event; the instruction cache holds 32 KB per TPC -- two SMs share it
+// (scripts/microbench/icache_tpc.cu) -- the hot set of the engine is larger, and ncu shows the GPC-level
+// instruction cache ~90 % busy in every version of this kernel (run time == its request count / 7.1e9 per
+// second).  So the code is kept SMALL rather than "fast": events travel in registers, big bodies are
+// __noinline__ and shared by all call sites, the four HBM lists (event lists A/B, two book pools) share one
+// implementation, the batch descriptor lives in constant memory.  (Inlining hot helpers to save instructions
+// has repeatedly made it slower.)
 //
 // No tensor cores: there is no dense contraction on this path (integer / latency bound).
 #include <cuda_runtime.h>
