@@ -51,6 +51,8 @@
 #include "abides_dd_math.h"
 
 #define FULL 0xffffffffu
+#define UNLIKELY(x) __builtin_expect(!!(x), 0)
+#define LIKELY(x) __builtin_expect(!!(x), 1)
 
 namespace {
 
@@ -318,11 +320,11 @@ __device__ __noinline__ unsigned philox_u32(int sid) {
   return sel == 0 ? o[0] : sel == 1 ? o[1] : sel == 2 ? o[2] : o[3];
 }
 __device__ __noinline__ unsigned rng_u32(int sid) {
-  if (c_db.rng_mode == ABIDES_RNG_PHILOX) return philox_u32(sid);
+  if (UNLIKELY(c_db.rng_mode == ABIDES_RNG_PHILOX)) return philox_u32(sid);
   RngState& r = rng_state(sid);
   unsigned* mt = RUN.mt0 + (size_t)rng_stream(sid) * ABIDES_MT_N;
   int p = r.pos;
-  if (p >= ABIDES_MT_N) { mt_twist(mt); p = 0; }
+  if (UNLIKELY(p >= ABIDES_MT_N)) { mt_twist(mt); p = 0; }
   unsigned y = mt[p];
   r.pos = p + 1;
   y ^= (y >> 11);
@@ -412,7 +414,7 @@ __device__ __noinline__ void list_compact(int L) {
 __device__ __noinline__ void list_append(int L, long long t, unsigned long long k2, int w0, int w1, int w2, int w3,
                                          int w4, int w5) {
   int i = HOT.l_total[L];
-  if (i >= RUN.lcap[L]) {
+  if (UNLIKELY(i >= RUN.lcap[L])) {
     list_compact(L);
     i = HOT.l_total[L];
     if (i >= RUN.lcap[L]) { HOT.status = ABIDES_EOVERFLOW; return; }
@@ -598,12 +600,12 @@ __device__ __noinline__ void a_rebalance() {
 
 __device__ __noinline__ void q_push(long long t, unsigned long long k2, int w0, int w1, int w2, int w3, int w4, int w5) {
   if (key_less(t, k2, HOT.lim_t, HOT.lim_k)) {
-    if (HOT.n_near == NEAR_CAP) near_spill();
+    if (UNLIKELY(HOT.n_near == NEAR_CAP)) near_spill();
     if (key_less(t, k2, HOT.lim_t, HOT.lim_k)) near_insert(t, k2, near_alloc(w0, w1, w2, w3, w4, w5));
     else list_append(L_A, t, k2, w0, w1, w2, w3, w4, w5);
   } else if (key_less(t, k2, HOT.hz_t, HOT.hz_k)) {
     list_append(L_A, t, k2, w0, w1, w2, w3, w4, w5);
-    if (HOT.l_live[L_A] > A_REBALANCE) a_rebalance();
+    if (UNLIKELY(HOT.l_live[L_A] > A_REBALANCE)) a_rebalance();
   } else {
     list_append(L_B, t, k2, w0, w1, w2, w3, w4, w5);
   }
@@ -724,14 +726,14 @@ __device__ __noinline__ double oracle_step(long long ts, double v_adj, long long
   if (!(v > 0)) v = 0;
   v = rint(v);
   HOT.or_pt = ts; HOT.or_pv = v;
-  if (RUN.trace) trace_write(ts, -1, TRACE_FUNDAMENTAL, (long long)v, 0, 0, 0);
+  if (UNLIKELY(RUN.trace != nullptr)) trace_write(ts, -1, TRACE_FUNDAMENTAL, (long long)v, 0, 0, 0);
   return v;
 }
 __device__ __noinline__ double oracle_advance(long long t) {
   const abides_instance_cfg& cfg = RUN.cfg;
   long long pt = HOT.or_pt; double pv = HOT.or_pv;
   if (t <= pt) return pv;
-  while (HOT.ms_time < t) {
+  while (UNLIKELY(HOT.ms_time < t)) {
     double v = oracle_step(HOT.ms_time, HOT.ms_value, pt, pv);
     pt = HOT.ms_time; pv = v;
     double dt = rng_exponential(ABIDES_STREAM_GLOBAL, fdiv(1.0, cfg.megashock_lambda_a));
@@ -807,7 +809,7 @@ __device__ __noinline__ void pool_append(int s, int price, int qty, int id, int 
   if (nf > 0) { i = RUN.pfree[s][nf - 1]; HOT.n_pfree[s] = nf - 1; }
   else {
     i = HOT.l_total[L];
-    if (i >= RUN.lcap[L]) { HOT.status = ABIDES_EOVERFLOW; HOT.last_hint = 0; return; }
+    if (UNLIKELY(i >= RUN.lcap[L])) { HOT.status = ABIDES_EOVERFLOW; HOT.last_hint = 0; return; }
     HOT.l_total[L] = i + 1;
   }
   if (LANE == 0) { EvKey k; k.t = kt; k.k2 = kk; RUN.lk[L][i] = k; }
@@ -914,7 +916,7 @@ __device__ __noinline__ void book_enter(int s, int price, int qty, int id, int a
     to_top = HOT.l_live[L_POOL + s] == 0 ||
              key_less(pool_rank(s, price), pool_k2((unsigned)arr, id), HOT.pb_t[s], HOT.pb_k[s]);
   if (to_top) {
-    if (ns == BOOK_TOP) {                                // spill the worst shared entry to the pool
+    if (UNLIKELY(ns == BOOK_TOP)) {                      // spill the worst shared entry to the pool
       BookOrd w = ST.top[s][ns - 1];
       pool_append(s, w.price, w.qty, w.id, w.agent, ST.tseq[s][ns - 1], ST.tarr[s][ns - 1]);
       if (HOT.status) return;
@@ -1234,16 +1236,16 @@ __device__ __noinline__ void ta_place_limit(int a, long long qty, bool is_buy, l
   int id = (int)h.next_order_id++;
   if (qty <= 0) return;
   OpenOrd oo; oo.key = id; oo.id = id; oo.price = (int)price; oo.sqty = is_buy ? (int)qty : -(int)qty;
-  if (id == 0) oo.id = (int)h.next_order_id++;            // deepcopy of order id 0 takes a fresh id (Order.py:29)
+  if (UNLIKELY(id == 0)) oo.id = (int)h.next_order_id++;            // deepcopy of order id 0 takes a fresh id (Order.py:29)
   int init_cap = ty.klass == ABIDES_ADAPTIVE_MM ? (int)(2 * ty.num_ticks + 8) : (ty.klass == ABIDES_MOMENTUM ? 16 : 4);
   ord_reserve(init_cap);
-  if (h.status) return;
+  if (UNLIKELY(h.status != 0)) return;
   __syncwarp();
   if (LANE == 0) RUN.arena[A.ord_off + A.ord_cnt] = oo;
   __syncwarp();
   A.ord_cnt++;
   agent_send(a, order_w0(ABIDES_MSG_LIMIT_ORDER, is_buy), id, (int)price, (int)qty, -1);
-  if (ty.log_orders && id == 0) h.next_order_id++;
+  if (UNLIKELY(ty.log_orders && id == 0)) h.next_order_id++;
 }
 __device__ __noinline__ void ta_cancel_all(int a) {
   AgentRec& A = ST.ag;
@@ -1289,7 +1291,7 @@ __device__ __noinline__ void ord_remove(int idx) {
 __device__ __forceinline__ bool ta_wakeup(int a) {
   AgentRec& A = ST.ag;
   A.cur_time = HOT.now;
-  if (!(A.flags & F_HAS_OPEN)) {
+  if (UNLIKELY(!(A.flags & F_HAS_OPEN))) {
     agent_send(a, ABIDES_MSG_WHEN_MKT_OPEN, 0, 0, 0, 0);
     agent_send(a, ABIDES_MSG_WHEN_MKT_CLOSE, 0, 0, 0, 0);
   }
@@ -1345,7 +1347,7 @@ __device__ __forceinline__ void ta_receive(int a, const Msg& m, int klass, const
     default: break;
   }
   bool have = (A.flags & F_HAS_OPEN) && (A.flags & F_HAS_CLOSE);
-  if (have && !had) {
+  if (UNLIKELY(have && !had)) {
     long long off;
     if (klass == ABIDES_ZI || klass == ABIDES_VALUE || klass == ABIDES_NOISE) off = rng_randint(SID_AGENT, 0, 100);
     else off = ty.wake_up_freq;
@@ -1389,8 +1391,8 @@ __device__ __noinline__ void zi_place_order(int a, const abides_agent_type& ty) 
   long long obs = oracle_observe(A.cur_time, ty.sigma_n, SID_AGENT);
   long long q = A.holdings / 100;
   bool buy;
-  if (q >= ty.q_max) buy = false;
-  else if (q <= -ty.q_max) buy = true;
+  if (UNLIKELY(q >= ty.q_max)) buy = false;
+  else if (UNLIKELY(q <= -ty.q_max)) buy = true;
   else buy = rng_randint(SID_AGENT, 0, 2) != 0;
   long long r_T = estimator_update(obs, ty, c_db.type_log1mk[A.type_idx], c_db.type_omp2[A.type_idx]);
   q += ty.q_max - 1;
@@ -1507,16 +1509,16 @@ __device__ __noinline__ void zvn_wakeup(int a, const abides_agent_type& ty) {
   AgentRec& A = ST.ag; Hot& h = HOT;
   ta_wakeup(a);
   ag_set_state(A, ST_INACTIVE);
-  if (!(A.flags & F_HAS_OPEN) || !(A.flags & F_HAS_CLOSE)) return;
+  if (UNLIKELY(!(A.flags & F_HAS_OPEN) || !(A.flags & F_HAS_CLOSE))) return;
   A.flags |= F_TRADING;
-  if ((A.flags & F_MKT_CLOSED) && (A.flags & F_HAS_DAILY_CLOSE)) return;
+  if (UNLIKELY((A.flags & F_MKT_CLOSED) && (A.flags & F_HAS_DAILY_CLOSE))) return;
   if (ty.klass == ABIDES_NOISE) {
     if (A.u.noise.wakeup_time > h.now) k_wakeup(a, A.u.noise.wakeup_time);
   } else {
     double dt = rng_exponential(SID_AGENT, fdiv(1.0, ty.lambda_a));
     k_wakeup(a, h.now + (long long)rint(dt));
   }
-  if ((A.flags & F_MKT_CLOSED) && !(A.flags & F_HAS_DAILY_CLOSE)) { ta_query_spread(a); ag_set_state(A, ST_AWAITING_SPREAD); return; }
+  if (UNLIKELY((A.flags & F_MKT_CLOSED) && !(A.flags & F_HAS_DAILY_CLOSE))) { ta_query_spread(a); ag_set_state(A, ST_AWAITING_SPREAD); return; }
   if (ty.klass != ABIDES_NOISE) ta_cancel_all(a);
   ta_query_spread(a);
   ag_set_state(A, ST_AWAITING_SPREAD);
@@ -1627,11 +1629,10 @@ __device__ __noinline__ void exchange_receive(int w0, int w1, int w2, int w3, in
                         code == ABIDES_MSG_QUERY_ORDER_STREAM || code == ABIDES_MSG_QUERY_TRANSACTED_VOLUME;
   const bool closed = h.now > cfg.mkt_close;
   const int cflag = closed ? 1 << 8 : 0;
-  if (closed && !is_query) { k_send(0, sender, 0, ABIDES_MSG_MKT_CLOSED, 0, 0, 0, 0, 0); return; }
+  if (UNLIKELY(closed && !is_query)) { k_send(0, sender, 0, ABIDES_MSG_MKT_CLOSED, 0, 0, 0, 0, 0); return; }
   int oid = w2;
   if (is_order) {
-    if (cfg.exch_log_orders && oid == 0) h.next_order_id++;
-    if (oid == 0) oid = (int)h.next_order_id++;
+    if (UNLIKELY(oid == 0)) { if (cfg.exch_log_orders) h.next_order_id++; oid = (int)h.next_order_id++; }
   }
   switch (code) {
     case ABIDES_MSG_WHEN_MKT_OPEN:
@@ -1918,9 +1919,9 @@ __global__ void __launch_bounds__(32) sim_kernel(long long until_time) {
     bool finished = false;
     for (;;) {
       PROF_T0();
-      if (h.status != 0) { finished = true; break; }
-      if (!(h.now <= stop_time)) { finished = true; break; }
-      if (h.n_near == 0) {
+      if (UNLIKELY(h.status != 0)) { finished = true; break; }
+      if (UNLIKELY(!(h.now <= stop_time))) { finished = true; break; }
+      if (UNLIKELY(h.n_near == 0)) {
         if (h.l_live[0] + h.l_live[1] == 0) { finished = true; break; }
         q_refill();
         PROF_ADD(P_REFILL);
@@ -1930,7 +1931,7 @@ __global__ void __launch_bounds__(32) sim_kernel(long long until_time) {
       const long long t = ST.nt[top_i];
       const unsigned long long k2 = ST.nk[top_i];
       const int slot = ST.nslot[top_i];
-      if (t > until_time) break;
+      if (UNLIKELY(t > until_time)) break;
       h.n_near = top_i;
       h.now = t;
       h.ttl++;
@@ -1960,7 +1961,7 @@ __global__ void __launch_bounds__(32) sim_kernel(long long until_time) {
       h.near_free |= 1u << slot;
       __syncwarp();
       h.delivered++;
-      if (tracing) trace_event(t, k2, p0.x, p0.y, p0.z, p0.w, p1.x, p1.y);
+      if (UNLIKELY(tracing)) trace_event(t, k2, p0.x, p0.y, p0.z, p0.w, p1.x, p1.y);
       if (rcpt == 0) {
         h.exch_busy = t;
         if (is_wakeup) h.exch_cur_time = t;
