@@ -41,7 +41,8 @@ class AgentType(C.Structure):
         ("backstop_quantity", C.c_int64), ("window_size", C.c_int64),
         ("anchor", C.c_int32), ("log_orders", C.c_int32),
         ("percent_aggr", C.c_double), ("depth_spread", C.c_int64),
-        ("reserved", C.c_int64 * 2),
+        ("exec_start_time", C.c_int64), ("exec_end_time", C.c_int64), ("exec_lookback", C.c_int64),
+        ("exec_quantity", C.c_double), ("exec_is_buy", C.c_int32), ("exec_trade", C.c_int32),
     ]
 
 

@@ -1,6 +1,7 @@
-"""POVExecutionAgent descriptor (reference: agent/execution/POVExecutionAgent.py:12-48).  With
-trade=False (every BASELINE population) it is a one-minute heartbeat; it must still exist so agent
-ids, latency rows and message counts match."""
+"""POVExecutionAgent descriptor (reference: agent/execution/POVExecutionAgent.py:12-72).  With trade=False (every
+BASELINE population) it is a one-minute heartbeat that must still exist so agent ids, latency rows and message
+counts match; with trade=True (rmsc03 `-e`) it buys / sells `pov` of the last minute's transacted volume with a
+MARKET order on every wake between start_time and end_time."""
 import pandas as pd
 
 from agent.TradingAgent import TradingAgent

@@ -87,7 +87,7 @@ enum : unsigned {
   F_HAS_OPEN = 1u, F_HAS_CLOSE = 2u, F_MKT_CLOSED = 4u, F_HAS_LAST_TRADE = 8u, F_HAS_DAILY_CLOSE = 16u,
   F_KNOWN_BOOK = 32u, F_TRADING = 64u, F_HAS_PREV_WAKE = 128u,
   F_MM_AWAIT_SPREAD = 512u, F_MM_AWAIT_TV = 1024u, F_HAS_LAST_MID = 2048u, F_HAS_AVG20 = 4096u,
-  F_HAS_AVG50 = 8192u, F_STATE_SHIFT = 16u, F_STATE_MASK = 3u << 16
+  F_HAS_AVG50 = 8192u, F_HAS_TV = 16384u, F_STATE_SHIFT = 16u, F_STATE_MASK = 3u << 16
 };
 enum { ST_AWAITING_WAKEUP = 0, ST_INACTIVE = 1, ST_AWAITING_SPREAD = 2, ST_ACTIVE = 3 };
 enum { BID = 0, ASK = 1 };              // book side index; a BUY order rests on BID and matches ASK
@@ -111,6 +111,7 @@ struct __align__(128) AgentRec {        // 128 bytes: one coalesced transaction
     struct { double csum; int n_mids; int ring; double avg20, avg50; } mom;
     struct { double last_spread, window_size; long long transacted_volume;
              int buy_size, sell_size, tick_size, last_mid; } mm;
+    struct { long long executed, transacted_volume; } pov;                         // POVExecutionAgent
   } u;
 };
 static_assert(sizeof(AgentRec) == 128, "AgentRec must be 128 bytes");
@@ -1343,6 +1344,10 @@ __device__ __forceinline__ void ta_receive(int a, const Msg& m, int klass, const
       if (pay_closed(m.w0)) A.flags |= F_MKT_CLOSED;
       if (klass == ABIDES_ADAPTIVE_MM)
         A.u.mm.transacted_volume = ((long long)(unsigned)m.w2) | ((long long)m.w3 << 32);
+      else if (klass == ABIDES_POV_EXEC) {
+        A.u.pov.transacted_volume = ((long long)(unsigned)m.w2) | ((long long)m.w3 << 32);
+        A.flags |= F_HAS_TV;
+      }
       break;
     default: break;
   }
@@ -1539,10 +1544,20 @@ __device__ __noinline__ void other_wakeup(int a, const abides_agent_type& ty) {
                    (int)(ty.wake_up_freq >> 32), 0, 0);
       }
       return;
-    case ABIDES_POV_EXEC:
-      ta_wakeup(a);
+    case ABIDES_POV_EXEC: {                                     // POVExecutionAgent.wakeup (:40-48)
+      const bool can_trade = ta_wakeup(a);
       k_wakeup(a, h.now + ty.wake_up_freq);
+      if (!can_trade) return;
+      if (ty.exec_trade && ty.exec_quantity - (double)A.u.pov.executed > 0 && ty.exec_start_time < h.now &&
+          h.now < ty.exec_end_time) {
+        ta_cancel_all(a);                                       // its market orders cannot be cancelled: no-op
+        agent_send(a, ABIDES_MSG_QUERY_SPREAD, -1, 0, 0, 0);    // getCurrentSpread(depth=sys.maxsize)
+        agent_send(a, ABIDES_MSG_QUERY_TRANSACTED_VOLUME, (int)(unsigned)(ty.exec_lookback & 0xffffffffll),
+                   (int)(ty.exec_lookback >> 32), 0, 0);
+        A.flags |= F_MM_AWAIT_TV;                               // state = 'AWAITING_TRANSACTED_VOLUME' (never reset)
+      }
       return;
+    }
     default: return;
   }
 }
@@ -1553,7 +1568,7 @@ __device__ __forceinline__ void agent_wakeup(int a) {
 }
 
 // receiveMessage() tails of Momentum / AdaptiveMarketMaker agents
-__device__ __noinline__ void other_receive(int a, int code, const abides_agent_type& ty) {
+__device__ __noinline__ void other_receive(int a, int code, int w4_of_last_msg, const abides_agent_type& ty) {
   AgentRec& A = ST.ag; Hot& h = HOT;
   switch (ty.klass) {
     case ABIDES_MOMENTUM:
@@ -1590,6 +1605,23 @@ __device__ __noinline__ void other_receive(int a, int code, const abides_agent_t
       }
       return;
     }
+    case ABIDES_POV_EXEC: {                                     // POVExecutionAgent.receiveMessage (:53-72)
+      if (code == ABIDES_MSG_ORDER_EXECUTED) A.u.pov.executed += w4_of_last_msg;
+      if (h.now > ty.exec_end_time) return;
+      if (ty.exec_quantity - (double)A.u.pov.executed > 0 && (A.flags & F_MM_AWAIT_TV) &&
+          code == ABIDES_MSG_QUERY_TRANSACTED_VOLUME && (A.flags & F_HAS_TV) && h.now > ty.exec_start_time) {
+        const long long qty = (long long)rint(ty.pov * (double)A.u.pov.transacted_volume);
+        ta_cancel_all(a);
+        // TradingAgent.placeMarketOrder (:333-365): the MarketOrder takes an id even when it is then ignored
+        const int id = (int)h.next_order_id++;
+        if (qty > 0) {
+          if (UNLIKELY(id == 0)) h.next_order_id++;
+          agent_send(a, order_w0(ABIDES_MSG_MARKET_ORDER, ty.exec_is_buy != 0), id, 0, (int)qty, -1);
+          if (UNLIKELY(ty.log_orders && id == 0)) h.next_order_id++;
+        }
+      }
+      return;
+    }
     default: return;
   }
 }
@@ -1611,7 +1643,7 @@ __device__ __noinline__ void agent_receive(int a, int w0, int w1, int w2, int w3
     }
     return;
   }
-  other_receive(a, code, ty);
+  other_receive(a, code, w4, ty);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -1688,7 +1720,7 @@ __device__ __noinline__ void trace_event(long long t, unsigned long long k2, int
         code == ABIDES_MSG_MODIFY_ORDER) {
       p1 = w2; p2 = w3; p3 = pay_is_buy(w0) ? w4 : -(long long)w4;
       if (code == ABIDES_MSG_CANCEL_ORDER) p3 = pay_is_buy(w0) ? 1 : -1;
-    } else if (code == ABIDES_MSG_QUERY_SPREAD) p1 = w2;
+    } else if (code == ABIDES_MSG_QUERY_SPREAD) p1 = w2 < 0 ? LLONG_MAX : w2;   // depth (-1: sys.maxsize)
   } else {
     switch (code) {
       case ABIDES_MSG_ORDER_ACCEPTED: case ABIDES_MSG_ORDER_EXECUTED: case ABIDES_MSG_ORDER_CANCELLED:

@@ -63,7 +63,8 @@ def _type_row(agent, klass):
                R_min=0, R_max=0, wake_up_freq=0, pov=0.0, level_spacing=0.0, spread_alpha=0.0,
                skew_beta=0.0, min_order_size=0, num_ticks=0, cancel_limit_delay=0,
                backstop_quantity=-1, window_size=-1, anchor=0,
-               log_orders=1 if g("log_orders", False) else 0, percent_aggr=0.0, depth_spread=0)
+               log_orders=1 if g("log_orders", False) else 0, percent_aggr=0.0, depth_spread=0,
+               exec_start_time=0, exec_end_time=0, exec_lookback=0, exec_quantity=0.0, exec_is_buy=0, exec_trade=0)
     if klass in (_abi.ZI, _abi.VALUE):
         row.update(sigma_n=float(agent.sigma_n), r_bar=float(agent.r_bar), kappa=float(agent.kappa),
                    sigma_s=float(agent.sigma_s), lambda_a=float(agent.lambda_a))
@@ -77,9 +78,12 @@ def _type_row(agent, klass):
             raise NotImplementedError("MomentumAgent(subscribe=True) is not supported")
         row.update(wake_up_freq=_ns(agent.wake_up_freq))
     if klass == _abi.POV_EXEC:
-        if g("trade", False):
-            raise NotImplementedError("POVExecutionAgent(trade=True) is not supported")
         row.update(wake_up_freq=_ns(agent.freq))
+        if g("trade", False):                      # trade=False is a pure heartbeat: nothing else is read
+            row.update(pov=float(agent.pov), exec_start_time=_ns(agent.start_time),
+                       exec_end_time=_ns(agent.end_time), exec_lookback=_ns(agent.look_back_period),
+                       exec_quantity=float(agent.quantity), exec_is_buy=1 if agent.direction == "BUY" else 0,
+                       exec_trade=1)
     if klass == _abi.ADAPTIVE_MM:
         if g("subscribe", False):
             raise NotImplementedError("AdaptiveMarketMakerAgent(subscribe=True) is not supported")

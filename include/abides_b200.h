@@ -45,7 +45,7 @@ enum abides_agent_class {
   ABIDES_NOISE = 3,         /* agent/NoiseAgent.py */
   ABIDES_MOMENTUM = 4,      /* agent/examples/MomentumAgent.py */
   ABIDES_ADAPTIVE_MM = 5,   /* agent/market_makers/AdaptiveMarketMakerAgent.py */
-  ABIDES_POV_EXEC = 6       /* agent/execution/POVExecutionAgent.py (trade=False heartbeat) */
+  ABIDES_POV_EXEC = 6       /* agent/execution/POVExecutionAgent.py */
 };
 
 enum abides_latency_kind {
@@ -75,7 +75,12 @@ typedef struct abides_agent_type {
   int32_t log_orders;         /* TradingAgent.log_orders: only affects order-id consumption of order 0 */
   double  percent_aggr;       /* Value: 0.1 */
   int64_t depth_spread;       /* Value: 2 */
-  int64_t reserved[2];
+  /* POVExecutionAgent (agent/execution/POVExecutionAgent.py:14-33); also uses pov and wake_up_freq (= freq) */
+  int64_t exec_start_time, exec_end_time;   /* trades while start < now < end */
+  int64_t exec_lookback;      /* lookback_period of its QUERY_TRANSACTED_VOLUME, ns */
+  double  exec_quantity;      /* total quantity to execute */
+  int32_t exec_is_buy;        /* direction == "BUY" */
+  int32_t exec_trade;         /* trade flag: 0 = heartbeat only */
 } abides_agent_type;
 
 /* One simulation instance (one reference process). */

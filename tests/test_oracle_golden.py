@@ -20,6 +20,9 @@ CASES = {
     "zi100_s123456789": ("sparse_zi_100", ["-s", "123456789"]),
     "zi1000_s123456789": ("sparse_zi_1000", ["-s", "123456789"]),
     "rmsc03_s1234_1000": ("rmsc03", ["-t", "ABM", "-d", "20200603", "-s", "1234", "--end-time", "10:00:00"]),
+    # rmsc03 with the execution agent trading (`-e`): POVExecutionAgent(trade=True) buys 10 % of the
+    # transacted volume with MARKET orders every minute from 10:00 to 10:30
+    "rmsc03e_s1234_1100": ("rmsc03", ["-t", "ABM", "-d", "20200603", "-s", "1234", "-e", "--end-time", "11:00:00"]),
     # BASELINE configs[2] "rmsc01: value + noise agents + market maker" from the supported classes: the rmsc03
     # population at rmsc01 scale (103 agents), one full market day; reference side: tests/golden/refcfg/rmsc_small.py
     "rmsc01s_s77": ("rmsc03", ["-t", "ABM", "-d", "20200603", "-s", "77", "--end-time", "16:00:00",
