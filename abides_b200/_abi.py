@@ -11,7 +11,7 @@ EXTRA_STREAMS = 4
 STREAM_ORACLE, STREAM_KERNEL, STREAM_LATENCY, STREAM_GLOBAL = 0, 1, 2, 3
 
 # enum abides_agent_class
-EXCHANGE, ZI, VALUE, NOISE, MOMENTUM, ADAPTIVE_MM, POV_EXEC = range(7)
+EXCHANGE, ZI, VALUE, NOISE, MOMENTUM, ADAPTIVE_MM, POV_EXEC, MARKET_MAKER, HBL = range(9)
 # enum abides_latency_kind
 LAT_DETERMINISTIC, LAT_CUBIC, LAT_LEGACY_NOISE = range(3)
 # enum abides_rng_mode
@@ -43,6 +43,7 @@ class AgentType(C.Structure):
         ("percent_aggr", C.c_double), ("depth_spread", C.c_int64),
         ("exec_start_time", C.c_int64), ("exec_end_time", C.c_int64), ("exec_lookback", C.c_int64),
         ("exec_quantity", C.c_double), ("exec_is_buy", C.c_int32), ("exec_trade", C.c_int32),
+        ("mm_min_size", C.c_int64), ("mm_max_size", C.c_int64), ("mm_num_levels", C.c_int32), ("hbl_L", C.c_int32),
     ]
 
 

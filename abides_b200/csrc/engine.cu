@@ -1238,7 +1238,8 @@ __device__ __noinline__ void ta_place_limit(int a, long long qty, bool is_buy, l
   if (qty <= 0) return;
   OpenOrd oo; oo.key = id; oo.id = id; oo.price = (int)price; oo.sqty = is_buy ? (int)qty : -(int)qty;
   if (UNLIKELY(id == 0)) oo.id = (int)h.next_order_id++;            // deepcopy of order id 0 takes a fresh id (Order.py:29)
-  int init_cap = ty.klass == ABIDES_ADAPTIVE_MM ? (int)(2 * ty.num_ticks + 8) : (ty.klass == ABIDES_MOMENTUM ? 16 : 4);
+  int init_cap = ty.klass == ABIDES_ADAPTIVE_MM ? (int)(2 * ty.num_ticks + 8)
+               : ty.klass == ABIDES_MARKET_MAKER ? 8 * ty.mm_num_levels + 8 : (ty.klass == ABIDES_MOMENTUM ? 16 : 4);
   ord_reserve(init_cap);
   if (UNLIKELY(h.status != 0)) return;
   __syncwarp();
@@ -1544,6 +1545,13 @@ __device__ __noinline__ void other_wakeup(int a, const abides_agent_type& ty) {
                    (int)(ty.wake_up_freq >> 32), 0, 0);
       }
       return;
+    case ABIDES_MARKET_MAKER:                                   // MarketMakerAgent.wakeup (:56-66), polling mode
+      if (ta_wakeup(a)) {
+        ta_cancel_all(a);
+        agent_send(a, ABIDES_MSG_QUERY_SPREAD, ty.mm_num_levels, 0, 0, 0);   // depth = subscribe_num_levels
+        ag_set_state(A, ST_AWAITING_SPREAD);
+      }
+      return;
     case ABIDES_POV_EXEC: {                                     // POVExecutionAgent.wakeup (:40-48)
       const bool can_trade = ta_wakeup(a);
       k_wakeup(a, h.now + ty.wake_up_freq);
@@ -1605,6 +1613,26 @@ __device__ __noinline__ void other_receive(int a, int code, int w4_of_last_msg, 
       }
       return;
     }
+    case ABIDES_MARKET_MAKER:                                   // MarketMakerAgent.receiveMessage (:68-91)
+      if (ag_state(A) == ST_AWAITING_SPREAD && code == ABIDES_MSG_QUERY_SPREAD) {
+        ta_cancel_all(a);
+        long long mid = A.last_trade, spread = 10;              // self.last_spread is never updated
+        if (A.bid > 0 && A.ask > 0) {
+          mid = (long long)((double)((long long)A.ask + A.bid) / 2);
+          long long d = (long long)A.ask - A.bid; if (d < 0) d = -d;
+          spread = (long long)((double)d / 2);
+        }
+#pragma unroll 1
+        for (long long i = 0; i < 2 * ty.mm_num_levels; i++) {
+          // round(randint(min, max) / 2): Python rounds x.5 to even
+          const long long size = (long long)rint((double)rng_randint(SID_AGENT, ty.mm_min_size, ty.mm_max_size) / 2);
+          ta_place_limit(a, size, true, mid - spread - i);
+          ta_place_limit(a, size, false, mid + spread + i);
+        }
+        k_wakeup(a, h.now + ty.wake_up_freq);
+        ag_set_state(A, ST_AWAITING_WAKEUP);
+      }
+      return;
     case ABIDES_POV_EXEC: {                                     // POVExecutionAgent.receiveMessage (:53-72)
       if (code == ABIDES_MSG_ORDER_EXECUTED) A.u.pov.executed += w4_of_last_msg;
       if (h.now > ty.exec_end_time) return;
@@ -2249,7 +2277,8 @@ int abides_load(abides_handle* h, const abides_batch* b) {
       if (t < 0 || t >= b->n_types) return fail(ABIDES_EINVAL, "abides_load: agent_type out of range");
       int k = b->types[t].klass;
       if ((a == 0) != (k == ABIDES_EXCHANGE)) return fail(ABIDES_EINVAL, "abides_load: agent 0 (and only agent 0) must be the exchange");
-      if (k < 0 || k > ABIDES_POV_EXEC) return fail(ABIDES_EINVAL, "abides_load: unknown agent class");
+      if (k < 0 || k > ABIDES_HBL) return fail(ABIDES_EINVAL, "abides_load: unknown agent class");
+      if (k == ABIDES_HBL) return fail(ABIDES_EINVAL, "abides_load: HeuristicBeliefLearningAgent is not implemented on the device yet");
       if (k == ABIDES_MOMENTUM) mom_index[off + a] = n_mom++;
       if (k == ABIDES_ZI && (b->agent_theta[off + a] < 0 || !b->theta)) return fail(ABIDES_EINVAL, "abides_load: ZI agent without theta");
     }

@@ -19,6 +19,8 @@ _CLASS_BY_NAME = {
     "MomentumAgent": _abi.MOMENTUM,
     "AdaptiveMarketMakerAgent": _abi.ADAPTIVE_MM,
     "POVExecutionAgent": _abi.POV_EXEC,
+    "MarketMakerAgent": _abi.MARKET_MAKER,
+    "HeuristicBeliefLearningAgent": _abi.HBL,
 }
 
 
@@ -40,7 +42,7 @@ def agent_class(agent):
     for k in type(agent).__mro__:
         if k.__name__ in _CLASS_BY_NAME:
             if k is not type(agent) and k.__name__ != "ExchangeAgent":
-                # e.g. HeuristicBeliefLearningAgent(ZeroIntelligenceAgent): different strategy
+                # a subclass of a supported agent that is not itself supported: different strategy
                 raise NotImplementedError(
                     "agent class %s (subclass of %s) is not supported by the B200 engine"
                     % (type(agent).__name__, k.__name__))
@@ -64,13 +66,21 @@ def _type_row(agent, klass):
                skew_beta=0.0, min_order_size=0, num_ticks=0, cancel_limit_delay=0,
                backstop_quantity=-1, window_size=-1, anchor=0,
                log_orders=1 if g("log_orders", False) else 0, percent_aggr=0.0, depth_spread=0,
-               exec_start_time=0, exec_end_time=0, exec_lookback=0, exec_quantity=0.0, exec_is_buy=0, exec_trade=0)
-    if klass in (_abi.ZI, _abi.VALUE):
+               exec_start_time=0, exec_end_time=0, exec_lookback=0, exec_quantity=0.0, exec_is_buy=0, exec_trade=0,
+               mm_min_size=0, mm_max_size=0, mm_num_levels=0, hbl_L=0)
+    if klass in (_abi.ZI, _abi.VALUE, _abi.HBL):
         row.update(sigma_n=float(agent.sigma_n), r_bar=float(agent.r_bar), kappa=float(agent.kappa),
                    sigma_s=float(agent.sigma_s), lambda_a=float(agent.lambda_a))
-    if klass == _abi.ZI:
+    if klass in (_abi.ZI, _abi.HBL):
         row.update(q_max=int(agent.q_max), R_min=int(agent.R_min), R_max=int(agent.R_max),
                    eta=float(agent.eta))
+    if klass == _abi.HBL:
+        row.update(hbl_L=int(agent.L))
+    if klass == _abi.MARKET_MAKER:
+        if g("subscribe", False):
+            raise NotImplementedError("MarketMakerAgent(subscribe=True) is not supported")
+        row.update(wake_up_freq=_ns(agent.wake_up_freq), mm_min_size=int(agent.min_size),
+                   mm_max_size=int(agent.max_size), mm_num_levels=int(agent.subscribe_num_levels))
     if klass == _abi.VALUE:
         row.update(percent_aggr=float(agent.percent_aggr), depth_spread=int(agent.depth_spread))
     if klass == _abi.MOMENTUM:
@@ -168,7 +178,7 @@ def lower_instance(agents, startTime, stopTime, defaultComputationDelay=1, defau
         if k == _abi.NOISE:
             wt = a.wakeup_time
             wake[i] = _ns(wt[0] if isinstance(wt, tuple) else wt)
-        if k == _abi.ZI:
+        if k in (_abi.ZI, _abi.HBL):
             th = [int(x) for x in a.theta]
             if len(th) != 2 * int(a.q_max):
                 raise ValueError("ZI theta must have 2*q_max entries")

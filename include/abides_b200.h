@@ -45,7 +45,9 @@ enum abides_agent_class {
   ABIDES_NOISE = 3,         /* agent/NoiseAgent.py */
   ABIDES_MOMENTUM = 4,      /* agent/examples/MomentumAgent.py */
   ABIDES_ADAPTIVE_MM = 5,   /* agent/market_makers/AdaptiveMarketMakerAgent.py */
-  ABIDES_POV_EXEC = 6       /* agent/execution/POVExecutionAgent.py */
+  ABIDES_POV_EXEC = 6,      /* agent/execution/POVExecutionAgent.py */
+  ABIDES_MARKET_MAKER = 7,  /* agent/market_makers/MarketMakerAgent.py (polling mode, subscribe=False) */
+  ABIDES_HBL = 8            /* agent/HeuristicBeliefLearningAgent.py (a ZeroIntelligenceAgent subclass) */
 };
 
 enum abides_latency_kind {
@@ -81,6 +83,10 @@ typedef struct abides_agent_type {
   double  exec_quantity;      /* total quantity to execute */
   int32_t exec_is_buy;        /* direction == "BUY" */
   int32_t exec_trade;         /* trade flag: 0 = heartbeat only */
+  /* MarketMakerAgent (agent/market_makers/MarketMakerAgent.py:27-50); also uses wake_up_freq */
+  int64_t mm_min_size, mm_max_size;
+  int32_t mm_num_levels;      /* subscribe_num_levels: depth of its spread query, 2x = price levels quoted per side */
+  int32_t hbl_L;              /* HeuristicBeliefLearningAgent: order-stream buckets it looks at */
 } abides_agent_type;
 
 /* One simulation instance (one reference process). */

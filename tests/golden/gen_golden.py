@@ -195,9 +195,11 @@ def spec_digest(spec):
     import numpy as np
     h = hashlib.sha256()
     h.update(json.dumps(spec.cfg, sort_keys=True).encode())
-    # exec_* columns (POVExecutionAgent with trade=True) were added after the first fixtures were frozen: they only
-    # enter the digest of populations that use them, so the older fixtures keep their spec_sha256
-    types = [{k: v for k, v in row.items() if not (k.startswith("exec_") and not row.get("exec_trade"))}
+    # columns added after the first fixtures were frozen (exec_*: POVExecutionAgent trade=True; mm_*, hbl_L: MarketMaker
+    # / HBL agents) only enter the digest of the rows that use them, so the older fixtures keep their spec_sha256
+    late = ("exec_", "mm_", "hbl_")
+    types = [{k: v for k, v in row.items()
+              if not (k.startswith(late) and not (row.get("exec_trade") if k.startswith("exec_") else v))}
              for row in spec.types]
     h.update(json.dumps(types, sort_keys=True).encode())
     for a in (spec.agent_type, spec.lat_to, spec.lat_from, spec.size, spec.wakeup_time, spec.agent_theta,

@@ -23,6 +23,10 @@ CASES = {
     # rmsc03 with the execution agent trading (`-e`): POVExecutionAgent(trade=True) buys 10 % of the
     # transacted volume with MARKET orders every minute from 10:00 to 10:30
     "rmsc03e_s1234_1100": ("rmsc03", ["-t", "ABM", "-d", "20200603", "-s", "1234", "-e", "--end-time", "11:00:00"]),
+    # SURVEY 8(f)1 (first half): the reference's rmsc01 population with its MarketMakerAgent (20 quotes a second) and
+    # 75 ZI + 24 momentum agents, 09:30-11:00; HBL agents are not on the device yet.  Reference side:
+    # tests/golden/refcfg/rmsc01_flags.py
+    "rmsc01mm_s33": ("rmsc01", ["-s", "33", "--num-zi", "75", "--num-hbl", "0", "--end-time", "11:00:00"]),
     # BASELINE configs[2] "rmsc01: value + noise agents + market maker" from the supported classes: the rmsc03
     # population at rmsc01 scale (103 agents), one full market day; reference side: tests/golden/refcfg/rmsc_small.py
     "rmsc01s_s77": ("rmsc03", ["-t", "ABM", "-d", "20200603", "-s", "77", "--end-time", "16:00:00",
