@@ -75,21 +75,24 @@ constexpr int UNR_CAP = 1 << 16;        // ring of de-duplicated rows the volume
 constexpr int TRACE_FUNDAMENTAL = 64;   // trace code of an oracle step (time = ts, p0 = value)
 constexpr int SID_AGENT = 4;            // RNG stream id of the agent being dispatched (0..3: ABIDES_STREAM_*)
 constexpr int N_PROF = 16;
+constexpr int OLOG_CAP = 1 << 18;       // ring of order-log rows (HBL populations only; a bucket = all orders between two trades)
+constexpr int HBL_RANGE_CAP = 16384;    // widest price range (ticks) an HBL belief table may span
 
 struct __align__(16) EvKey { long long t; unsigned long long k2; };   // k2 = rcpt<<33 | wakeup<<32 | uniq
 struct __align__(16) EvPay { int w[8]; };
 struct __align__(16) BookOrd { int price, qty, id, agent; };
 struct __align__(16) OpenOrd { int key, id, price, sqty; };            // sqty > 0 buy, < 0 sell
 struct __align__(16) TxnRow { long long t; int q; int seq; };          // OrderBook.history transaction + bucket of its record
+struct __align__(16) OLogRow { int bucket, price, flags, pad; };        // OrderBook.history[bucket][order]: side (bit 0), has transactions (bit 1)
 struct __align__(16) RngState { int pos; unsigned flags; double gauss; };   // flags bit 0: cached gaussian valid
 
 enum : unsigned {
   F_HAS_OPEN = 1u, F_HAS_CLOSE = 2u, F_MKT_CLOSED = 4u, F_HAS_LAST_TRADE = 8u, F_HAS_DAILY_CLOSE = 16u,
   F_KNOWN_BOOK = 32u, F_TRADING = 64u, F_HAS_PREV_WAKE = 128u,
   F_MM_AWAIT_SPREAD = 512u, F_MM_AWAIT_TV = 1024u, F_HAS_LAST_MID = 2048u, F_HAS_AVG20 = 4096u,
-  F_HAS_AVG50 = 8192u, F_HAS_TV = 16384u, F_STATE_SHIFT = 16u, F_STATE_MASK = 3u << 16
+  F_HAS_AVG50 = 8192u, F_HAS_TV = 16384u, F_STATE_SHIFT = 16u, F_STATE_MASK = 7u << 16
 };
-enum { ST_AWAITING_WAKEUP = 0, ST_INACTIVE = 1, ST_AWAITING_SPREAD = 2, ST_ACTIVE = 3 };
+enum { ST_AWAITING_WAKEUP = 0, ST_INACTIVE = 1, ST_AWAITING_SPREAD = 2, ST_ACTIVE = 3, ST_AWAITING_STREAM = 4 };
 enum { BID = 0, ASK = 1 };              // book side index; a BUY order rests on BID and matches ASK
 
 struct __align__(128) AgentRec {        // 128 bytes: one coalesced transaction
@@ -106,7 +109,8 @@ struct __align__(128) AgentRec {        // 128 bytes: one coalesced transaction
   int size;                             // Noise / Value / Momentum order size
   int type_idx;                         // absolute row in the types table
   union {
-    struct { double r_t, sigma_t; long long prev_wake; int hint_id, hint; } est;   // ZI / Value (+ pool slot of the last accepted order)
+    struct { double r_t, sigma_t; long long prev_wake; int hint_id, hint;      // ZI / Value / HBL (+ pool slot of the last
+             int stream_n, stream_B; } est;                                    //  accepted order; HBL: order-stream window)
     struct { long long wakeup_time; } noise;
     struct { double csum; int n_mids; int ring; double avg20, avg50; } mom;
     struct { double last_spread, window_size; long long transacted_volume;
@@ -132,6 +136,7 @@ struct Hot {
   unsigned near_free;                   // free payload slots of the near tier
   int n_pfree[2];                       // book pools: free (tombstoned) slots available for reuse
   int last_hint;                        // pool slot + 1 of the order book_enter just placed (0: shared part)
+  long long olog_len;                   // order-log rows written (HBL populations)
   unsigned book_arr;                    // arrival counter of resting orders (time priority)
   long long pb_t[2]; unsigned long long pb_k[2];   // per side: lower bound of every pool key
   int last_trade, has_last_trade;
@@ -150,6 +155,7 @@ struct __align__(128) InstShared {      // persisted per instance between launch
   BookOrd top[2][BOOK_TOP];             // best first
   int tseq[2][BOOK_TOP];                // history bucket in which each resting order was entered
   int tarr[2][BOOK_TOP];                // arrival number (time priority across top and pool)
+  int tlog[2][BOOK_TOP];                // order-log row of each resting order (-1: no log)
   AgentRec ag;
   Hot hot;
 };
@@ -177,6 +183,8 @@ struct DevBatch {
   EvKey* b_keys; EvPay* b_pay;          // [n_instances][b_cap]
   EvKey* p_keys; EvPay* p_pay;          // [n_instances][2][deep_cap] book pools
   int* p_free;                          // [n_instances][2][deep_cap] free-slot stacks of the pools
+  OLogRow* olog;                        // [n_instances][OLOG_CAP] order log, or NULL (no HBL agent in the batch)
+  int* hbl_cnt;                         // [n_instances][4][HBL_RANGE_CAP] belief-table scratch, or NULL
   OpenOrd* arena;
   TxnRow* txn_log;                      // [n_instances][TXN_CAP]
   TxnRow* unrolled;                     // [n_instances][UNR_CAP]
@@ -195,6 +203,7 @@ struct Run {                            // per-launch context, shared memory, no
   EvKey* lk[N_LISTS]; EvPay* lp[N_LISTS]; int lcap[N_LISTS];
   OpenOrd* arena; TxnRow* txn_log; TxnRow* unrolled;
   int* pfree[2];
+  OLogRow* olog; int* hbl_cnt;
   abides_trace_rec* trace;
   unsigned* mt0;                        // MT state of this instance's stream 0 (agent 0)
   const double* lat_to; const double* lat_from;   // this instance's rows
@@ -767,29 +776,29 @@ __device__ __noinline__ void top_remove(int s, int n, int idx) {                
   __syncwarp();
 #pragma unroll 1
   for (int base = idx; base < n - 1; base += 32) {
-    int j = base + LANE; BookOrd t; int tq = 0, ta = 0;
+    int j = base + LANE; BookOrd t; int tq = 0, ta = 0, tl = 0;
     bool act = j < n - 1;
-    if (act) { t = ST.top[s][j + 1]; tq = ST.tseq[s][j + 1]; ta = ST.tarr[s][j + 1]; }
+    if (act) { t = ST.top[s][j + 1]; tq = ST.tseq[s][j + 1]; ta = ST.tarr[s][j + 1]; tl = ST.tlog[s][j + 1]; }
     __syncwarp();
-    if (act) { ST.top[s][j] = t; ST.tseq[s][j] = tq; ST.tarr[s][j] = ta; }
+    if (act) { ST.top[s][j] = t; ST.tseq[s][j] = tq; ST.tarr[s][j] = ta; ST.tlog[s][j] = tl; }
     __syncwarp();
   }
 }
-__device__ __noinline__ void top_insert(int s, int n, int idx, int price, int qty, int id, int agent, int oseq, int arr) {
+__device__ __noinline__ void top_insert(int s, int n, int idx, int price, int qty, int id, int agent, int oseq, int arr, int olog) {
   __syncwarp();
   int cnt = n - idx;
 #pragma unroll 1
   for (int done = 0; done < cnt; done += 32) {
-    int j = n - 1 - done - LANE; BookOrd t; int tq = 0, ta = 0;
+    int j = n - 1 - done - LANE; BookOrd t; int tq = 0, ta = 0, tl = 0;
     bool act = j >= idx;
-    if (act) { t = ST.top[s][j]; tq = ST.tseq[s][j]; ta = ST.tarr[s][j]; }
+    if (act) { t = ST.top[s][j]; tq = ST.tseq[s][j]; ta = ST.tarr[s][j]; tl = ST.tlog[s][j]; }
     __syncwarp();
-    if (act) { ST.top[s][j + 1] = t; ST.tseq[s][j + 1] = tq; ST.tarr[s][j + 1] = ta; }
+    if (act) { ST.top[s][j + 1] = t; ST.tseq[s][j + 1] = tq; ST.tarr[s][j + 1] = ta; ST.tlog[s][j + 1] = tl; }
     __syncwarp();
   }
   if (LANE == 0) {
     BookOrd o; o.price = price; o.qty = qty; o.id = id; o.agent = agent;
-    ST.top[s][idx] = o; ST.tseq[s][idx] = oseq; ST.tarr[s][idx] = arr;
+    ST.top[s][idx] = o; ST.tseq[s][idx] = oseq; ST.tarr[s][idx] = arr; ST.tlog[s][idx] = olog;
   }
   __syncwarp();
 }
@@ -800,7 +809,7 @@ __device__ __forceinline__ int top_count_better_eq(int s, int n, int price) {
   for (int j = LANE; j < n; j += 32) cnt += px_better_eq(s, ST.top[s][j].price, price) ? 1 : 0;
   return warp_sum_i(cnt);
 }
-__device__ __noinline__ void pool_append(int s, int price, int qty, int id, int agent, int hseq, int arr) {
+__device__ __noinline__ void pool_append(int s, int price, int qty, int id, int agent, int hseq, int arr, int olog) {
   const int L = L_POOL + s;
   const long long kt = pool_rank(s, price); const unsigned long long kk = pool_k2((unsigned)arr, id);
   if (HOT.l_live[L] == 0 || key_less(kt, kk, HOT.pb_t[s], HOT.pb_k[s])) { HOT.pb_t[s] = kt; HOT.pb_k[s] = kk; }
@@ -815,7 +824,7 @@ __device__ __noinline__ void pool_append(int s, int price, int qty, int id, int 
   }
   if (LANE == 0) { EvKey k; k.t = kt; k.k2 = kk; RUN.lk[L][i] = k; }
   else if (LANE == 1) *reinterpret_cast<int4*>(&RUN.lp[L][i].w[0]) = make_int4(price, qty, id, agent);
-  else if (LANE == 2) *reinterpret_cast<int4*>(&RUN.lp[L][i].w[4]) = make_int4(hseq, arr, 0, 0);
+  else if (LANE == 2) *reinterpret_cast<int4*>(&RUN.lp[L][i].w[4]) = make_int4(hseq, arr, olog, 0);
   __syncwarp();
   HOT.l_live[L] += 1;
   HOT.last_hint = i + 1;
@@ -850,7 +859,7 @@ __device__ __noinline__ void side_refill(int s) {
         int pos = nn + __popc(m & ((1u << LANE) - 1u));
         EvPay p = pay[i];
         BookOrd o; o.price = p.w[0]; o.qty = p.w[1]; o.id = p.w[2]; o.agent = p.w[3];
-        ST.top[s][pos] = o; ST.tseq[s][pos] = p.w[4]; ST.tarr[s][pos] = p.w[5];
+        ST.top[s][pos] = o; ST.tseq[s][pos] = p.w[4]; ST.tarr[s][pos] = p.w[5]; ST.tlog[s][pos] = p.w[6];
         keys[i].t = LLONG_MAX;
         fr[nf + pos] = i;
       }
@@ -860,8 +869,8 @@ __device__ __noinline__ void side_refill(int s) {
   HOT.n_pfree[s] = nf + nn;
   __syncwarp();
   // rank sort (<= TOP_FILL = 32 entries, lane i owns entry i): better price first, then arrival
-  BookOrd e; int eq = 0, ea = 0, rank = 0;
-  if (LANE < nn) { e = ST.top[s][LANE]; eq = ST.tseq[s][LANE]; ea = ST.tarr[s][LANE]; }
+  BookOrd e; int eq = 0, ea = 0, el = 0, rank = 0;
+  if (LANE < nn) { e = ST.top[s][LANE]; eq = ST.tseq[s][LANE]; ea = ST.tarr[s][LANE]; el = ST.tlog[s][LANE]; }
   else { e.price = 0; e.qty = 0; e.id = 0; e.agent = 0; }
   const long long er = pool_rank(s, e.price);
 #pragma unroll 1
@@ -870,7 +879,7 @@ __device__ __noinline__ void side_refill(int s) {
     rank += (orr < er || (orr == er && oa < (unsigned)ea)) ? 1 : 0;
   }
   __syncwarp();
-  if (LANE < nn) { ST.top[s][rank] = e; ST.tseq[s][rank] = eq; ST.tarr[s][rank] = ea; }
+  if (LANE < nn) { ST.top[s][rank] = e; ST.tseq[s][rank] = eq; ST.tarr[s][rank] = ea; ST.tlog[s][rank] = el; }
   HOT.n_top[s] = nn;
   HOT.l_live[L] -= cnt;
   HOT.pb_t[s] = pt; HOT.pb_k[s] = pk;
@@ -906,7 +915,7 @@ __device__ __noinline__ int2 side_inside(int s) {
   return make_int2(p, v);
 }
 // OrderBook.enterOrder (:272-298): position = number of resting orders with better-or-equal price
-__device__ __noinline__ void book_enter(int s, int price, int qty, int id, int agent) {
+__device__ __noinline__ void book_enter(int s, int price, int qty, int id, int agent, int olog) {
   int ns = HOT.n_top[s];
   const int oseq = HOT.hist_B;                           // history[0][order_id] = {...} (:60-64)
   const int arr = (int)HOT.book_arr;
@@ -919,15 +928,15 @@ __device__ __noinline__ void book_enter(int s, int price, int qty, int id, int a
   if (to_top) {
     if (UNLIKELY(ns == BOOK_TOP)) {                      // spill the worst shared entry to the pool
       BookOrd w = ST.top[s][ns - 1];
-      pool_append(s, w.price, w.qty, w.id, w.agent, ST.tseq[s][ns - 1], ST.tarr[s][ns - 1]);
+      pool_append(s, w.price, w.qty, w.id, w.agent, ST.tseq[s][ns - 1], ST.tarr[s][ns - 1], ST.tlog[s][ns - 1]);
       if (HOT.status) return;
       ns--;
     }
-    top_insert(s, ns, cs, price, qty, id, agent, oseq, arr);
+    top_insert(s, ns, cs, price, qty, id, agent, oseq, arr, olog);
     HOT.n_top[s] = ns + 1;
     HOT.last_hint = 0;
   } else {
-    pool_append(s, price, qty, id, agent, oseq, arr);
+    pool_append(s, price, qty, id, agent, oseq, arr, olog);
   }
   int tot = HOT.n_top[0] + HOT.n_top[1] + HOT.l_live[L_POOL] + HOT.l_live[L_POOL + 1];
   if (tot > HOT.book_peak_orders) HOT.book_peak_orders = tot;
@@ -1053,6 +1062,27 @@ __device__ __forceinline__ void book_send(int rcpt, int code, bool is_buy, int i
               id, price, qty, fill);        // ORDER_ACCEPTED/CANCELLED/EXECUTED get +pipeline_delay (ExchangeAgent.py:404-407)
 }
 
+// ---- order log: OrderBook.history as the HBL agents see it (QUERY_ORDER_STREAM, ExchangeAgent.py:210-225) --------
+// One row per limit order the book accepted for processing (history[0][order_id] = {...}, :60-64), tagged with its
+// bucket; bit 1 is set when a transaction is appended to that order's record (:245-253).  Kept only when the batch
+// holds HBL agents (RUN.olog != NULL).
+__device__ __forceinline__ int olog_append(int bucket, int price, bool is_buy) {
+  if (RUN.olog == nullptr) return -1;
+  const long long i = HOT.olog_len;
+  __syncwarp();
+  if (LANE == 0) { OLogRow r; r.bucket = bucket; r.price = price; r.flags = is_buy ? 1 : 0; r.pad = 0; RUN.olog[i & (OLOG_CAP - 1)] = r; }
+  __syncwarp();
+  HOT.olog_len = i + 1;
+  return (int)(i & 0x7fffffff);
+}
+__device__ __forceinline__ void olog_mark(int row) {
+  if (RUN.olog == nullptr || row < 0) return;
+  if ((HOT.olog_len & 0x7fffffff) - row > OLOG_CAP) return;          // the row has left the ring (older than any window)
+  __syncwarp();
+  if (LANE == 0) RUN.olog[row & (OLOG_CAP - 1)].flags |= 2;
+  __syncwarp();
+}
+
 // OrderBook.handleLimitOrder (:46-158)
 template <bool RP>
 __device__ __noinline__ void book_handle_limit(int agent, int id, int price, int qty, bool is_buy) {
@@ -1060,17 +1090,20 @@ __device__ __noinline__ void book_handle_limit(int agent, int id, int price, int
   if (qty <= 0) return;
   long long ex_qty = 0, ex_pq = 0; int executed = 0;
   const int os = is_buy ? ASK : BID;
+  const int my_log = RP ? -1 : olog_append(h.hist_B, price, is_buy);
   for (;;) {
     __syncwarp();
     bool match = false; BookOrd top;
     if (h.n_top[os] > 0) { top = ST.top[os][0]; match = is_buy ? price >= top.price : price <= top.price; }
     if (match) {                                               // executeOrder (:190-256)
       int fill, tseq = ST.tseq[os][0];
+      const int rest_log = ST.tlog[os][0];
       if (qty >= top.qty) { fill = top.qty; side_pop_front(os); }
       else { fill = qty; __syncwarp(); if (LANE == 0) ST.top[os][0].qty = top.qty - qty; __syncwarp(); }
       // history (:245-253): the aggressor logs its REMAINING quantity, the resting order the fill
       txn_log_row(h.now, qty, h.hist_B);
-      if (h.hist_B - tseq <= RUN.cfg.stream_history) txn_log_row(h.now, fill, tseq);
+      if (h.hist_B - tseq <= RUN.cfg.stream_history) { txn_log_row(h.now, fill, tseq); if (!RP) olog_mark(rest_log); }
+      if (!RP) olog_mark(my_log);
       qty -= fill;
       book_send<RP>(agent, ABIDES_MSG_ORDER_EXECUTED, is_buy, id, price, fill, top.price);
       book_send<RP>(top.agent, ABIDES_MSG_ORDER_EXECUTED, !is_buy, top.id, top.price, fill, top.price);
@@ -1078,7 +1111,7 @@ __device__ __noinline__ void book_handle_limit(int agent, int id, int price, int
       h.n_fills++; h.volume += fill;
       if (qty <= 0) break;
     } else {
-      book_enter(is_buy ? BID : ASK, price, qty, id, agent);
+      book_enter(is_buy ? BID : ASK, price, qty, id, agent, my_log);
       book_send<RP>(agent, ABIDES_MSG_ORDER_ACCEPTED, is_buy, id, price, qty, -1, HOT.last_hint);   // w1: pool slot hint
       break;
     }
@@ -1252,7 +1285,7 @@ __device__ __noinline__ void ta_place_limit(int a, long long qty, bool is_buy, l
 __device__ __noinline__ void ta_cancel_all(int a) {
   AgentRec& A = ST.ag;
   const int klass = c_db.types[A.type_idx].klass;
-  const bool hinted = klass == ABIDES_ZI || klass == ABIDES_VALUE;
+  const bool hinted = klass == ABIDES_ZI || klass == ABIDES_VALUE || klass == ABIDES_HBL;
   __syncwarp();
   for (int i = 0; i < A.ord_cnt; i++) {
     OpenOrd o = RUN.arena[A.ord_off + i];
@@ -1322,7 +1355,7 @@ __device__ __forceinline__ void ta_receive(int a, const Msg& m, int klass, const
       break;
     }
     case ABIDES_MSG_ORDER_ACCEPTED:                           // (not in the reference) remember where the order rests
-      if (klass == ABIDES_ZI || klass == ABIDES_VALUE) { A.u.est.hint_id = m.w2; A.u.est.hint = m.w1; }
+      if (klass == ABIDES_ZI || klass == ABIDES_VALUE || klass == ABIDES_HBL) { A.u.est.hint_id = m.w2; A.u.est.hint = m.w1; }
       break;
     case ABIDES_MSG_ORDER_CANCELLED: {
       int idx = ord_find(m.w2);
@@ -1341,6 +1374,10 @@ __device__ __forceinline__ void ta_receive(int a, const Msg& m, int klass, const
       if (A.flags & F_MKT_CLOSED) A.flags |= F_HAS_DAILY_CLOSE;
       A.bid = m.w1; A.bid_vol = m.w2; A.ask = m.w3; A.ask_vol = m.w4; A.flags |= F_KNOWN_BOOK;
       break;
+    case ABIDES_MSG_QUERY_ORDER_STREAM:                       // queryOrderStream (:514-520): which buckets we were handed
+      if (pay_closed(m.w0)) A.flags |= F_MKT_CLOSED;
+      if (klass == ABIDES_HBL) { A.u.est.stream_n = m.w1; A.u.est.stream_B = m.w2; }
+      break;
     case ABIDES_MSG_QUERY_TRANSACTED_VOLUME:
       if (pay_closed(m.w0)) A.flags |= F_MKT_CLOSED;
       if (klass == ABIDES_ADAPTIVE_MM)
@@ -1355,7 +1392,7 @@ __device__ __forceinline__ void ta_receive(int a, const Msg& m, int klass, const
   bool have = (A.flags & F_HAS_OPEN) && (A.flags & F_HAS_CLOSE);
   if (UNLIKELY(have && !had)) {
     long long off;
-    if (klass == ABIDES_ZI || klass == ABIDES_VALUE || klass == ABIDES_NOISE) off = rng_randint(SID_AGENT, 0, 100);
+    if (klass == ABIDES_ZI || klass == ABIDES_VALUE || klass == ABIDES_NOISE || klass == ABIDES_HBL) off = rng_randint(SID_AGENT, 0, 100);
     else off = ty.wake_up_freq;
     k_wakeup(a, RUN.cfg.mkt_open + off);
   }
@@ -1392,7 +1429,8 @@ __device__ __forceinline__ long long round_hundreds(long long hld) {     // int(
   return q;
 }
 // ZeroIntelligenceAgent.placeOrder (:249-281)
-__device__ __noinline__ void zi_place_order(int a, const abides_agent_type& ty) {
+// ZeroIntelligenceAgent.updateEstimates (:163-247): observation, side, total unit valuation (side in HOT.find_idx)
+__device__ __noinline__ long long zi_update_estimates(int a, const abides_agent_type& ty) {
   AgentRec& A = ST.ag;
   long long obs = oracle_observe(A.cur_time, ty.sigma_n, SID_AGENT);
   long long q = A.holdings / 100;
@@ -1404,7 +1442,13 @@ __device__ __noinline__ void zi_place_order(int a, const abides_agent_type& ty) 
   q += ty.q_max - 1;
   long long row = RUN.aoff + a;
   long long theta = c_db.theta[RUN.cfg.theta_offset + c_db.agent_theta[row] + (buy ? q + 1 : q)];
-  long long v = r_T + theta;
+  HOT.find_idx = buy ? 1 : 0;
+  return r_T + theta;
+}
+__device__ __noinline__ void zi_place_order(int a, const abides_agent_type& ty) {
+  AgentRec& A = ST.ag;
+  const long long v = zi_update_estimates(a, ty);
+  const bool buy = HOT.find_idx != 0;
   long long R = rng_randint(SID_AGENT, ty.R_min, ty.R_max + 1);
   long long p = buy ? v - R : v + R;
   if (buy && A.ask_vol > 0) {
@@ -1415,6 +1459,119 @@ __device__ __noinline__ void zi_place_order(int a, const abides_agent_type& ty) 
     if ((double)R_bid >= ty.eta * (double)R) p = A.bid;
   }
   ta_place_limit(a, 100, buy, p);
+}
+__device__ __forceinline__ int warp_incl_scan(int v) {         // inclusive prefix sum over lanes 0..31
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { int x = __shfl_up_sync(FULL, v, o); if (LANE >= o) v += x; }
+  return v;
+}
+// HeuristicBeliefLearningAgent.placeOrder (:42-153).  The buckets it was handed are [stream_B - stream_n, stream_B):
+// it holds the exchange's history dicts themselves, so "has transactions" is read as of NOW from the order log.
+// nd[:, 0..3] = sa, sb, ua, ub per price; cumulative sums; Pr = num / denom; Es = Pr * surplus; first arg-max.
+__device__ __noinline__ void hbl_place_order(int a, const abides_agent_type& ty) {
+  AgentRec& A = ST.ag;
+  if (A.u.est.stream_n < ty.hbl_L) { zi_place_order(a, ty); return; }      // not enough history: exactly ZI
+  const long long v = zi_update_estimates(a, ty);
+  const bool buy = HOT.find_idx != 0;
+  const int lo_b = A.u.est.stream_B - A.u.est.stream_n, hi_b = A.u.est.stream_B - 1;
+  const OLogRow* lg = RUN.olog;
+  const long long end = HOT.olog_len;
+  // rows are in bucket order: walk back (newest first, lane 0 = newest) to the first row of bucket lo_b
+  long long start = -1;
+  int low_p = INT_MAX, high_p = 0;
+#pragma unroll 1
+  for (long long base = end; start < 0; base -= 32) {
+    const long long i = base - 1 - LANE;
+    const bool lost = i >= 0 && end - i > OLOG_CAP;          // the window reaches past the ring
+    bool stop = i < 0 || lost;
+    if (!stop) {
+      OLogRow r = lg[i & (OLOG_CAP - 1)];
+      stop = r.bucket < lo_b;
+      if (!stop && r.bucket <= hi_b) { low_p = min(low_p, r.price); high_p = max(high_p, r.price); }
+    }
+    const unsigned m = __ballot_sync(FULL, stop), ml = __ballot_sync(FULL, lost);
+    if (m) {
+      const int k = __ffs(m) - 1;
+      if ((ml >> k) & 1u) { HOT.status = ABIDES_EOVERFLOW; return; }
+      start = base - k;                                        // first row that is not older than the window
+    }
+  }
+  low_p = __reduce_min_sync(FULL, low_p);
+  high_p = __reduce_max_sync(FULL, high_p);
+  const int R = high_p - low_p + 1;
+  if (R <= 0) { HOT.status = ABIDES_ESTATE; return; }                       // np.zeros((negative, 8)) raises in the reference
+  if (R > HBL_RANGE_CAP) { HOT.status = ABIDES_EOVERFLOW; return; }
+  int* c0 = RUN.hbl_cnt;                       // sa: successful asks   (rows of HBL_RANGE_CAP ints)
+  int* c1 = c0 + HBL_RANGE_CAP;                // sb: successful bids
+  int* c2 = c1 + HBL_RANGE_CAP;                // ua: unsuccessful asks
+  int* c3 = c2 + HBL_RANGE_CAP;                // ub: unsuccessful bids
+  for (int i = LANE; i < R; i += 32) { c0[i] = 0; c1[i] = 0; c2[i] = 0; c3[i] = 0; }
+  __syncwarp();
+  for (long long i = start + LANE; i < end; i += 32) {
+    OLogRow r = lg[i & (OLOG_CAP - 1)];
+    if (r.bucket < lo_b || r.bucket > hi_b) continue;
+    int* col = (r.flags & 1) ? ((r.flags & 2) ? c1 : c3) : ((r.flags & 2) ? c0 : c2);
+    atomicAdd(&col[r.price - low_p], 1);
+  }
+  __syncwarp();
+  double best_es = -INFINITY; int best_i = INT_MAX;
+  const int nchunk = (R + 31) / 32;
+  if (buy) {
+    // ub becomes a suffix sum (in place), then one ascending pass with the three prefix sums
+    int carry = 0;
+    for (int ch = nchunk - 1; ch >= 0; ch--) {
+      int i = ch * 32 + (31 - LANE);
+      int x = i < R ? c3[i] : 0;
+      int sc = warp_incl_scan(x) + carry;
+      if (i < R) c3[i] = sc;
+      carry = __shfl_sync(FULL, sc, 31);
+    }
+    __syncwarp();
+    int k0 = 0, k1 = 0, k2 = 0;
+    for (int ch = 0; ch < nchunk; ch++) {
+      int i = ch * 32 + LANE;
+      bool in = i < R;
+      int s0 = warp_incl_scan(in ? c0[i] : 0) + k0, s1 = warp_incl_scan(in ? c1[i] : 0) + k1, s2 = warp_incl_scan(in ? c2[i] : 0) + k2;
+      k0 = __shfl_sync(FULL, s0, 31); k1 = __shfl_sync(FULL, s1, 31); k2 = __shfl_sync(FULL, s2, 31);
+      if (in) {
+        double num = ((double)s0 + (double)s1) + (double)s2, den = num + (double)c3[i];
+        double pr = den == 0 ? 0.0 : fdiv(num, den);
+        double es = pr * (double)(v - ((long long)low_p + i));
+        if (es > best_es) { best_es = es; best_i = i; }
+      }
+    }
+  } else {
+    // ua becomes a prefix sum (in place), then one descending pass with the three suffix sums
+    int carry = 0;
+    for (int ch = 0; ch < nchunk; ch++) {
+      int i = ch * 32 + LANE;
+      int x = i < R ? c2[i] : 0;
+      int sc = warp_incl_scan(x) + carry;
+      if (i < R) c2[i] = sc;
+      carry = __shfl_sync(FULL, sc, 31);
+    }
+    __syncwarp();
+    int k0 = 0, k1 = 0, k3 = 0;
+    for (int ch = nchunk - 1; ch >= 0; ch--) {
+      int i = ch * 32 + (31 - LANE);
+      bool in = i < R;
+      int s0 = warp_incl_scan(in ? c0[i] : 0) + k0, s1 = warp_incl_scan(in ? c1[i] : 0) + k1, s3 = warp_incl_scan(in ? c3[i] : 0) + k3;
+      k0 = __shfl_sync(FULL, s0, 31); k1 = __shfl_sync(FULL, s1, 31); k3 = __shfl_sync(FULL, s3, 31);
+      if (in) {
+        double num = ((double)s0 + (double)s1) + (double)s3, den = (((double)s0 + (double)s1) + (double)c2[i]) + (double)s3;
+        double pr = den == 0 ? 0.0 : fdiv(num, den);
+        double es = pr * (double)(((long long)low_p + i) - v);
+        if (es >= best_es) { best_es = es; best_i = i; }          // descending walk: a later equal value has the smaller index
+      }
+    }
+  }
+  // np.argmax: the first (lowest-index) maximum over all lanes
+#pragma unroll 1
+  for (int o = 16; o; o >>= 1) {
+    double oe = __shfl_xor_sync(FULL, best_es, o); int oi = __shfl_xor_sync(FULL, best_i, o);
+    if (oe > best_es || (oe == best_es && oi < best_i)) { best_es = oe; best_i = oi; }
+  }
+  if (best_es > 0) ta_place_limit(a, 100, buy, (long long)low_p + best_i);
 }
 // ValueAgent.placeOrder (:188-220)
 __device__ __noinline__ void value_place_order(int a, const abides_agent_type& ty) {
@@ -1526,6 +1683,11 @@ __device__ __noinline__ void zvn_wakeup(int a, const abides_agent_type& ty) {
   }
   if (UNLIKELY((A.flags & F_MKT_CLOSED) && !(A.flags & F_HAS_DAILY_CLOSE))) { ta_query_spread(a); ag_set_state(A, ST_AWAITING_SPREAD); return; }
   if (ty.klass != ABIDES_NOISE) ta_cancel_all(a);
+  if (ty.klass == ABIDES_HBL) {                               // HBL.wakeup (:29-40): state 'ACTIVE' -> ask for the order stream
+    agent_send(a, ABIDES_MSG_QUERY_ORDER_STREAM, ty.hbl_L, 0, 0, 0);
+    ag_set_state(A, ST_AWAITING_STREAM);
+    return;
+  }
   ta_query_spread(a);
   ag_set_state(A, ST_AWAITING_SPREAD);
 }
@@ -1571,7 +1733,7 @@ __device__ __noinline__ void other_wakeup(int a, const abides_agent_type& ty) {
 }
 __device__ __forceinline__ void agent_wakeup(int a) {
   const abides_agent_type& ty = c_db.types[ST.ag.type_idx];
-  if (ty.klass <= ABIDES_NOISE) zvn_wakeup(a, ty);
+  if (ty.klass <= ABIDES_NOISE || ty.klass == ABIDES_HBL) zvn_wakeup(a, ty);
   else other_wakeup(a, ty);
 }
 
@@ -1661,13 +1823,19 @@ __device__ __noinline__ void agent_receive(int a, int w0, int w1, int w2, int w3
   const int code = pay_code(w0) & ~ABIDES_MSG_REPLY;
   const int klass = ty.klass;
   ta_receive(a, m, klass, ty);
-  if (klass <= ABIDES_NOISE) {
+  if (klass <= ABIDES_NOISE || klass == ABIDES_HBL) {
     if (ag_state(A) == ST_AWAITING_SPREAD && code == ABIDES_MSG_QUERY_SPREAD) {
       if (A.flags & F_MKT_CLOSED) return;
       if (klass == ABIDES_ZI) zi_place_order(a, ty);
+      else if (klass == ABIDES_HBL) hbl_place_order(a, ty);
       else if (klass == ABIDES_VALUE) value_place_order(a, ty);
       else noise_place_order(a);
       ag_set_state(A, ST_AWAITING_WAKEUP);
+    }
+    if (klass == ABIDES_HBL && ag_state(A) == ST_AWAITING_STREAM && code == ABIDES_MSG_QUERY_ORDER_STREAM) {
+      if (A.flags & F_MKT_CLOSED) return;                      // HBL.receiveMessage (:155-173)
+      ta_query_spread(a);
+      ag_set_state(A, ST_AWAITING_SPREAD);
     }
     return;
   }
@@ -1706,6 +1874,12 @@ __device__ __noinline__ void exchange_receive(int w0, int w1, int w2, int w3, in
     case ABIDES_MSG_QUERY_LAST_TRADE:
       k_send(0, sender, 0, (ABIDES_MSG_QUERY_LAST_TRADE | ABIDES_MSG_REPLY) | cflag, 0, 0, 0, 0, h.last_trade);
       break;
+    case ABIDES_MSG_QUERY_ORDER_STREAM: {                      // history[1:length+1] (ExchangeAgent.py:210-225)
+      int avail = h.hist_B < cfg.stream_history ? h.hist_B : cfg.stream_history;
+      if (w2 < avail) avail = w2;
+      k_send(0, sender, 0, (ABIDES_MSG_QUERY_ORDER_STREAM | ABIDES_MSG_REPLY) | cflag, avail, h.hist_B, 0, 0, 0);
+      break;
+    }
     case ABIDES_MSG_QUERY_SPREAD: {
       int2 b = side_inside(BID), a = side_inside(ASK);
       k_send(0, sender, 0, (ABIDES_MSG_QUERY_SPREAD | ABIDES_MSG_REPLY) | cflag, b.x, b.y, a.x, a.y, h.last_trade);
@@ -1794,13 +1968,19 @@ __device__ __noinline__ void finalize() {
     long long cash = A.cash;
     if (A.holdings != 0) cash += (long long)A.last_trade * A.holdings;
     double fv = nan("");
-    if (ty.klass == ABIDES_ZI) {
+    if (ty.klass == ABIDES_ZI || ty.klass == ABIDES_HBL) {
       long long H = round_hundreds(A.holdings);
       long long rT = oracle_observe(A.cur_time, 0, SID_AGENT);
       long long surplus = 0;
       const int* th = c_db.theta + RUN.cfg.theta_offset + c_db.agent_theta[RUN.aoff + a];
+      // past q_max lots the reference indexes theta out of range: IndexError when long (H > q_max), Python's
+      // negative-index wrap-around when short (ZeroIntelligenceAgent.py:75-81)
+      if (H > ty.q_max) { if (h.status == 0) h.status = ABIDES_ESTATE; H = ty.q_max; }
       if (H > 0) for (long long x = 1; x <= H; x++) surplus += th[x + ty.q_max - 1];
-      else if (H < 0) { for (long long x = H + 1; x <= 0; x++) surplus += th[x + ty.q_max - 1]; surplus = -surplus; }
+      else if (H < 0) {
+        for (long long x = H + 1; x <= 0; x++) { long long j = x + ty.q_max - 1; surplus += th[j < 0 ? j + 2 * ty.q_max : j]; }
+        surplus = -surplus;
+      }
       surplus += rT * H;
       surplus += A.cash - ty.starting_cash;
       fv = (double)surplus;
@@ -1875,7 +2055,7 @@ __global__ void __launch_bounds__(32) init_kernel() {
       A.rng.flags = db.mt_has_gauss[stream] ? 1u : 0u;
     }
     switch (ty.klass) {
-      case ABIDES_ZI: case ABIDES_VALUE: A.u.est.r_t = ty.r_bar; A.u.est.sigma_t = 0; break;
+      case ABIDES_ZI: case ABIDES_VALUE: case ABIDES_HBL: A.u.est.r_t = ty.r_bar; A.u.est.sigma_t = 0; break;
       case ABIDES_NOISE: A.u.noise.wakeup_time = db.wakeup_time[row]; break;
       case ABIDES_MOMENTUM: A.u.mom.ring = db.mom_index[row]; break;
       case ABIDES_ADAPTIVE_MM:
@@ -1943,6 +2123,8 @@ __device__ __noinline__ void run_setup(int inst) {
     r.lcap[L_POOL + s] = db.deep_cap;
     r.pfree[s] = db.p_free + ((size_t)inst * 2 + s) * db.deep_cap;
   }
+  r.olog = db.olog ? db.olog + (size_t)inst * OLOG_CAP : nullptr;
+  r.hbl_cnt = db.hbl_cnt ? db.hbl_cnt + (size_t)inst * 4 * HBL_RANGE_CAP : nullptr;
   r.arena = db.arena + (size_t)inst * db.arena_cap;
   r.txn_log = db.txn_log + (size_t)inst * TXN_CAP;
   r.unrolled = db.unrolled + (size_t)inst * UNR_CAP;
@@ -2135,10 +2317,11 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
 namespace {
 struct ShapeSig {
   int ni = 0, n_types = 0, rng_mode = -1, trace_cap = -1, max_agents = 0, n_mom = 0;
+  bool has_hbl = false;
   long long na = -1, n_theta = -1;
   bool operator==(const ShapeSig& o) const {
     return ni == o.ni && n_types == o.n_types && rng_mode == o.rng_mode && trace_cap == o.trace_cap &&
-           max_agents == o.max_agents && n_mom == o.n_mom && na == o.na && n_theta == o.n_theta;
+           max_agents == o.max_agents && n_mom == o.n_mom && na == o.na && n_theta == o.n_theta && has_hbl == o.has_hbl;
   }
 };
 }  // namespace
@@ -2265,7 +2448,7 @@ int abides_load(abides_handle* h, const abides_batch* b) {
   int max_agents = 0;
   long long off = 0;
   std::vector<int> mom_index((size_t)na, -1);
-  int n_mom = 0;
+  int n_mom = 0, n_hbl = 0;
   for (int i = 0; i < ni; i++) {
     const abides_instance_cfg& ic = b->instances[i];
     if (ic.agent_offset != off || ic.n_agents <= 0) return fail(ABIDES_EINVAL, "abides_load: agent_offset must be the prefix sum of n_agents");
@@ -2278,9 +2461,9 @@ int abides_load(abides_handle* h, const abides_batch* b) {
       int k = b->types[t].klass;
       if ((a == 0) != (k == ABIDES_EXCHANGE)) return fail(ABIDES_EINVAL, "abides_load: agent 0 (and only agent 0) must be the exchange");
       if (k < 0 || k > ABIDES_HBL) return fail(ABIDES_EINVAL, "abides_load: unknown agent class");
-      if (k == ABIDES_HBL) return fail(ABIDES_EINVAL, "abides_load: HeuristicBeliefLearningAgent is not implemented on the device yet");
+      if (k == ABIDES_HBL) { n_hbl++; if (b->types[t].hbl_L < 1) return fail(ABIDES_EINVAL, "abides_load: HBL agent with L < 1"); }
       if (k == ABIDES_MOMENTUM) mom_index[off + a] = n_mom++;
-      if (k == ABIDES_ZI && (b->agent_theta[off + a] < 0 || !b->theta)) return fail(ABIDES_EINVAL, "abides_load: ZI agent without theta");
+      if ((k == ABIDES_ZI || k == ABIDES_HBL) && (b->agent_theta[off + a] < 0 || !b->theta)) return fail(ABIDES_EINVAL, "abides_load: ZI / HBL agent without theta");
     }
     if (ic.n_agents > max_agents) max_agents = ic.n_agents;
     off += ic.n_agents;
@@ -2288,7 +2471,7 @@ int abides_load(abides_handle* h, const abides_batch* b) {
   if (off != na) return fail(ABIDES_EINVAL, "abides_load: n_agents_total mismatch");
   ShapeSig sig;
   sig.ni = ni; sig.n_types = b->n_types; sig.rng_mode = b->rng_mode; sig.trace_cap = b->trace_capacity;
-  sig.max_agents = max_agents; sig.n_mom = n_mom; sig.na = na; sig.n_theta = b->n_theta_total;
+  sig.max_agents = max_agents; sig.n_mom = n_mom; sig.na = na; sig.n_theta = b->n_theta_total; sig.has_hbl = n_hbl > 0;
   DevBatch& d = h->db;
   int rc;
   size_t ns = (size_t)na + (size_t)ABIDES_EXTRA_STREAMS * ni;
@@ -2334,6 +2517,10 @@ int abides_load(abides_handle* h, const abides_batch* b) {
     if ((rc = dev_alloc(h, &d.p_keys, (size_t)ni * 2 * d.deep_cap))) return rc;
     if ((rc = dev_alloc(h, &d.p_pay, (size_t)ni * 2 * d.deep_cap))) return rc;
     if ((rc = dev_alloc(h, &d.p_free, (size_t)ni * 2 * d.deep_cap))) return rc;
+    if (n_hbl > 0) {
+      if ((rc = dev_alloc(h, &d.olog, (size_t)ni * OLOG_CAP))) return rc;
+      if ((rc = dev_alloc(h, &d.hbl_cnt, (size_t)ni * 4 * HBL_RANGE_CAP))) return rc;
+    }
     if ((rc = dev_alloc(h, &d.txn_log, (size_t)ni * TXN_CAP))) return rc;
     if ((rc = dev_alloc(h, &d.unrolled, (size_t)ni * UNR_CAP))) return rc;
     if ((rc = dev_alloc(h, &d.mom_ring, (size_t)(n_mom > 0 ? n_mom : 1) * MOM_RING))) return rc;

@@ -36,6 +36,8 @@ WORKLOADS = {
     # BASELINE configs[2] "rmsc01: value + noise agents + market maker", from the supported classes
     "rmsc01": ("rmsc03", ["-t", "ABM", "-d", "20200603", "--end-time", "16:00:00", "--num-noise", "50",
                           "--num-value", "25", "--num-momentum", "24"]),
+    # the reference's literal config/rmsc01.py population: 1 MarketMaker + 50 ZI + 25 HBL + 24 momentum
+    "rmsc01_literal": ("rmsc01", []),
 }
 
 

@@ -27,6 +27,9 @@ CASES = {
     # 75 ZI + 24 momentum agents, 09:30-11:00; HBL agents are not on the device yet.  Reference side:
     # tests/golden/refcfg/rmsc01_flags.py
     "rmsc01mm_s33": ("rmsc01", ["-s", "33", "--num-zi", "75", "--num-hbl", "0", "--end-time", "11:00:00"]),
+    # the literal rmsc01 population (1 MarketMaker + 50 ZI + 25 HBL + 24 momentum), 09:30-11:00
+    "rmsc01_s33_1100": ("rmsc01", ["-s", "33", "--end-time", "11:00:00"]),
+    "rmsc01_s34_1100": ("rmsc01", ["-s", "34", "--end-time", "11:00:00"]),
     # BASELINE configs[2] "rmsc01: value + noise agents + market maker" from the supported classes: the rmsc03
     # population at rmsc01 scale (103 agents), one full market day; reference side: tests/golden/refcfg/rmsc_small.py
     "rmsc01s_s77": ("rmsc03", ["-t", "ABM", "-d", "20200603", "-s", "77", "--end-time", "16:00:00",
