@@ -21,7 +21,7 @@ def build_cuda(force=False, verbose=False, profile=False):
     """Compile csrc/engine.cu for sm_100a.  profile=True builds the instrumented variant next to it."""
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    deps = srcs + [os.path.join(INCLUDE, h) for h in ("abides_b200.h", "abides_dd_math.h", "abides_math_tables.h")]
+    deps = srcs + [os.path.join(CSRC, "engine_device.inc")] + [os.path.join(INCLUDE, h) for h in ("abides_b200.h", "abides_dd_math.h", "abides_math_tables.h")]
     out = OUT_PROF if profile else OUT
     if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
         return out
