@@ -456,11 +456,11 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
 namespace {
 struct ShapeSig {
   int ni = 0, n_types = 0, rng_mode = -1, trace_cap = -1, max_agents = 0, n_mom = 0;
-  bool has_hbl = false;
+  bool has_hbl = false, needs_tv = false;
   long long na = -1, n_theta = -1;
   bool operator==(const ShapeSig& o) const {
     return ni == o.ni && n_types == o.n_types && rng_mode == o.rng_mode && trace_cap == o.trace_cap &&
-           max_agents == o.max_agents && n_mom == o.n_mom && na == o.na && n_theta == o.n_theta && has_hbl == o.has_hbl;
+           max_agents == o.max_agents && n_mom == o.n_mom && na == o.na && n_theta == o.n_theta && has_hbl == o.has_hbl && needs_tv == o.needs_tv;
   }
 };
 }  // namespace
@@ -620,6 +620,8 @@ int abides_load(abides_handle* h, const abides_batch* b) {
   ShapeSig sig;
   sig.ni = ni; sig.n_types = b->n_types; sig.rng_mode = b->rng_mode; sig.trace_cap = b->trace_capacity;
   sig.max_agents = max_agents; sig.n_mom = n_mom; sig.na = na; sig.n_theta = b->n_theta_total; sig.has_hbl = n_hbl > 0;
+  const bool needs_tv = (class_mask & ((1u << ABIDES_ADAPTIVE_MM) | (1u << ABIDES_POV_EXEC))) != 0;
+  sig.needs_tv = needs_tv;
   DevBatch& d = h->db;
   int rc;
   size_t ns = (size_t)na + (size_t)ABIDES_EXTRA_STREAMS * ni;
@@ -669,8 +671,10 @@ int abides_load(abides_handle* h, const abides_batch* b) {
       if ((rc = dev_alloc(h, &d.olog, (size_t)ni * OLOG_CAP))) return rc;
       if ((rc = dev_alloc(h, &d.hbl_cnt, (size_t)ni * 4 * HBL_RANGE_CAP))) return rc;
     }
-    if ((rc = dev_alloc(h, &d.txn_log, (size_t)ni * TXN_CAP))) return rc;
-    if ((rc = dev_alloc(h, &d.unrolled, (size_t)ni * UNR_CAP))) return rc;
+    if (needs_tv) {                           // 2 MB per instance: only where some agent queries transacted volume
+      if ((rc = dev_alloc(h, &d.txn_log, (size_t)ni * TXN_CAP))) return rc;
+      if ((rc = dev_alloc(h, &d.unrolled, (size_t)ni * UNR_CAP))) return rc;
+    }
     if ((rc = dev_alloc(h, &d.mom_ring, (size_t)(n_mom > 0 ? n_mom : 1) * MOM_RING))) return rc;
     if ((rc = dev_alloc(h, &d.trace, (size_t)ni * (d.trace_cap > 0 ? d.trace_cap : 0)))) return rc;
     if ((rc = dev_alloc(h, &d.res, (size_t)ni))) return rc;
