@@ -70,3 +70,50 @@ def test_device_book_replay_many_books_property():
     events_o, counts_o, states_o = eng_mod.unpack_replay(ev2, cnt2[:len(rows)], st2, len(rows), 64)
     assert np.array_equal(states, states_o)
     assert np.array_equal(events, events_o)
+
+
+@pytest.mark.gpu
+def test_device_deep_book_fuzz_matches_oracle():
+    """Deep, wide books with every message type: thousands of resting orders per book (far past the 64 per side kept
+    in shared memory, so the pool, its slot reuse, refills and level sums that run into the pool are all exercised),
+    cancels of live / dead / never-seen orders, modifies (incl. the reference's index-0 overwrite) and market orders
+    that sweep several levels.  Device == oracle on every notification and on the book state after every message."""
+    rng = np.random.default_rng(20261020)
+    rows, off = [], [0]
+    for b in range(48):
+        t, next_id, placed = 0, 1, []
+        width = int(rng.choice([5, 40, 400, 3000]))
+        n_ops = int(rng.choice([400, 1500, 4000]))
+        for i in range(n_ops):
+            t += int(rng.integers(1, 1000))
+            u = rng.random()
+            agent = int(rng.integers(1, 60))
+            if u < 0.62 or not placed:                      # limit order; mostly passive, sometimes crossing
+                buy = int(rng.integers(0, 2))
+                off_px = int(rng.integers(-width // 10 - 1, width))
+                price = 100000 - off_px if buy else 100000 + off_px
+                qty = int(rng.integers(1, 400))
+                rows.append((7, agent, next_id, price, qty, buy, 0, t))
+                placed.append((next_id, price, buy, agent))
+                next_id += 1
+            elif u < 0.88:                                  # cancel (some already gone, some twice)
+                oid, price, buy, ag = placed[int(rng.integers(0, len(placed)))]
+                rows.append((9, ag, oid, price, 1, buy, 0, t))
+            elif u < 0.93:                                  # modify
+                oid, price, buy, ag = placed[int(rng.integers(0, len(placed)))]
+                rows.append((10, ag, oid, price, 1, buy, int(rng.integers(1, 500)), t))
+            else:                                           # market order
+                rows.append((8, agent, next_id, 0, int(rng.integers(1, 3000)), int(rng.integers(0, 2)), 0, t))
+                next_id += 1
+        off.append(len(rows))
+    rows = np.array(rows, np.int64)
+    offs = np.array(off, np.int64)
+    e = eng_mod.Engine(0)
+    events, counts, states = eng_mod.replay_book(e, offs, rows, 25, 96)
+    ev2, cnt2, st2 = oracle.replay_book(offs, eng_mod.make_book_ops(rows), 25, 96)
+    events_o, counts_o, states_o = eng_mod.unpack_replay(ev2, cnt2[:len(rows)], st2, len(rows), 96)
+    assert (counts <= 96).all() and np.array_equal(counts, counts_o)
+    assert np.array_equal(states, states_o)
+    # market-order children take fresh ids from 1 << 30 in both restatements
+    assert np.array_equal(events, events_o)
+    assert states[:, 5].max() > 100 and states[:, 6].max() > 100      # books really were deep (levels per side; 64 orders per side fit in shared memory)
