@@ -24,6 +24,7 @@ MSG_NAMES = {
     13: "ORDER_CANCELLED", 14: "ORDER_MODIFIED", 15: "MKT_CLOSED",
 }
 MSG_CODES = {v: k for k, v in MSG_NAMES.items()}
+TRACE_FUNDAMENTAL = 64          # trace code of an oracle step (include/abides_b200.h: abides_trace_rec)
 MSG_REPLY = 32
 
 

@@ -45,8 +45,13 @@ class Kernel:
         if runtime.capturing():
             runtime.captured(spec, self)
             return self.custom_state
-        out = runtime.run_specs([spec])
+        trace = None
+        if skip_log:
+            out = runtime.run_specs([spec])
+        else:
+            out, trace = runtime.run_spec_logged(spec)
         runtime.write_back(self, out, 0)
+        runtime.write_logs(self, trace)
         runtime.report(self, out, 0)
         return self.custom_state
 

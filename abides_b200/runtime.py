@@ -94,6 +94,67 @@ def write_back(kernel, out, inst):
     kernel.custom_state['ttl_messages'] = int(r["ttl_messages"])
 
 
+def summary_log_rows(kernel):
+    """The rows the reference's agents append to the kernel summary log (Kernel.py:514-520): STARTING_CASH from
+    every TradingAgent.kernelStarting (TradingAgent.py:108), then per agent FINAL_CASH_POSITION / ENDING_CASH
+    (TradingAgent.py:127-132) and, for the classes that report it, FINAL_VALUATION (ZeroIntelligenceAgent.py:93,
+    ValueAgent.py:75, NoiseAgent.py:68).  Needs write_back() to have run."""
+    rows = []
+
+    def row(a, ev, val):
+        rows.append({'AgentID': a.id, 'AgentStrategy': a.type, 'EventType': ev, 'Event': val})
+
+    for a in kernel.agents[1:]:
+        row(a, 'STARTING_CASH', a.starting_cash)
+    for a in kernel.agents[1:]:
+        row(a, 'FINAL_CASH_POSITION', a.holdings['CASH'])
+        row(a, 'ENDING_CASH', a.marked_to_market)
+        if a.final_valuation is not None:
+            fv = a.final_valuation
+            row(a, 'FINAL_VALUATION', int(fv) if float(fv).is_integer() else fv)
+    return rows
+
+
+def fundamental_frame(kernel, trace):
+    """The oracle's f_log as the frame ExchangeAgent.kernelTerminating archives (ExchangeAgent.py:96-101,
+    SparseMeanRevertingOracle.py:66,:121): the opening (mkt_open, r_bar) row, then one row per oracle step, taken
+    from the device trace's ABIDES_TRACE_FUNDAMENTAL records."""
+    import pandas as pd
+    sym = next(iter(kernel.agents[0].order_books))
+    fund = trace[trace[:, 2] == _abi.TRACE_FUNDAMENTAL]
+    t = np.concatenate([[pd.Timestamp(kernel.oracle.mkt_open).value], fund[:, 0]]).astype(np.int64)
+    v = np.concatenate([[float(kernel.oracle.symbols[sym]['r_bar'])], fund[:, 3].astype(np.float64)])
+    df = pd.DataFrame({'FundamentalTime': pd.to_datetime(t), 'FundamentalValue': v})
+    return sym, df.set_index('FundamentalTime')
+
+
+def write_logs(kernel, trace=None, root="."):
+    """Kernel.writeSummaryLog (Kernel.py:523-532) and, when a trace was taken, the exchange's fundamental archive --
+    bz2-pickled DataFrames under ./log/<log_dir>/ with the reference's file names, columns and dtypes.  The
+    per-agent event logs and the order-book snapshots are not emitted (out of scope)."""
+    import pandas as pd
+    path = os.path.join(root, "log", kernel.log_dir)
+    os.makedirs(path, exist_ok=True)
+    kernel.summaryLog = summary_log_rows(kernel)
+    pd.DataFrame(kernel.summaryLog).to_pickle(os.path.join(path, "summary_log.bz2"), compression='bz2')
+    if trace is not None and getattr(kernel.oracle, "symbols", None):
+        sym, df = fundamental_frame(kernel, trace)
+        df.to_pickle(os.path.join(path, "fundamental_{}.bz2".format(sym)), compression='bz2')
+    return path
+
+
+def run_spec_logged(spec, device=0):
+    """One instance with its full device trace: a first run sizes the trace (every dispatched event plus at most
+    one oracle step per event), the second records it."""
+    out = run_specs([spec], device=device)
+    cap = 2 * int(out.res["delivered"][0]) + 2 * spec.n_agents + 64
+    out = run_specs([spec], device=device, trace_capacity=cap)
+    tr, n = engine(device).trace(0)
+    if n > cap:
+        raise RuntimeError("trace overflow: %d records, capacity %d" % (n, cap))
+    return out, tr
+
+
 def mean_ending_values(kernel):
     """"Mean ending value by agent type" (Kernel.py:318-322): int(round(sum / count))."""
     return {t: int(round(v / kernel.agentCountByType[t])) for t, v in kernel.meanResultByAgentType.items()}

@@ -1,0 +1,64 @@
+"""Log files: summary_log.bz2 and fundamental_<symbol>.bz2 as the reference writes them
+(Kernel.py:514-532, ExchangeAgent.py:91-101), checked against files the unmodified reference produced
+(tests/golden/gen_log_golden.py)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from abides_b200 import engine as eng_mod, lowering, runtime
+from parity_util import GOLDEN, TRACE_FUNDAMENTAL, load_golden
+
+NAME, CONFIG, SEED = "zi100_s123456789", "sparse_zi_100", 123456789
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _check_files(path):
+    want = np.load(os.path.join(GOLDEN, NAME + ".logs.npz"))
+    s = pd.read_pickle(os.path.join(path, "summary_log.bz2"), compression="bz2")
+    assert list(s.columns) == ["AgentID", "AgentStrategy", "EventType", "Event"]
+    assert np.array_equal(s.AgentID.to_numpy(np.int64), want["summary_agent"])
+    assert list(s.AgentStrategy) == list(want["summary_strategy"])
+    assert list(s.EventType) == list(want["summary_type"])
+    assert s.Event.dtype == np.int64 and np.array_equal(s.Event.to_numpy(), want["summary_event"])
+    f = pd.read_pickle(os.path.join(path, str(want["fundamental_file"])), compression="bz2")
+    assert f.index.name == "FundamentalTime" and list(f.columns) == ["FundamentalValue"]
+    assert str(f.index.dtype) == "datetime64[ns]" and f.FundamentalValue.dtype == np.float64
+    assert np.array_equal(f.index.to_numpy("datetime64[ns]").astype(np.int64), want["fundamental_time"])
+    assert np.allclose(f.FundamentalValue.to_numpy(), want["fundamental_value"], rtol=1e-9, atol=0)
+
+
+def test_log_writers_reproduce_reference_files(tmp_path):
+    """Host side only: results and trace come from the reference golden, the files from runtime.write_logs."""
+    g, meta = load_golden(NAME)
+    ((spec, kernel),) = runtime.build_instances(CONFIG, [["-s", SEED, "-l", "x"]])
+    hb = lowering.HostBatch([spec])
+    res = np.zeros(1, eng_mod.INSTANCE_RESULT_DTYPE)
+    for k in ("ttl_messages", "last_trade", "slowest_agent_finish_time"):
+        res[k][0] = meta[k]
+    ares = np.zeros(meta["n_agents"], eng_mod.AGENT_RESULT_DTYPE)
+    ares["cash"], ares["holdings"], ares["marked_to_market"] = g["cash"], g["holdings"], g["mtm"]
+    ares["final_valuation"] = g["final_valuation"]
+    out = runtime.RunOutput(hb, res, ares, 0.0, 1.0)
+    runtime.write_back(kernel, out, 0)
+    n = len(g["f_time"]) - 1
+    fund = np.zeros((n, 7), np.int64)
+    fund[:, 0], fund[:, 1], fund[:, 2], fund[:, 3] = g["f_time"][1:], -1, TRACE_FUNDAMENTAL, g["f_value"][1:]
+    trace = np.concatenate([g["trace"], fund])
+    path = runtime.write_logs(kernel, trace, root=str(tmp_path))
+    assert path == os.path.join(str(tmp_path), "log", "x")
+    _check_files(path)
+
+
+@pytest.mark.gpu
+def test_cli_run_writes_reference_logs(tmp_path):
+    """`python -m abides_b200 -c sparse_zi_100 -s ... -l run` (abides.py) end to end on the device."""
+    env = dict(os.environ, PYTHONPATH=REPO + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    r = subprocess.run([sys.executable, "-m", "abides_b200", "-c", CONFIG, "-s", str(SEED), "-l", "run"],
+                       cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "Simulation ending!" in r.stdout
+    _check_files(os.path.join(str(tmp_path), "log", "run"))
