@@ -34,6 +34,12 @@ CASES = {
     # population at rmsc01 scale (103 agents), one full market day; reference side: tests/golden/refcfg/rmsc_small.py
     "rmsc01s_s77": ("rmsc03", ["-t", "ABM", "-d", "20200603", "-s", "77", "--end-time", "16:00:00",
                                "--num-noise", "50", "--num-value", "25", "--num-momentum", "24"]),
+    # more of the reference's stock configs that run on the supported classes (compat/config/ re-states each one;
+    # the goldens come from the reference's own config files): legacy latency matrix + noise with Noise / Value
+    # agents; full-day 5000 noise + 100 value; and the same plus the polling MarketMakerAgent and 25 momentum agents
+    "value_noise_s7": ("value_noise", ["-s", "7"]),
+    "random_fund_value_s7": ("random_fund_value", ["-s", "7", "-t", "ABM", "-d", "20200603"]),
+    "random_fund_diverse_s7": ("random_fund_diverse", ["-s", "7", "-t", "ABM", "-d", "20200603"]),
 }
 
 
@@ -67,6 +73,21 @@ def check_against_golden(r, g, meta, trace=None):
 def test_builders_reproduce_reference_inputs(name):
     _, meta = load_golden(name)
     assert spec_digest(build_case(name)) == meta["spec_sha256"]
+
+
+REF_CONFIG = os.path.join(os.environ.get("ABIDES_REFERENCE", "/root/reference"), "config")
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_CONFIG), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("name", ["zi100_s123456789", "zi1000_s123456789", "rmsc03_s1234_1000", "rmsc03e_s1234_1100",
+                                  "value_noise_s7", "random_fund_value_s7", "random_fund_diverse_s7"])
+def test_reference_config_files_run_unmodified_on_the_compat_tree(name):
+    """The drop-in claim at the config level: the reference's OWN config file, executed against abides_b200/compat
+    (its imports resolve to the descriptor classes), lowers to exactly the inputs the reference run received."""
+    cfg, args = CASES[name]
+    _, meta = load_golden(name)
+    ((spec, _),) = runtime.build_instances(os.path.join(REF_CONFIG, cfg + ".py"), [args])
+    assert spec_digest(spec) == meta["spec_sha256"]
 
 
 def test_stored_spec_equals_built_spec():
