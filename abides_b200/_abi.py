@@ -11,7 +11,7 @@ EXTRA_STREAMS = 4
 STREAM_ORACLE, STREAM_KERNEL, STREAM_LATENCY, STREAM_GLOBAL = 0, 1, 2, 3
 
 # enum abides_agent_class
-EXCHANGE, ZI, VALUE, NOISE, MOMENTUM, ADAPTIVE_MM, POV_EXEC, MARKET_MAKER, HBL = range(9)
+EXCHANGE, ZI, VALUE, NOISE, MOMENTUM, ADAPTIVE_MM, POV_EXEC, MARKET_MAKER, HBL, SCHEDULE_EXEC = range(10)
 # enum abides_latency_kind
 LAT_DETERMINISTIC, LAT_CUBIC, LAT_LEGACY_NOISE = range(3)
 # enum abides_rng_mode

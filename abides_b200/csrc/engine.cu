@@ -116,6 +116,7 @@ struct __align__(128) AgentRec {        // 128 bytes: one coalesced transaction
     struct { double last_spread, window_size; long long transacted_volume;
              int buy_size, sell_size, tick_size, last_mid; } mm;
     struct { long long executed, transacted_volume; } pov;                         // POVExecutionAgent
+    struct { long long executed; double arrival; } sx;                             // TWAP / VWAP ExecutionAgent
   } u;
 };
 static_assert(sizeof(AgentRec) == 128, "AgentRec must be 128 bytes");
@@ -303,6 +304,7 @@ __global__ void __launch_bounds__(32) init_kernel() {
     switch (ty.klass) {
       case ABIDES_ZI: case ABIDES_VALUE: case ABIDES_HBL: A.u.est.r_t = ty.r_bar; A.u.est.sigma_t = 0; break;
       case ABIDES_NOISE: A.u.noise.wakeup_time = db.wakeup_time[row]; break;
+      case ABIDES_SCHEDULE_EXEC: A.u.sx.executed = 0; A.u.sx.arrival = nan(""); break;
       case ABIDES_MOMENTUM: A.u.mom.ring = db.mom_index[row]; break;
       case ABIDES_ADAPTIVE_MM:
         A.flags |= F_MM_AWAIT_SPREAD | F_MM_AWAIT_TV;
@@ -364,7 +366,7 @@ __global__ void init_types_kernel() {
 namespace v_full {                      // everything (tracing, Philox, every agent class, book replay)
 #define ABM_V_TRACE 1
 #define ABM_V_PHILOX 1
-#define ABM_V_CLASSES 0x1ff
+#define ABM_V_CLASSES 0x3ff
 #define ABM_V_LAT (-1)
 #define ABM_V_OLOG 1
 #define ABM_V_TVLOG 1
@@ -607,11 +609,18 @@ int abides_load(abides_handle* h, const abides_batch* b) {
       if (t < 0 || t >= b->n_types) return fail(ABIDES_EINVAL, "abides_load: agent_type out of range");
       int k = b->types[t].klass;
       if ((a == 0) != (k == ABIDES_EXCHANGE)) return fail(ABIDES_EINVAL, "abides_load: agent 0 (and only agent 0) must be the exchange");
-      if (k < 0 || k > ABIDES_HBL) return fail(ABIDES_EINVAL, "abides_load: unknown agent class");
+      if (k < 0 || k > ABIDES_SCHEDULE_EXEC) return fail(ABIDES_EINVAL, "abides_load: unknown agent class");
       if (k == ABIDES_HBL) { n_hbl++; if (b->types[t].hbl_L < 1) return fail(ABIDES_EINVAL, "abides_load: HBL agent with L < 1"); }
       if (a > 0) class_mask |= 1u << k;
       if (k == ABIDES_MOMENTUM) mom_index[off + a] = n_mom++;
       if ((k == ABIDES_ZI || k == ABIDES_HBL) && (b->agent_theta[off + a] < 0 || !b->theta)) return fail(ABIDES_EINVAL, "abides_load: ZI / HBL agent without theta");
+      if (k == ABIDES_SCHEDULE_EXEC && b->types[t].exec_trade) {
+        const abides_agent_type& ty = b->types[t];
+        if (ty.wake_up_freq <= 0 || ty.exec_end_time < ty.exec_start_time + 2 * ty.wake_up_freq ||
+            (ty.exec_end_time - ty.exec_start_time) % ty.wake_up_freq != 0)
+          return fail(ABIDES_EINVAL, "abides_load: execution agent horizon is not a regular grid of >= 3 points");
+        if (b->agent_theta[off + a] < 0 || !b->theta) return fail(ABIDES_EINVAL, "abides_load: execution agent without schedule");
+      }
     }
     if (ic.n_agents > max_agents) max_agents = ic.n_agents;
     off += ic.n_agents;

@@ -21,6 +21,8 @@ _CLASS_BY_NAME = {
     "POVExecutionAgent": _abi.POV_EXEC,
     "MarketMakerAgent": _abi.MARKET_MAKER,
     "HeuristicBeliefLearningAgent": _abi.HBL,
+    "TWAPExecutionAgent": _abi.SCHEDULE_EXEC,
+    "VWAPExecutionAgent": _abi.SCHEDULE_EXEC,
 }
 
 
@@ -56,6 +58,37 @@ def _mt_state(rs):
     if name != "MT19937":
         raise ValueError("only MT19937 RandomState streams are supported")
     return np.asarray(key, dtype=np.uint32), int(pos), int(has_gauss), float(gauss)
+
+
+def _regular_horizon(agent):
+    """(first point, step, number of points) of a TWAP / VWAP agent's execution_time_horizon, all in ns."""
+    pts = [_ns(t) for t in agent.execution_time_horizon]
+    if len(pts) < 3:
+        raise NotImplementedError("execution_time_horizon needs at least three points")
+    step = pts[1] - pts[0]
+    if step <= 0 or any(b - a != step for a, b in zip(pts, pts[1:])):
+        raise NotImplementedError("execution_time_horizon must be a regular grid")
+    return pts[0], step, len(pts)
+
+
+def _schedule_rows(agent):
+    """schedule[slot] for the slots that place limit orders.  ExecutionAgent.placeOrders (:96-97) looks the slot up
+    as pd.Interval(t, t + 1 minute), so only a one-minute grid with one-minute bins can work in the reference."""
+    import pandas as pd
+    h0, step, n = _regular_horizon(agent)
+    if not getattr(agent, "trade", False):
+        return []
+    out = []
+    for i in range(n - 2):
+        t = pd.Timestamp(h0 + i * step)
+        key = pd.Interval(t, t + pd.Timedelta(minutes=1))
+        if key not in agent.schedule:
+            raise NotImplementedError("schedule has no bin %s (the reference raises KeyError there)" % (key,))
+        q = agent.schedule[key]
+        if int(q) != q or not (0 <= int(q) < 2 ** 31):
+            raise NotImplementedError("schedule quantity %r" % (q,))
+        out.append(int(q))
+    return out
 
 
 def _type_row(agent, klass):
@@ -94,6 +127,15 @@ def _type_row(agent, klass):
                        exec_end_time=_ns(agent.end_time), exec_lookback=_ns(agent.look_back_period),
                        exec_quantity=float(agent.quantity), exec_is_buy=1 if agent.direction == "BUY" else 0,
                        exec_trade=1)
+    if klass == _abi.SCHEDULE_EXEC:
+        h0, step, n = _regular_horizon(agent)
+        # getWakeFrequency needs the first horizon point even for a non-trading agent; the rest is only read when trading
+        row.update(exec_start_time=h0)
+        if g("trade", False):
+            if float(agent.quantity) != int(agent.quantity):
+                raise NotImplementedError("non-integral execution quantity")
+            row.update(wake_up_freq=step, exec_end_time=h0 + (n - 1) * step, exec_quantity=float(agent.quantity),
+                       exec_is_buy=1 if agent.direction == "BUY" else 0, exec_trade=1)
     if klass == _abi.ADAPTIVE_MM:
         if g("subscribe", False):
             raise NotImplementedError("AdaptiveMarketMakerAgent(subscribe=True) is not supported")
@@ -184,6 +226,9 @@ def lower_instance(agents, startTime, stopTime, defaultComputationDelay=1, defau
                 raise ValueError("ZI theta must have 2*q_max entries")
             agent_theta[i] = len(theta)
             theta.extend(th)
+        if k == _abi.SCHEDULE_EXEC:
+            agent_theta[i] = len(theta)
+            theta.extend(_schedule_rows(a))
         mt_key[i], mt_pos[i], mt_hg[i], mt_g[i] = _mt_state(a.random_state)
         spec.agent_names.append(getattr(a, "name", str(i)))
         spec.agent_type_names.append(getattr(a, "type", ""))

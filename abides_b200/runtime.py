@@ -85,6 +85,12 @@ def write_back(kernel, out, inst):
         a.marked_to_market = int(rec["marked_to_market"])
         fv = float(rec["final_valuation"])
         a.final_valuation = None if np.isnan(fv) else fv
+        if hasattr(a, "execution_time_horizon"):              # TWAP / VWAP: the slot carries the arrival mid price
+            a.arrival_price, a.final_valuation = a.final_valuation, None
+            executed = abs(int(rec["holdings"]))
+            a.rem_quantity = a.quantity - executed
+            a.average_transaction_price = (round(abs(int(rec["cash"]) - a.starting_cash) / executed, 2)
+                                           if executed else None)
         gain = a.marked_to_market - a.starting_cash
         kernel.meanResultByAgentType[a.type] = kernel.meanResultByAgentType.get(a.type, 0) + gain
         kernel.agentCountByType[a.type] = kernel.agentCountByType.get(a.type, 0) + 1
@@ -110,8 +116,19 @@ def summary_log_rows(kernel):
         row(a, 'FINAL_CASH_POSITION', a.holdings['CASH'])
         row(a, 'ENDING_CASH', a.marked_to_market)
         if a.final_valuation is not None:
-            fv = a.final_valuation
-            row(a, 'FINAL_VALUATION', int(fv) if float(fv).is_integer() else fv)
+            # ZI / HBL report an integer surplus, Value / Noise agents a ratio to the starting cash
+            zi = any(k.__name__ == "ZeroIntelligenceAgent" for k in type(a).__mro__)
+            row(a, 'FINAL_VALUATION', int(a.final_valuation) if zi else a.final_valuation)
+        if hasattr(a, "execution_time_horizon") and a.trade:  # ExecutionAgent.kernelStopping (:32-42)
+            avg, mid = a.average_transaction_price, a.arrival_price
+            if avg is None or mid is None:
+                raise RuntimeError("the reference raises in ExecutionAgent.kernelStopping: no fill or no arrival price")
+            row(a, 'DIRECTION', a.direction)
+            row(a, 'TOTAL_QTY', a.quantity)
+            row(a, 'REM_QTY', a.rem_quantity)
+            row(a, 'ARRIVAL_MID', mid)
+            row(a, 'AVG_TXN_PRICE', avg)
+            row(a, 'SLIPPAGE', avg - mid if a.direction == 'BUY' else mid - avg)
     return rows
 
 

@@ -47,7 +47,8 @@ enum abides_agent_class {
   ABIDES_ADAPTIVE_MM = 5,   /* agent/market_makers/AdaptiveMarketMakerAgent.py */
   ABIDES_POV_EXEC = 6,      /* agent/execution/POVExecutionAgent.py */
   ABIDES_MARKET_MAKER = 7,  /* agent/market_makers/MarketMakerAgent.py (polling mode, subscribe=False) */
-  ABIDES_HBL = 8            /* agent/HeuristicBeliefLearningAgent.py (a ZeroIntelligenceAgent subclass) */
+  ABIDES_HBL = 8,           /* agent/HeuristicBeliefLearningAgent.py (a ZeroIntelligenceAgent subclass) */
+  ABIDES_SCHEDULE_EXEC = 9  /* agent/execution/ExecutionAgent.py with a schedule: TWAPExecutionAgent.py, VWAPExecutionAgent.py */
 };
 
 enum abides_latency_kind {
@@ -83,6 +84,10 @@ typedef struct abides_agent_type {
   double  exec_quantity;      /* total quantity to execute */
   int32_t exec_is_buy;        /* direction == "BUY" */
   int32_t exec_trade;         /* trade flag: 0 = heartbeat only */
+  /* TWAP / VWAP ExecutionAgent (agent/execution/ExecutionAgent.py:10-30): execution_time_horizon is the regular
+   * grid exec_start_time, + wake_up_freq, ..., exec_end_time; exec_quantity / exec_is_buy / exec_trade as above; the
+   * agent's `theta` rows hold schedule[slot] for the slots that place limit orders (all but the last two);
+   * abides_agent_result.final_valuation returns its arrival mid price (NaN if never set) */
   /* MarketMakerAgent (agent/market_makers/MarketMakerAgent.py:27-50); also uses wake_up_freq */
   int64_t mm_min_size, mm_max_size;
   int32_t mm_num_levels;      /* subscribe_num_levels: depth of its spread query, 2x = price levels quoted per side */

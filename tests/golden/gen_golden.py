@@ -167,6 +167,8 @@ def main():
                 mtm[a.id] = ev["Event"]
             if ev["EventType"] == "FINAL_VALUATION":
                 fval[a.id] = float(ev["Event"])
+            if ev["EventType"] == "ARRIVAL_MID":        # TWAP / VWAP agents: abides_agent_result.final_valuation
+                fval[a.id] = float(ev["Event"])         # carries their arrival mid price (include/abides_b200.h)
     f_log = oracle.f_log[sym]
     f_t = np.array([x["FundamentalTime"].value for x in f_log], np.int64)
     f_v = np.array([x["FundamentalValue"] for x in f_log], np.float64)

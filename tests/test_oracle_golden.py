@@ -37,6 +37,15 @@ CASES = {
     # more of the reference's stock configs that run on the supported classes (compat/config/ re-states each one;
     # the goldens come from the reference's own config files): legacy latency matrix + noise with Noise / Value
     # agents; full-day 5000 noise + 100 value; and the same plus the polling MarketMakerAgent and 25 momentum agents
+    # schedule-driven execution agents (config/execution.py `-e`) in the rmsc03 market at 1/10 scale:
+    # a limit order of schedule[minute] shares at the ask every minute 10:00-10:58, the rest as a MARKET order at
+    # 10:59.  Reference side: tests/golden/refcfg/execution_flags.py
+    "exec_twap_s6": ("execution", ["-t", "ABM", "-d", "20200603", "-s", "6", "-e",
+                                   "--num-noise", "500", "--num-value", "50", "--num-momentum", "10"]),
+    "exec_vwap_s5": ("execution", ["-t", "ABM", "-d", "20200603", "-s", "5", "-e", "--execution-type", "vwap",
+                                   "--num-noise", "500", "--num-value", "50", "--num-momentum", "10"]),
+    # the reference's config/execution.py itself, full size (5129 agents, TWAP agent trading)
+    "execution_s8_e": ("execution", ["-t", "ABM", "-d", "20200603", "-s", "8", "-e"]),
     "value_noise_s7": ("value_noise", ["-s", "7"]),
     "random_fund_value_s7": ("random_fund_value", ["-s", "7", "-t", "ABM", "-d", "20200603"]),
     "random_fund_diverse_s7": ("random_fund_diverse", ["-s", "7", "-t", "ABM", "-d", "20200603"]),
@@ -80,7 +89,8 @@ REF_CONFIG = os.path.join(os.environ.get("ABIDES_REFERENCE", "/root/reference"),
 
 @pytest.mark.skipif(not os.path.isdir(REF_CONFIG), reason="reference tree not present (GPU box)")
 @pytest.mark.parametrize("name", ["zi100_s123456789", "zi1000_s123456789", "rmsc03_s1234_1000", "rmsc03e_s1234_1100",
-                                  "value_noise_s7", "random_fund_value_s7", "random_fund_diverse_s7"])
+                                  "value_noise_s7", "random_fund_value_s7", "random_fund_diverse_s7",
+                                  "execution_s8_e"])
 def test_reference_config_files_run_unmodified_on_the_compat_tree(name):
     """The drop-in claim at the config level: the reference's OWN config file, executed against abides_b200/compat
     (its imports resolve to the descriptor classes), lowers to exactly the inputs the reference run received."""
