@@ -17,15 +17,20 @@ NVCC_FLAGS = [
 ]
 
 
-def build_cuda(force=False, verbose=False, profile=False):
-    """Compile csrc/engine.cu for sm_100a.  profile=True builds the instrumented variant next to it."""
+def build_cuda(force=False, verbose=False, profile=False, cta_warps=None):
+    """Compile csrc/engine.cu for sm_100a.  profile=True builds the instrumented variant next to it;
+    cta_warps=W builds libabides_b200_w<W>.so with W instances per CTA (experiments; the default is 1)."""
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
     deps = srcs + [os.path.join(CSRC, "engine_device.inc")] + [os.path.join(INCLUDE, h) for h in ("abides_b200.h", "abides_dd_math.h", "abides_math_tables.h")]
     out = OUT_PROF if profile else OUT
+    if cta_warps:
+        out = out.replace(".so", "_w%d.so" % cta_warps)
     if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
         return out
     flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + (["-DABIDES_PROFILE"] if profile else [])
+    if cta_warps:
+        flags.append("-DABM_CTA_WARPS=%d" % cta_warps)
     cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-I", INCLUDE, "-o", out] + srcs
     print(" ".join(cmd), file=sys.stderr)
     subprocess.check_call(cmd)
@@ -33,4 +38,6 @@ def build_cuda(force=False, verbose=False, profile=False):
 
 
 if __name__ == "__main__":
-    build_cuda(force=True, verbose="-v" in sys.argv, profile="--profile" in sys.argv)
+    w = [a for a in sys.argv if a.startswith("--cta-warps=")]
+    build_cuda(force=True, verbose="-v" in sys.argv, profile="--profile" in sys.argv,
+               cta_warps=int(w[0].split("=")[1]) if w else None)

@@ -217,7 +217,16 @@ struct Run {                            // per-launch context, shared memory, no
   unsigned long long prof[N_PROF];
 };
 struct __align__(128) Smem { InstShared st; Run run; };
+// ABM_CTA_WARPS instances share one CTA (warp y = instance blockIdx.x * ABM_CTA_WARPS + y) and meet at a barrier before
+// every event, so that the warps of an SM walk the same code at about the same time and share instruction-cache lines
+#ifndef ABM_CTA_WARPS
+#define ABM_CTA_WARPS 1
+#endif
+#if ABM_CTA_WARPS > 1
+#define SM (reinterpret_cast<Smem*>(smem_raw + threadIdx.y * (unsigned)sizeof(Smem)))
+#else
 #define SM (reinterpret_cast<Smem*>(smem_raw))
+#endif
 #define ST (SM->st)
 #define HOT (SM->st.hot)
 #define RUN (SM->run)
@@ -560,10 +569,10 @@ int abides_create(int device, abides_handle** out) {
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CK(cudaEventCreate(&h->ev0));
   CK(cudaEventCreate(&h->ev1));
-  CK(cudaFuncSetAttribute(v_full::sim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
-  CK(cudaFuncSetAttribute(v_zi_legacy::sim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
-  CK(cudaFuncSetAttribute(v_zi_cubic::sim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
-  CK(cudaFuncSetAttribute(v_rmsc::sim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+  CK(cudaFuncSetAttribute(v_full::sim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ABM_CTA_WARPS * sizeof(Smem))));
+  CK(cudaFuncSetAttribute(v_zi_legacy::sim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ABM_CTA_WARPS * sizeof(Smem))));
+  CK(cudaFuncSetAttribute(v_zi_cubic::sim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ABM_CTA_WARPS * sizeof(Smem))));
+  CK(cudaFuncSetAttribute(v_rmsc::sim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ABM_CTA_WARPS * sizeof(Smem))));
   *out = h;
   return 0;
 }
@@ -750,10 +759,10 @@ int abides_run(abides_handle* h, int64_t until_time) {
   CK(cudaEventRecord(h->ev0, h->stream));
   CK(cudaMemcpyToSymbolAsync(c_db, &h->db, sizeof(DevBatch), 0, cudaMemcpyHostToDevice, h->stream));
   switch (h->variant) {
-    case VAR_ZI_LEGACY: v_zi_legacy::sim_kernel<<<h->n_instances, 32, sizeof(Smem), h->stream>>>((long long)until_time); break;
-    case VAR_ZI_CUBIC: v_zi_cubic::sim_kernel<<<h->n_instances, 32, sizeof(Smem), h->stream>>>((long long)until_time); break;
-    case VAR_RMSC: v_rmsc::sim_kernel<<<h->n_instances, 32, sizeof(Smem), h->stream>>>((long long)until_time); break;
-    default: v_full::sim_kernel<<<h->n_instances, 32, sizeof(Smem), h->stream>>>((long long)until_time); break;
+    case VAR_ZI_LEGACY: v_zi_legacy::sim_kernel<<<(h->n_instances + ABM_CTA_WARPS - 1) / ABM_CTA_WARPS, dim3(32, ABM_CTA_WARPS), ABM_CTA_WARPS * sizeof(Smem), h->stream>>>((long long)until_time); break;
+    case VAR_ZI_CUBIC: v_zi_cubic::sim_kernel<<<(h->n_instances + ABM_CTA_WARPS - 1) / ABM_CTA_WARPS, dim3(32, ABM_CTA_WARPS), ABM_CTA_WARPS * sizeof(Smem), h->stream>>>((long long)until_time); break;
+    case VAR_RMSC: v_rmsc::sim_kernel<<<(h->n_instances + ABM_CTA_WARPS - 1) / ABM_CTA_WARPS, dim3(32, ABM_CTA_WARPS), ABM_CTA_WARPS * sizeof(Smem), h->stream>>>((long long)until_time); break;
+    default: v_full::sim_kernel<<<(h->n_instances + ABM_CTA_WARPS - 1) / ABM_CTA_WARPS, dim3(32, ABM_CTA_WARPS), ABM_CTA_WARPS * sizeof(Smem), h->stream>>>((long long)until_time); break;
   }
   CK(cudaGetLastError());
   CK(cudaEventRecord(h->ev1, h->stream));
