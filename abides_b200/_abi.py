@@ -11,7 +11,7 @@ EXTRA_STREAMS = 4
 STREAM_ORACLE, STREAM_KERNEL, STREAM_LATENCY, STREAM_GLOBAL = 0, 1, 2, 3
 
 # enum abides_agent_class
-EXCHANGE, ZI, VALUE, NOISE, MOMENTUM, ADAPTIVE_MM, POV_EXEC, MARKET_MAKER, HBL, SCHEDULE_EXEC = range(10)
+EXCHANGE, ZI, VALUE, NOISE, MOMENTUM, ADAPTIVE_MM, POV_EXEC, MARKET_MAKER, HBL, SCHEDULE_EXEC, SUBSCRIPTION = range(11)
 # enum abides_latency_kind
 LAT_DETERMINISTIC, LAT_CUBIC, LAT_LEGACY_NOISE = range(3)
 # enum abides_rng_mode
@@ -22,7 +22,9 @@ MSG_NAMES = {
     5: "QUERY_ORDER_STREAM", 6: "QUERY_TRANSACTED_VOLUME", 7: "LIMIT_ORDER", 8: "MARKET_ORDER",
     9: "CANCEL_ORDER", 10: "MODIFY_ORDER", 11: "ORDER_ACCEPTED", 12: "ORDER_EXECUTED",
     13: "ORDER_CANCELLED", 14: "ORDER_MODIFIED", 15: "MKT_CLOSED",
+    16: "MARKET_DATA_SUBSCRIPTION_REQUEST", 17: "MARKET_DATA_SUBSCRIPTION_CANCELLATION", 18: "MARKET_DATA",
 }
+MD_MAX_LEVELS = 8
 MSG_CODES = {v: k for k, v in MSG_NAMES.items()}
 TRACE_FUNDAMENTAL = 64          # trace code of an oracle step (include/abides_b200.h: abides_trace_rec)
 MSG_REPLY = 32
@@ -45,6 +47,7 @@ class AgentType(C.Structure):
         ("exec_start_time", C.c_int64), ("exec_end_time", C.c_int64), ("exec_lookback", C.c_int64),
         ("exec_quantity", C.c_double), ("exec_is_buy", C.c_int32), ("exec_trade", C.c_int32),
         ("mm_min_size", C.c_int64), ("mm_max_size", C.c_int64), ("mm_num_levels", C.c_int32), ("hbl_L", C.c_int32),
+        ("subscribe", C.c_int32), ("sub_levels", C.c_int32), ("subscribe_freq", C.c_double),
     ]
 
 

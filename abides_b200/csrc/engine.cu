@@ -88,11 +88,12 @@ struct __align__(16) RngState { int pos; unsigned flags; double gauss; };   // f
 
 enum : unsigned {
   F_HAS_OPEN = 1u, F_HAS_CLOSE = 2u, F_MKT_CLOSED = 4u, F_HAS_LAST_TRADE = 8u, F_HAS_DAILY_CLOSE = 16u,
-  F_KNOWN_BOOK = 32u, F_TRADING = 64u, F_HAS_PREV_WAKE = 128u,
+  F_KNOWN_BOOK = 32u, F_TRADING = 64u, F_HAS_PREV_WAKE = 128u, F_SUB_REQUESTED = 256u,
   F_MM_AWAIT_SPREAD = 512u, F_MM_AWAIT_TV = 1024u, F_HAS_LAST_MID = 2048u, F_HAS_AVG20 = 4096u,
   F_HAS_AVG50 = 8192u, F_HAS_TV = 16384u, F_STATE_SHIFT = 16u, F_STATE_MASK = 7u << 16
 };
-enum { ST_AWAITING_WAKEUP = 0, ST_INACTIVE = 1, ST_AWAITING_SPREAD = 2, ST_ACTIVE = 3, ST_AWAITING_STREAM = 4 };
+enum { ST_AWAITING_WAKEUP = 0, ST_INACTIVE = 1, ST_AWAITING_SPREAD = 2, ST_ACTIVE = 3, ST_AWAITING_STREAM = 4,
+       ST_AWAITING_MARKET_DATA = 5 };
 enum { BID = 0, ASK = 1 };              // book side index; a BUY order rests on BID and matches ASK
 
 struct __align__(128) AgentRec {        // 128 bytes: one coalesced transaction
@@ -121,6 +122,13 @@ struct __align__(128) AgentRec {        // 128 bytes: one coalesced transaction
 };
 static_assert(sizeof(AgentRec) == 128, "AgentRec must be 128 bytes");
 
+// market-data subscriptions (ExchangeAgent.subscription_dict :286-297, in insertion order) and the bodies of the
+// MARKET_DATA messages that carry more than one level (a ring: the message holds the sequence number)
+constexpr int MAX_SUBS = 256;
+constexpr int MD_RING = 4096;
+struct SubRec { int agent; int levels; double freq; long long last; };
+struct MdSnap { unsigned seq; int nb, na, pad; int bp[ABIDES_MD_MAX_LEVELS]; int ap[ABIDES_MD_MAX_LEVELS]; };
+
 struct Hot {
   long long now, ttl, delivered, n_fills, volume;
   long long exch_busy, exch_cd, exch_cur_time, additional_delay;
@@ -145,6 +153,8 @@ struct Hot {
   int find_idx;                         // result of side_find
   int hist_B, tv_prev_len;              // open history bucket; OrderBook._transacted_volume previous length
   long long log_len, log_mark, unr_len; // transaction rows logged / scanned by the last query / unrolled rows
+  long long book_update_ts;             // OrderBook.last_update_ts (LLONG_MIN: None)
+  int n_subs; unsigned md_seq;          // subscribers registered; MARKET_DATA bodies written to the ring
   RngState rs[ABIDES_EXTRA_STREAMS];
 };
 
@@ -184,6 +194,8 @@ struct DevBatch {
   EvKey* b_keys; EvPay* b_pay;          // [n_instances][b_cap]
   EvKey* p_keys; EvPay* p_pay;          // [n_instances][2][deep_cap] book pools
   int* p_free;                          // [n_instances][2][deep_cap] free-slot stacks of the pools
+  SubRec* subs;                         // [n_instances][MAX_SUBS], or NULL (no subscribing agent in the batch)
+  MdSnap* md;                           // [n_instances][MD_RING], or NULL
   OLogRow* olog;                        // [n_instances][OLOG_CAP] order log, or NULL (no HBL agent in the batch)
   int* hbl_cnt;                         // [n_instances][4][HBL_RANGE_CAP] belief-table scratch, or NULL
   OpenOrd* arena;
@@ -205,6 +217,7 @@ struct Run {                            // per-launch context, shared memory, no
   OpenOrd* arena; TxnRow* txn_log; TxnRow* unrolled;
   int* pfree[2];
   OLogRow* olog; int* hbl_cnt;
+  SubRec* subs; MdSnap* md;
   abides_trace_rec* trace;
   unsigned* mt0;                        // MT state of this instance's stream 0 (agent 0)
   const double* lat_to; const double* lat_from;   // this instance's rows
@@ -348,6 +361,7 @@ __global__ void __launch_bounds__(32) init_kernel() {
     h.near_free = 0xffffffffu;
     h.l_total[L_B] = n; h.l_live[L_B] = n; h.queue_peak = n;
     h.last_trade = (int)cfg->r_bar; h.has_last_trade = 1;
+    h.book_update_ts = LLONG_MIN;
     for (int s = 0; s < ABIDES_EXTRA_STREAMS; s++) {
       long long stream = aoff + (long long)ABIDES_EXTRA_STREAMS * inst + n + s;
       if (db.rng_mode == ABIDES_RNG_MT19937) {
@@ -375,7 +389,7 @@ __global__ void init_types_kernel() {
 namespace v_full {                      // everything (tracing, Philox, every agent class, book replay)
 #define ABM_V_TRACE 1
 #define ABM_V_PHILOX 1
-#define ABM_V_CLASSES 0x3ff
+#define ABM_V_CLASSES 0x7ff
 #define ABM_V_LAT (-1)
 #define ABM_V_OLOG 1
 #define ABM_V_TVLOG 1
@@ -467,11 +481,11 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
 namespace {
 struct ShapeSig {
   int ni = 0, n_types = 0, rng_mode = -1, trace_cap = -1, max_agents = 0, n_mom = 0;
-  bool has_hbl = false, needs_tv = false;
+  bool has_hbl = false, needs_tv = false, has_md = false;
   long long na = -1, n_theta = -1;
   bool operator==(const ShapeSig& o) const {
     return ni == o.ni && n_types == o.n_types && rng_mode == o.rng_mode && trace_cap == o.trace_cap &&
-           max_agents == o.max_agents && n_mom == o.n_mom && na == o.na && n_theta == o.n_theta && has_hbl == o.has_hbl && needs_tv == o.needs_tv;
+           max_agents == o.max_agents && n_mom == o.n_mom && na == o.na && n_theta == o.n_theta && has_hbl == o.has_hbl && needs_tv == o.needs_tv && has_md == o.has_md;
   }
 };
 }  // namespace
@@ -604,6 +618,7 @@ int abides_load(abides_handle* h, const abides_batch* b) {
   std::vector<int> mom_index((size_t)na, -1);
   int n_mom = 0, n_hbl = 0;
   unsigned class_mask = 0, lat_mask = 0;
+  long long n_sub = 0;
   for (int i = 0; i < ni; i++) {
     const abides_instance_cfg& ic = b->instances[i];
     if (ic.latency_kind < ABIDES_LAT_DETERMINISTIC || ic.latency_kind > ABIDES_LAT_LEGACY_NOISE)
@@ -618,9 +633,16 @@ int abides_load(abides_handle* h, const abides_batch* b) {
       if (t < 0 || t >= b->n_types) return fail(ABIDES_EINVAL, "abides_load: agent_type out of range");
       int k = b->types[t].klass;
       if ((a == 0) != (k == ABIDES_EXCHANGE)) return fail(ABIDES_EINVAL, "abides_load: agent 0 (and only agent 0) must be the exchange");
-      if (k < 0 || k > ABIDES_SCHEDULE_EXEC) return fail(ABIDES_EINVAL, "abides_load: unknown agent class");
+      if (k < 0 || k > ABIDES_SUBSCRIPTION) return fail(ABIDES_EINVAL, "abides_load: unknown agent class");
       if (k == ABIDES_HBL) { n_hbl++; if (b->types[t].hbl_L < 1) return fail(ABIDES_EINVAL, "abides_load: HBL agent with L < 1"); }
       if (a > 0) class_mask |= 1u << k;
+      if (b->types[t].subscribe) {
+        if (k != ABIDES_MARKET_MAKER && k != ABIDES_MOMENTUM && k != ABIDES_SUBSCRIPTION)
+          return fail(ABIDES_EINVAL, "abides_load: subscribe set on an agent class without a subscription mode");
+        if (b->types[t].sub_levels < 1 || b->types[t].sub_levels > ABIDES_MD_MAX_LEVELS || !(b->types[t].subscribe_freq >= 0))
+          return fail(ABIDES_EINVAL, "abides_load: bad subscription levels / freq");
+        n_sub++;
+      } else if (k == ABIDES_SUBSCRIPTION) return fail(ABIDES_EINVAL, "abides_load: SubscriptionAgent without subscribe");
       if (k == ABIDES_MOMENTUM) mom_index[off + a] = n_mom++;
       if ((k == ABIDES_ZI || k == ABIDES_HBL) && (b->agent_theta[off + a] < 0 || !b->theta)) return fail(ABIDES_EINVAL, "abides_load: ZI / HBL agent without theta");
       if (k == ABIDES_SCHEDULE_EXEC && b->types[t].exec_trade) {
@@ -640,6 +662,7 @@ int abides_load(abides_handle* h, const abides_batch* b) {
   sig.max_agents = max_agents; sig.n_mom = n_mom; sig.na = na; sig.n_theta = b->n_theta_total; sig.has_hbl = n_hbl > 0;
   const bool needs_tv = (class_mask & ((1u << ABIDES_ADAPTIVE_MM) | (1u << ABIDES_POV_EXEC))) != 0;
   sig.needs_tv = needs_tv;
+  sig.has_md = n_sub > 0;
   DevBatch& d = h->db;
   int rc;
   size_t ns = (size_t)na + (size_t)ABIDES_EXTRA_STREAMS * ni;
@@ -689,6 +712,10 @@ int abides_load(abides_handle* h, const abides_batch* b) {
       if ((rc = dev_alloc(h, &d.olog, (size_t)ni * OLOG_CAP))) return rc;
       if ((rc = dev_alloc(h, &d.hbl_cnt, (size_t)ni * 4 * HBL_RANGE_CAP))) return rc;
     }
+    if (n_sub > 0) {
+      if ((rc = dev_alloc(h, &d.subs, (size_t)ni * MAX_SUBS))) return rc;
+      if ((rc = dev_alloc(h, &d.md, (size_t)ni * MD_RING))) return rc;
+    }
     if (needs_tv) {                           // 2 MB per instance: only where some agent queries transacted volume
       if ((rc = dev_alloc(h, &d.txn_log, (size_t)ni * TXN_CAP))) return rc;
       if ((rc = dev_alloc(h, &d.unrolled, (size_t)ni * UNR_CAP))) return rc;
@@ -708,7 +735,7 @@ int abides_load(abides_handle* h, const abides_batch* b) {
                           (1u << ABIDES_POV_EXEC);
     if ((class_mask & ~zi) == 0 && lat_mask == (1u << ABIDES_LAT_LEGACY_NOISE)) h->variant = VAR_ZI_LEGACY;
     else if ((class_mask & ~zi) == 0 && lat_mask == (1u << ABIDES_LAT_CUBIC)) h->variant = VAR_ZI_CUBIC;
-    else if ((class_mask & ~rmsc) == 0 && lat_mask == (1u << ABIDES_LAT_DETERMINISTIC)) h->variant = VAR_RMSC;
+    else if ((class_mask & ~rmsc) == 0 && lat_mask == (1u << ABIDES_LAT_DETERMINISTIC) && n_sub == 0) h->variant = VAR_RMSC;
   }
   if ((rc = h2d(h, d.cfg, b->instances, (size_t)ni))) return rc;
   if ((rc = h2d(h, d.types, b->types, (size_t)b->n_types))) return rc;

@@ -23,6 +23,7 @@ _CLASS_BY_NAME = {
     "HeuristicBeliefLearningAgent": _abi.HBL,
     "TWAPExecutionAgent": _abi.SCHEDULE_EXEC,
     "VWAPExecutionAgent": _abi.SCHEDULE_EXEC,
+    "SubscriptionAgent": _abi.SUBSCRIPTION,
 }
 
 
@@ -91,6 +92,18 @@ def _schedule_rows(agent):
     return out
 
 
+_MM_LEVELS_QUOTE_DICT = {1: [1, 0, 0, 0, 0], 2: [.5, .5, 0, 0, 0], 3: [.34, .33, .33, 0, 0], 4: [.25, .25, .25, .25, 0],
+                         5: [.20, .20, .20, .20, .20]}
+
+
+def _subscription(levels, freq):
+    if int(levels) != levels or not (1 <= int(levels) <= _abi.MD_MAX_LEVELS):
+        raise NotImplementedError("market-data subscription with %r levels (1..%d supported)" % (levels, _abi.MD_MAX_LEVELS))
+    if not (float(freq) >= 0):
+        raise ValueError("subscription freq %r" % (freq,))
+    return dict(subscribe=1, sub_levels=int(levels), subscribe_freq=float(freq))
+
+
 def _type_row(agent, klass):
     g = lambda n, d=0: getattr(agent, n, d)
     row = dict(klass=klass, q_max=0, starting_cash=int(g("starting_cash", 0)),
@@ -100,7 +113,7 @@ def _type_row(agent, klass):
                backstop_quantity=-1, window_size=-1, anchor=0,
                log_orders=1 if g("log_orders", False) else 0, percent_aggr=0.0, depth_spread=0,
                exec_start_time=0, exec_end_time=0, exec_lookback=0, exec_quantity=0.0, exec_is_buy=0, exec_trade=0,
-               mm_min_size=0, mm_max_size=0, mm_num_levels=0, hbl_L=0)
+               mm_min_size=0, mm_max_size=0, mm_num_levels=0, hbl_L=0, subscribe=0, sub_levels=0, subscribe_freq=0.0)
     if klass in (_abi.ZI, _abi.VALUE, _abi.HBL):
         row.update(sigma_n=float(agent.sigma_n), r_bar=float(agent.r_bar), kappa=float(agent.kappa),
                    sigma_s=float(agent.sigma_s), lambda_a=float(agent.lambda_a))
@@ -111,15 +124,19 @@ def _type_row(agent, klass):
         row.update(hbl_L=int(agent.L))
     if klass == _abi.MARKET_MAKER:
         if g("subscribe", False):
-            raise NotImplementedError("MarketMakerAgent(subscribe=True) is not supported")
+            row.update(_subscription(agent.subscribe_num_levels, agent.subscribe_freq))
+            if getattr(agent, "levels_quote_dict", None) not in (None, _MM_LEVELS_QUOTE_DICT):
+                raise NotImplementedError("MarketMakerAgent with a non-default levels_quote_dict")
         row.update(wake_up_freq=_ns(agent.wake_up_freq), mm_min_size=int(agent.min_size),
                    mm_max_size=int(agent.max_size), mm_num_levels=int(agent.subscribe_num_levels))
     if klass == _abi.VALUE:
         row.update(percent_aggr=float(agent.percent_aggr), depth_spread=int(agent.depth_spread))
     if klass == _abi.MOMENTUM:
         if g("subscribe", False):
-            raise NotImplementedError("MomentumAgent(subscribe=True) is not supported")
+            row.update(_subscription(1, 10e9))      # MomentumAgent.wakeup (:37): levels=1, freq=10e9, hard-coded
         row.update(wake_up_freq=_ns(agent.wake_up_freq))
+    if klass == _abi.SUBSCRIPTION:
+        row.update(_subscription(agent.levels, agent.freq), wake_up_freq=10 ** 9)   # getWakeFrequency: '1s' 
     if klass == _abi.POV_EXEC:
         row.update(wake_up_freq=_ns(agent.freq))
         if g("trade", False):                      # trade=False is a pure heartbeat: nothing else is read

@@ -48,7 +48,8 @@ enum abides_agent_class {
   ABIDES_POV_EXEC = 6,      /* agent/execution/POVExecutionAgent.py */
   ABIDES_MARKET_MAKER = 7,  /* agent/market_makers/MarketMakerAgent.py (polling mode, subscribe=False) */
   ABIDES_HBL = 8,           /* agent/HeuristicBeliefLearningAgent.py (a ZeroIntelligenceAgent subclass) */
-  ABIDES_SCHEDULE_EXEC = 9  /* agent/execution/ExecutionAgent.py with a schedule: TWAPExecutionAgent.py, VWAPExecutionAgent.py */
+  ABIDES_SCHEDULE_EXEC = 9, /* agent/execution/ExecutionAgent.py with a schedule: TWAPExecutionAgent.py, VWAPExecutionAgent.py */
+  ABIDES_SUBSCRIPTION = 10  /* agent/examples/SubscriptionAgent.py: subscribes to market data, never trades */
 };
 
 enum abides_latency_kind {
@@ -92,7 +93,14 @@ typedef struct abides_agent_type {
   int64_t mm_min_size, mm_max_size;
   int32_t mm_num_levels;      /* subscribe_num_levels: depth of its spread query, 2x = price levels quoted per side */
   int32_t hbl_L;              /* HeuristicBeliefLearningAgent: order-stream buckets it looks at */
+  /* market-data subscriptions (TradingAgent.requestDataSubscription :170-173, ExchangeAgent.py:285-317):
+   * MarketMakerAgent / MomentumAgent with subscribe=True and the SubscriptionAgent ask once, at their first wake,
+   * for `sub_levels` book levels per side (<= ABIDES_MD_MAX_LEVELS) no more often than every `subscribe_freq` ns */
+  int32_t subscribe;
+  int32_t sub_levels;
+  double  subscribe_freq;
 } abides_agent_type;
+#define ABIDES_MD_MAX_LEVELS 8
 
 /* One simulation instance (one reference process). */
 typedef struct abides_instance_cfg {
@@ -192,6 +200,8 @@ enum abides_msg {
   ABIDES_MSG_ORDER_ACCEPTED = 11, ABIDES_MSG_ORDER_EXECUTED = 12,
   ABIDES_MSG_ORDER_CANCELLED = 13, ABIDES_MSG_ORDER_MODIFIED = 14,
   ABIDES_MSG_MKT_CLOSED = 15,
+  ABIDES_MSG_MARKET_DATA_SUBSCRIPTION_REQUEST = 16, ABIDES_MSG_MARKET_DATA_SUBSCRIPTION_CANCELLATION = 17,
+  ABIDES_MSG_MARKET_DATA = 18,
   ABIDES_MSG_REPLY = 32          /* OR-ed in for exchange -> agent echoes of a query type */
 };
 

@@ -14,7 +14,7 @@ What is recorded, per run:
     payload (see include/abides_b200.h: abides_trace_rec) -- full when --trace, plus its sha256;
   * ttl_messages (Kernel.py:204), per-agent final CASH / holdings / marked-to-market /
     FINAL_VALUATION, "Mean ending value by agent type", the oracle's f_log.
-Compat shims: pandas.io.json.json_normalize alias; post-run order-book archival no-op.
+Compat shims: pandas.io.json.json_normalize alias; Timedelta.delta (= .value, removed in pandas 2); post-run order-book archival no-op.
 """
 import argparse
 import hashlib
@@ -49,6 +49,7 @@ def main():
     import pandas as pd
     import pandas.io.json
     pandas.io.json.json_normalize = pd.json_normalize
+    pd.Timedelta.delta = property(lambda self: self.value)     # removed in pandas 2 (ExchangeAgent.py:309)
 
     from abides_b200 import lowering, _abi
 
@@ -73,6 +74,8 @@ def main():
                     p[3] = 1 if o.is_buy_order else -1
             elif code_name == "QUERY_SPREAD":
                 p[1] = body["depth"]
+            elif code_name == "MARKET_DATA_SUBSCRIPTION_REQUEST":
+                p[1] = body["levels"]
             return p
         if code_name in ("ORDER_ACCEPTED", "ORDER_EXECUTED", "ORDER_CANCELLED"):
             return [o.order_id, o.limit_price, o.quantity if o.is_buy_order else -o.quantity,
@@ -80,7 +83,7 @@ def main():
         if code_name == "ORDER_MODIFIED":
             o = body["new_order"]
             return [o.order_id, o.limit_price, o.quantity if o.is_buy_order else -o.quantity, -1]
-        if code_name == "QUERY_SPREAD":
+        if code_name in ("QUERY_SPREAD", "MARKET_DATA"):
             b, a = body["bids"], body["asks"]
             return [b[0][0] if b else -1, b[0][1] if b else 0, a[0][0] if a else -1, a[0][1] if a else 0]
         if code_name in ("WHEN_MKT_OPEN", "WHEN_MKT_CLOSE"):
@@ -199,7 +202,7 @@ def spec_digest(spec):
     h.update(json.dumps(spec.cfg, sort_keys=True).encode())
     # columns added after the first fixtures were frozen (exec_*: POVExecutionAgent trade=True; mm_*, hbl_L: MarketMaker
     # / HBL agents) only enter the digest of the rows that use them, so the older fixtures keep their spec_sha256
-    late = ("exec_", "mm_", "hbl_")
+    late = ("exec_", "mm_", "hbl_", "sub")
     types = [{k: v for k, v in row.items()
               if not (k.startswith(late) and not (row.get("exec_trade") if k.startswith("exec_") else v))}
              for row in spec.types]

@@ -5,7 +5,7 @@ in a scratch directory, and store what its summary_log.bz2 and fundamental_<symb
 
     python tests/golden/gen_log_golden.py --name zi100_s123456789 -- -c sparse_zi_100 -s 123456789
 
-Only runs in the build container.  Compat shim: pandas.io.json.json_normalize alias.
+Only runs in the build container.  Compat shims: pandas.io.json.json_normalize alias, Timedelta.delta (= .value).
 """
 import argparse
 import contextlib
@@ -40,6 +40,7 @@ def main():
     import pandas as pd
     import pandas.io.json
     pandas.io.json.json_normalize = pd.json_normalize
+    pd.Timedelta.delta = property(lambda self: self.value)     # removed in pandas 2 (ExchangeAgent.py:309)
 
     work = tempfile.mkdtemp(prefix="abides_loggolden_")
     os.chdir(work)

@@ -44,6 +44,11 @@ CASES = {
                                    "--num-noise", "500", "--num-value", "50", "--num-momentum", "10"]),
     "exec_vwap_s5": ("execution", ["-t", "ABM", "-d", "20200603", "-s", "5", "-e", "--execution-type", "vwap",
                                    "--num-noise", "500", "--num-value", "50", "--num-momentum", "10"]),
+    # SURVEY 8(f)3, market-data subscriptions: config/rmsc02.py (the rmsc01 population with the market maker and the
+    # momentum agents on MARKET_DATA subscriptions) over a full day, and 09:30-11:00 with the reference's example
+    # SubscriptionAgent added (reference side: tests/golden/refcfg/rmsc02_flags.py)
+    "rmsc02_s22": ("rmsc02", ["-s", "22"]),
+    "rmsc02sub_s21_1100": ("rmsc02", ["-s", "21", "--end-time", "11:00:00", "--subscription-agent"]),
     # the reference's config/execution.py itself, full size (5129 agents, TWAP agent trading)
     "execution_s8_e": ("execution", ["-t", "ABM", "-d", "20200603", "-s", "8", "-e"]),
     "value_noise_s7": ("value_noise", ["-s", "7"]),
@@ -90,7 +95,7 @@ REF_CONFIG = os.path.join(os.environ.get("ABIDES_REFERENCE", "/root/reference"),
 @pytest.mark.skipif(not os.path.isdir(REF_CONFIG), reason="reference tree not present (GPU box)")
 @pytest.mark.parametrize("name", ["zi100_s123456789", "zi1000_s123456789", "rmsc03_s1234_1000", "rmsc03e_s1234_1100",
                                   "value_noise_s7", "random_fund_value_s7", "random_fund_diverse_s7",
-                                  "execution_s8_e"])
+                                  "execution_s8_e", "rmsc02_s22"])
 def test_reference_config_files_run_unmodified_on_the_compat_tree(name):
     """The drop-in claim at the config level: the reference's OWN config file, executed against abides_b200/compat
     (its imports resolve to the descriptor classes), lowers to exactly the inputs the reference run received."""
