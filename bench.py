@@ -38,6 +38,10 @@ WORKLOADS = {
                           "--num-value", "25", "--num-momentum", "24"]),
     # the reference's literal config/rmsc01.py population: 1 MarketMaker + 50 ZI + 25 HBL + 24 momentum
     "rmsc01_literal": ("rmsc01", []),
+    # config/rmsc02.py: the same population with the market maker and momentum agents on market-data subscriptions
+    "rmsc02": ("rmsc02", []),
+    # config/execution.py -e: the rmsc03 market 09:30-11:30 with a TWAP agent buying 1.2 M shares
+    "execution": ("execution", ["-t", "ABM", "-d", "20200603", "-e"]),
 }
 
 

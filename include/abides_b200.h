@@ -181,7 +181,12 @@ typedef struct abides_trace_rec {
   int64_t time;
   int32_t agent;                          /* recipient */
   int32_t code;                           /* 0 = WAKEUP, else enum abides_msg */
-  int64_t p0, p1, p2, p3;                 /* message payload, see abides_msg */
+  int64_t p0, p1, p2, p3;                 /* message payload, see abides_msg: to the exchange p0 = sender and, for
+                                             orders, id / limit price / signed quantity (CANCEL: side only), for
+                                             QUERY_SPREAD the depth, for a subscription request the levels; to an agent
+                                             order id / price / signed quantity / fill price for ORDER_*, best bid /
+                                             size / best ask / size for QUERY_SPREAD and MARKET_DATA, the value for
+                                             WHEN_MKT_*, QUERY_TRANSACTED_VOLUME and QUERY_LAST_TRADE */
 } abides_trace_rec;
 
 /* Message vocabulary.  Payload words for the trace:

@@ -34,6 +34,8 @@ ap.add_argument('--num-hbl', type=int, default=25)
 ap.add_argument('--num-momentum', type=int, default=24)
 ap.add_argument('--end-time', default='16:00:00')
 ap.add_argument('--subscription-agent', action='store_true')
+ap.add_argument('--mm-subscribe-levels', type=int, default=5)
+ap.add_argument('--mm-subscribe-freq', type=float, default=10e9)
 args, _ = ap.parse_known_args()
 if args.config_help:
     ap.print_help()
@@ -60,7 +62,9 @@ agents = [ExchangeAgent(id=0, name="EXCHANGE_AGENT", type="ExchangeAgent", mkt_o
                         symbols=[sym], log_orders=False, pipeline_delay=0, computation_delay=0, stream_history=10,
                         book_freq=0, random_state=fresh_state(dtype='uint64'))]
 agents.append(MarketMakerAgent(id=1, name="MARKET_MAKER_AGENT_1", type='MarketMakerAgent', symbol=sym,
-                               starting_cash=cash, min_size=500, max_size=1000, subscribe=True, log_orders=False,
+                               starting_cash=cash, min_size=500, max_size=1000, subscribe=True,
+                               subscribe_freq=args.mm_subscribe_freq, subscribe_num_levels=args.mm_subscribe_levels,
+                               log_orders=False,
                                random_state=fresh_state(dtype='uint64')))
 fund = {'r_bar': 1e5, 'kappa': 1.67e-12, 'agent_kappa': 1.67e-15, 'sigma_s': 0, 'fund_vol': 1e-8,
         'megashock_lambda_a': 2.77778e-13, 'megashock_mean': 1e3, 'megashock_var': 5e4,

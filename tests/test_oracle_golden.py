@@ -49,6 +49,9 @@ CASES = {
     # SubscriptionAgent added (reference side: tests/golden/refcfg/rmsc02_flags.py)
     "rmsc02_s22": ("rmsc02", ["-s", "22"]),
     "rmsc02sub_s21_1100": ("rmsc02", ["-s", "21", "--end-time", "11:00:00", "--subscription-agent"]),
+    # the market maker on 8 levels every 0.1 s: books shallower than the subscription, one-tick-past-the-book quotes
+    "rmsc02fast_s23_1100": ("rmsc02", ["-s", "23", "--end-time", "11:00:00", "--mm-subscribe-levels", "8",
+                                       "--mm-subscribe-freq", "1e8"]),
     # the reference's config/execution.py itself, full size (5129 agents, TWAP agent trading)
     "execution_s8_e": ("execution", ["-t", "ABM", "-d", "20200603", "-s", "8", "-e"]),
     "value_noise_s7": ("value_noise", ["-s", "7"]),
