@@ -153,8 +153,10 @@ def main():
     from abides_b200 import _abi, runtime
     rng_mode = _abi.RNG_MT19937 if args.rng == "mt" else _abi.RNG_PHILOX
     cores = host_cores()
-    config = {"workload": "%s x %d seeds per GPU, one market day each (09:30-16:00, kernel 00:00-17:00)"
-                          % (args.workload, args.instances),
+    hours = {"rmsc03_2h": "09:30-11:30, kernel 00:00-11:31", "execution": "09:30-11:30, kernel 00:00-11:31",
+             "sparse_zi_100": "09:30-16:00, kernel 00:00-17:00", "sparse_zi_1000": "09:30-16:00, kernel 00:00-17:00"
+             }.get(args.workload, "09:30-16:00, kernel 00:00-16:01")
+    config = {"workload": "%s x %d seeds per GPU, one market day each (%s)" % (args.workload, args.instances, hours),
               "instances_per_gpu": args.instances, "rng": args.rng,
               "l2": "per-step working set (agent records + RNG state + queues) exceeds the 126 MB L2",
               "seeds": "np.random.RandomState(%d).randint(0, 2**32, n) as config/parallel.py:11" % args.seed}
