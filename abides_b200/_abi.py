@@ -16,6 +16,7 @@ EXCHANGE, ZI, VALUE, NOISE, MOMENTUM, ADAPTIVE_MM, POV_EXEC, MARKET_MAKER, HBL, 
 LAT_DETERMINISTIC, LAT_CUBIC, LAT_LEGACY_NOISE = range(3)
 # enum abides_rng_mode
 RNG_MT19937, RNG_PHILOX = 0, 1
+OK, EINVAL, ENOMEM, ECUDA, ESTATE, EOVERFLOW = 0, -1, -2, -3, -4, -5     # enum abides_error
 
 MSG_NAMES = {
     0: "WAKEUP", 1: "WHEN_MKT_OPEN", 2: "WHEN_MKT_CLOSE", 3: "QUERY_LAST_TRADE", 4: "QUERY_SPREAD",

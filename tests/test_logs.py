@@ -74,3 +74,38 @@ def test_cli_run_writes_reference_logs(tmp_path):
     assert r.returncode == 0, r.stderr[-2000:]
     assert "Simulation ending!" in r.stdout
     _check_files(os.path.join(str(tmp_path), "log", "run"))
+
+
+def _load_parallel():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("abides_parallel", os.path.join(runtime.COMPAT_DIR, "config", "parallel.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def test_sweep_driver_draws_the_reference_seeds():
+    """config/parallel.py:10,:56: np.random.seed(seed) then np.random.randint(0, 2 ** 32, n)."""
+    m = _load_parallel()
+    np.random.seed(11)
+    want = [int(x) for x in np.random.randint(0, 2 ** 32, 5)]
+    assert m.sweep_seeds(11, 5) == want == runtime.parallel_seeds(11, 5)
+
+
+@pytest.mark.gpu
+def test_sweep_driver_runs_one_batch_and_writes_per_seed_logs(tmp_path, monkeypatch, capsys):
+    """`parallel.py --config sparse_zi_100 --num_simulations 3 --seed 123456789` equals three single runs; the first
+    global seed of that stream is not the golden's, so the check is against the single-instance path."""
+    m = _load_parallel()
+    monkeypatch.chdir(tmp_path)
+    out, kernels = m.main(["--config", CONFIG, "--num_simulations", "3", "--seed", "7", "--log_folder", "sw"])
+    seeds = m.sweep_seeds(7, 3)
+    text = capsys.readouterr().out
+    assert text.count("Simulation ending!") == 3
+    for i, s in enumerate(seeds):
+        f = os.path.join(str(tmp_path), "log", "sw_seed_%d" % s, "summary_log.bz2")
+        df = pd.read_pickle(f, compression="bz2")
+        assert len(df) == 400 and list(df.EventType[:1]) == ["STARTING_CASH"]
+        single, (k1,) = runtime.run_config_batch(CONFIG, [["-s", s]])
+        assert single.res["ttl_messages"][0] == out.res["ttl_messages"][i]
+        assert [a.holdings for a in k1.agents[1:]] == [a.holdings for a in kernels[i].agents[1:]]
