@@ -133,6 +133,17 @@ def cpu_baseline(hb, n_sample, threads):
     return msgs, dt
 
 
+def bounded_sample(hb, limit, threads, budget_s=20.0):
+    """How many instances the CPU leg takes: one instance per host thread is timed first, and the sample grows from
+    there only as far as about `budget_s` seconds of wall time allow (the whole batch for the ZI workloads, one
+    round of `threads` instances for rmsc03-sized ones).  Returns (n_sample, messages, seconds) of the probe if the
+    probe already is the sample, else (n_sample, None, None)."""
+    probe = min(limit, threads)
+    m, dt = cpu_baseline(hb, probe, threads)
+    n = min(limit, max(probe, int(budget_s / max(dt, 1e-3)) * probe))
+    return (n, m, dt) if n == probe else (n, None, None)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -164,11 +175,11 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        n_sample = args.cpu_sample or args.instances        # one full batch per step: a few core-seconds per thread
-        seeds = runtime.parallel_seeds(args.seed, n_sample)
+        seeds = runtime.parallel_seeds(args.seed, args.cpu_sample or args.instances)
         hb, build_s = build_batch(args.workload, seeds, _abi.RNG_MT19937)
-        for _ in range(min(args.warmup, 1)):
-            cpu_baseline(hb, min(n_sample, cores), cores)
+        # one batch per step where that is a few seconds of CPU (the ZI workloads), else one instance per thread;
+        # the sizing probe doubles as the warm-up
+        n_sample = args.cpu_sample or bounded_sample(hb, len(seeds), cores)[0]
         msgs = 0
         t = 0.0
         for _ in range(args.steps):
@@ -297,8 +308,12 @@ def main():
                              % ALGO_BYTES_PER_MESSAGE},
     }
     if world == 1:
-        n_sample = args.cpu_sample or args.instances        # the whole batch once (~2-3 s wall, tens of core-seconds)
-        m, dt = cpu_baseline(hb, n_sample, cores)
+        if args.cpu_sample:
+            n_sample, m, dt = args.cpu_sample, None, None
+        else:
+            n_sample, m, dt = bounded_sample(hb, args.instances, cores)    # the whole batch when that takes seconds
+        if m is None:
+            m, dt = cpu_baseline(hb, n_sample, cores)
         line["cpu_sample_ttl_messages_match"] = bool(CPU_TTL == [int(x) for x in res["ttl_messages"][:n_sample]])
         line["cpu_baseline"] = {"value": m / dt, "unit": "messages/s", "cores": cores, "kind": "port",
                                 "sample": "first %d instances of the same batch on %d host threads, %.1f s "
