@@ -28,6 +28,10 @@ sys.path.insert(0, ROOT)
 CPU_TTL = []
 ALGO_BYTES_PER_MESSAGE = 160          # pop 16 + payload 16 + agent state r/w 80 + emit 32 + book 16
 BASELINE_PUBLISHED = {"sparse_zi_1000": 3100.4, "sparse_zi_100": 3585.4}   # BASELINE.md section 1 (1 core i7)
+REFERENCE_NOTE = ("the reference arm / cpu_baseline is the C restatement of the reference (oracle/abides_oracle.c) on all "
+                  "host threads; the Python reference itself cannot travel to the GPU box and runs 14.7 k (sparse_zi_1000) "
+                  "and 4-5 k (rmsc03) messages/s per core in the build container (BASELINE.md section 2), i.e. the C port "
+                  "is ~400x the reference per core")
 WORKLOADS = {
     "sparse_zi_100": ("sparse_zi_100", []),
     "sparse_zi_1000": ("sparse_zi_1000", []),
@@ -196,7 +200,8 @@ def main():
                 "cpu_baseline": {"value": v, "unit": "messages/s", "cores": cores, "kind": "port",
                                  "sample": "%d instances of %s per step on %d host threads (C restatement of the "
                                            "reference, oracle/abides_oracle.c)" % (n_sample, args.workload, cores)},
-                "e2e": {"value": v, "unit": "messages/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+                "e2e": {"value": v, "unit": "messages/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "reference_note": REFERENCE_NOTE}
         print(json.dumps(line), flush=True)
         return 0
 
@@ -307,6 +312,7 @@ def main():
                              "instruction-fetch bound, not HBM bound: see DESIGN.md and profiles/"
                              % ALGO_BYTES_PER_MESSAGE},
     }
+    line["reference_note"] = REFERENCE_NOTE
     if world == 1:
         if args.cpu_sample:
             n_sample, m, dt = args.cpu_sample, None, None
