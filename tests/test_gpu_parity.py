@@ -109,6 +109,33 @@ def test_device_parameter_grid_matches_oracle():
     assert ok.sum() >= 12
 
 
+def test_ragged_batch_of_different_configs_matches_every_golden():
+    """One launch holding instances of DIFFERENT configs (agent classes, latency models, market hours, population
+    sizes from 101 to 564 agents, with and without subscriptions / execution agents): each instance ends exactly as
+    its reference run did.  The batch falls on the full kernel variant."""
+    names = ["zi100_s123456789", "value_noise_s7", "rmsc02sub_s21_1100", "rmsc02fast_s23_1100", "rmsc01_s33_1100",
+             "rmsc03_s1234_1000", "exec_vwap_s5", "zi100_s123456789"]
+    hb = lowering.HostBatch([build_case(n) for n in names])
+    eng, res, ares = device_run(hb)
+    for i, n in enumerate(names):
+        g, meta = load_golden(n)
+        assert res["status"][i] == 0, n
+        for f in ("ttl_messages", "delivered", "last_trade", "final_time", "slowest_agent_finish_time"):
+            assert res[f][i] == meta[f], (n, f)
+        sl = agent_slices(hb, i)
+        assert np.array_equal(ares["cash"][sl], g["cash"]), n
+        assert np.array_equal(ares["holdings"][sl], g["holdings"]), n
+        assert np.array_equal(ares["marked_to_market"][sl], g["mtm"]), n
+    # pausing the ragged batch anywhere changes nothing either
+    from abides_b200.engine import Engine
+    e2 = Engine(0)
+    e2.load(hb)
+    e2.run(until_time=min(ic.mkt_open for ic in hb.instances) + 20 * 60 * 10 ** 9)
+    e2.run()
+    r2, a2 = e2.results_arrays()
+    assert np.array_equal(res["ttl_messages"], r2["ttl_messages"]) and np.array_equal(ares["cash"], a2["cash"])
+
+
 def test_pause_and_resume_equals_one_run():
     """abides_run(until_time) parks the batch in HBM mid-day; resuming gives the same day as one uninterrupted run."""
     spec = load_spec("zi100_s123456789")
