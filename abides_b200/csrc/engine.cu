@@ -232,9 +232,6 @@ struct Run {                            // per-launch context, shared memory, no
 struct __align__(128) Smem { InstShared st; Run run; };
 // ABM_CTA_WARPS instances share one CTA (warp y = instance blockIdx.x * ABM_CTA_WARPS + y) and meet at a barrier before
 // every event, so that the warps of an SM walk the same code at about the same time and share instruction-cache lines
-#ifndef ABM_PREFETCH_NEXT
-#define ABM_PREFETCH_NEXT 0
-#endif
 #ifndef ABM_CTA_WARPS
 #define ABM_CTA_WARPS 1
 #endif
