@@ -462,7 +462,26 @@ namespace v_rmsc {                      // rmsc03 family: noise / value / moment
 #undef ABM_V_BOOKEXT
 #undef ABM_V_FULL
 }
-enum { VAR_FULL = 0, VAR_ZI_LEGACY, VAR_ZI_CUBIC, VAR_RMSC, N_VARIANTS };
+namespace v_rmsc01 {                    // literal rmsc01: market maker (polling) / ZI / HBL / momentum, deterministic latency
+#define ABM_V_TRACE 0
+#define ABM_V_PHILOX 0
+#define ABM_V_CLASSES (CLS(ABIDES_ZI) | CLS(ABIDES_HBL) | CLS(ABIDES_MOMENTUM) | CLS(ABIDES_MARKET_MAKER))
+#define ABM_V_LAT ABIDES_LAT_DETERMINISTIC
+#define ABM_V_OLOG 1
+#define ABM_V_TVLOG 0
+#define ABM_V_BOOKEXT 0
+#define ABM_V_FULL 0
+#include "engine_device.inc"
+#undef ABM_V_TRACE
+#undef ABM_V_PHILOX
+#undef ABM_V_CLASSES
+#undef ABM_V_LAT
+#undef ABM_V_OLOG
+#undef ABM_V_TVLOG
+#undef ABM_V_BOOKEXT
+#undef ABM_V_FULL
+}
+enum { VAR_FULL = 0, VAR_ZI_LEGACY, VAR_ZI_CUBIC, VAR_RMSC, VAR_RMSC01, N_VARIANTS };
 
 // ----------------------------------------------------------------------------------------------
 // host side
@@ -587,6 +606,7 @@ int abides_create(int device, abides_handle** out) {
   CK(cudaFuncSetAttribute(v_zi_legacy::sim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ABM_CTA_WARPS * sizeof(Smem))));
   CK(cudaFuncSetAttribute(v_zi_cubic::sim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ABM_CTA_WARPS * sizeof(Smem))));
   CK(cudaFuncSetAttribute(v_rmsc::sim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ABM_CTA_WARPS * sizeof(Smem))));
+  CK(cudaFuncSetAttribute(v_rmsc01::sim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ABM_CTA_WARPS * sizeof(Smem))));
   *out = h;
   return 0;
 }
@@ -731,11 +751,13 @@ int abides_load(abides_handle* h, const abides_batch* b) {
   h->variant = VAR_FULL;
   if (b->rng_mode == ABIDES_RNG_MT19937 && b->trace_capacity == 0) {
     const unsigned zi = 1u << ABIDES_ZI;
+    const unsigned rmsc01 = (1u << ABIDES_ZI) | (1u << ABIDES_HBL) | (1u << ABIDES_MOMENTUM) | (1u << ABIDES_MARKET_MAKER);
     const unsigned rmsc = (1u << ABIDES_NOISE) | (1u << ABIDES_VALUE) | (1u << ABIDES_MOMENTUM) | (1u << ABIDES_ADAPTIVE_MM) |
                           (1u << ABIDES_POV_EXEC);
     if ((class_mask & ~zi) == 0 && lat_mask == (1u << ABIDES_LAT_LEGACY_NOISE)) h->variant = VAR_ZI_LEGACY;
     else if ((class_mask & ~zi) == 0 && lat_mask == (1u << ABIDES_LAT_CUBIC)) h->variant = VAR_ZI_CUBIC;
     else if ((class_mask & ~rmsc) == 0 && lat_mask == (1u << ABIDES_LAT_DETERMINISTIC) && n_sub == 0) h->variant = VAR_RMSC;
+    else if ((class_mask & ~rmsc01) == 0 && lat_mask == (1u << ABIDES_LAT_DETERMINISTIC) && n_sub == 0) h->variant = VAR_RMSC01;
   }
   if ((rc = h2d(h, d.cfg, b->instances, (size_t)ni))) return rc;
   if ((rc = h2d(h, d.types, b->types, (size_t)b->n_types))) return rc;
@@ -788,6 +810,7 @@ int abides_run(abides_handle* h, int64_t until_time) {
   switch (h->variant) {
     case VAR_ZI_LEGACY: v_zi_legacy::sim_kernel<<<(h->n_instances + ABM_CTA_WARPS - 1) / ABM_CTA_WARPS, dim3(32, ABM_CTA_WARPS), ABM_CTA_WARPS * sizeof(Smem), h->stream>>>((long long)until_time); break;
     case VAR_ZI_CUBIC: v_zi_cubic::sim_kernel<<<(h->n_instances + ABM_CTA_WARPS - 1) / ABM_CTA_WARPS, dim3(32, ABM_CTA_WARPS), ABM_CTA_WARPS * sizeof(Smem), h->stream>>>((long long)until_time); break;
+    case VAR_RMSC01: v_rmsc01::sim_kernel<<<(h->n_instances + ABM_CTA_WARPS - 1) / ABM_CTA_WARPS, dim3(32, ABM_CTA_WARPS), ABM_CTA_WARPS * sizeof(Smem), h->stream>>>((long long)until_time); break;
     case VAR_RMSC: v_rmsc::sim_kernel<<<(h->n_instances + ABM_CTA_WARPS - 1) / ABM_CTA_WARPS, dim3(32, ABM_CTA_WARPS), ABM_CTA_WARPS * sizeof(Smem), h->stream>>>((long long)until_time); break;
     default: v_full::sim_kernel<<<(h->n_instances + ABM_CTA_WARPS - 1) / ABM_CTA_WARPS, dim3(32, ABM_CTA_WARPS), ABM_CTA_WARPS * sizeof(Smem), h->stream>>>((long long)until_time); break;
   }

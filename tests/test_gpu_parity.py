@@ -78,6 +78,32 @@ def test_device_seed_sweep_matches_oracle_zi1000():
     _compare_with_oracle(hb, res, ares)
 
 
+@pytest.mark.parametrize("config, extra", [
+    ("rmsc01", ["--end-time", "10:30:00"]),                                   # kernel variant v_rmsc01
+    ("rmsc02", ["--end-time", "10:30:00"]),                                   # subscriptions (full variant)
+    ("execution", ["-t", "ABM", "-d", "20200603", "-e", "--execution-type", "vwap", "--num-noise", "200",
+                   "--num-value", "30", "--num-momentum", "8"]),              # schedule execution agent (full variant)
+    ("value_noise", []),                                                      # legacy latency + noise / value agents
+])
+def test_device_seed_sweep_matches_oracle_other_populations(config, extra):
+    """Untraced seed sweeps (the lean kernel variants only run without a trace) against the CPU oracle, instance by
+    instance, including the seeds on which the reference itself would raise (same status on both sides)."""
+    seeds = runtime.parallel_seeds(21, 8)
+    specs = runtime.build_specs_parallel(config, [list(extra) + ["-s", s] for s in seeds])
+    hb = lowering.HostBatch(specs)
+    eng, res, ares = device_run(hb)
+    ores, oares = oracle.run_batch(hb)
+    o = np.frombuffer(oares, dtype=ares.dtype)
+    for i in range(hb.n_instances):
+        assert res["status"][i] == ores[i].status, i
+        for f in ("ttl_messages", "delivered", "final_time", "last_trade", "n_orders", "n_fills", "traded_volume"):
+            assert res[f][i] == getattr(ores[i], f), (i, f)
+        if res["status"][i] == 0:
+            sl = agent_slices(hb, i)
+            for f in ("cash", "holdings", "marked_to_market"):
+                assert np.array_equal(ares[f][sl], o[f][sl]), (i, f)
+
+
 def test_reset_reruns_identically():
     spec = load_spec("zi100_s123456789")
     hb = lowering.HostBatch([spec] * 3)
