@@ -395,6 +395,7 @@ namespace v_full {                      // everything (tracing, Philox, every ag
 #define ABM_V_TVLOG 1
 #define ABM_V_BOOKEXT 1
 #define ABM_V_FULL 1
+#define ABM_V_MD 1
 #include "engine_device.inc"
 #undef ABM_V_TRACE
 #undef ABM_V_PHILOX
@@ -404,6 +405,7 @@ namespace v_full {                      // everything (tracing, Philox, every ag
 #undef ABM_V_TVLOG
 #undef ABM_V_BOOKEXT
 #undef ABM_V_FULL
+#undef ABM_V_MD
 }
 namespace v_zi_legacy {                 // sparse_zi_1000: ZI agents, agentLatency matrix + noise, MT19937, no trace
 #define ABM_V_TRACE 0
@@ -414,6 +416,7 @@ namespace v_zi_legacy {                 // sparse_zi_1000: ZI agents, agentLaten
 #define ABM_V_TVLOG 0
 #define ABM_V_BOOKEXT 0
 #define ABM_V_FULL 0
+#define ABM_V_MD 0
 #include "engine_device.inc"
 #undef ABM_V_TRACE
 #undef ABM_V_PHILOX
@@ -423,6 +426,7 @@ namespace v_zi_legacy {                 // sparse_zi_1000: ZI agents, agentLaten
 #undef ABM_V_TVLOG
 #undef ABM_V_BOOKEXT
 #undef ABM_V_FULL
+#undef ABM_V_MD
 }
 namespace v_zi_cubic {                  // sparse_zi_100: ZI agents, cubic latency model
 #define ABM_V_TRACE 0
@@ -433,6 +437,7 @@ namespace v_zi_cubic {                  // sparse_zi_100: ZI agents, cubic laten
 #define ABM_V_TVLOG 0
 #define ABM_V_BOOKEXT 0
 #define ABM_V_FULL 0
+#define ABM_V_MD 0
 #include "engine_device.inc"
 #undef ABM_V_TRACE
 #undef ABM_V_PHILOX
@@ -442,6 +447,7 @@ namespace v_zi_cubic {                  // sparse_zi_100: ZI agents, cubic laten
 #undef ABM_V_TVLOG
 #undef ABM_V_BOOKEXT
 #undef ABM_V_FULL
+#undef ABM_V_MD
 }
 namespace v_rmsc {                      // rmsc03 family: noise / value / momentum / adaptive MM / POV, deterministic latency
 #define ABM_V_TRACE 0
@@ -452,6 +458,7 @@ namespace v_rmsc {                      // rmsc03 family: noise / value / moment
 #define ABM_V_TVLOG 1
 #define ABM_V_BOOKEXT 1
 #define ABM_V_FULL 0
+#define ABM_V_MD 0
 #include "engine_device.inc"
 #undef ABM_V_TRACE
 #undef ABM_V_PHILOX
@@ -461,6 +468,7 @@ namespace v_rmsc {                      // rmsc03 family: noise / value / moment
 #undef ABM_V_TVLOG
 #undef ABM_V_BOOKEXT
 #undef ABM_V_FULL
+#undef ABM_V_MD
 }
 namespace v_rmsc01 {                    // literal rmsc01: market maker (polling) / ZI / HBL / momentum, deterministic latency
 #define ABM_V_TRACE 0
@@ -471,6 +479,7 @@ namespace v_rmsc01 {                    // literal rmsc01: market maker (polling
 #define ABM_V_TVLOG 0
 #define ABM_V_BOOKEXT 0
 #define ABM_V_FULL 0
+#define ABM_V_MD 0
 #include "engine_device.inc"
 #undef ABM_V_TRACE
 #undef ABM_V_PHILOX
@@ -480,8 +489,51 @@ namespace v_rmsc01 {                    // literal rmsc01: market maker (polling
 #undef ABM_V_TVLOG
 #undef ABM_V_BOOKEXT
 #undef ABM_V_FULL
+#undef ABM_V_MD
 }
-enum { VAR_FULL = 0, VAR_ZI_LEGACY, VAR_ZI_CUBIC, VAR_RMSC, VAR_RMSC01, N_VARIANTS };
+namespace v_rmsc02 {                    // rmsc02: the rmsc01 classes with market-data subscriptions
+#define ABM_V_TRACE 0
+#define ABM_V_PHILOX 0
+#define ABM_V_CLASSES (CLS(ABIDES_ZI) | CLS(ABIDES_HBL) | CLS(ABIDES_MOMENTUM) | CLS(ABIDES_MARKET_MAKER) | CLS(ABIDES_SUBSCRIPTION))
+#define ABM_V_LAT ABIDES_LAT_DETERMINISTIC
+#define ABM_V_OLOG 1
+#define ABM_V_TVLOG 0
+#define ABM_V_BOOKEXT 0
+#define ABM_V_FULL 0
+#define ABM_V_MD 1
+#include "engine_device.inc"
+#undef ABM_V_TRACE
+#undef ABM_V_PHILOX
+#undef ABM_V_CLASSES
+#undef ABM_V_LAT
+#undef ABM_V_OLOG
+#undef ABM_V_TVLOG
+#undef ABM_V_BOOKEXT
+#undef ABM_V_FULL
+#undef ABM_V_MD
+}
+namespace v_exec {                      // config/execution.py: the rmsc03 classes plus a TWAP / VWAP execution agent
+#define ABM_V_TRACE 0
+#define ABM_V_PHILOX 0
+#define ABM_V_CLASSES (CLS(ABIDES_NOISE) | CLS(ABIDES_VALUE) | CLS(ABIDES_MOMENTUM) | CLS(ABIDES_ADAPTIVE_MM) | CLS(ABIDES_POV_EXEC) | CLS(ABIDES_SCHEDULE_EXEC))
+#define ABM_V_LAT ABIDES_LAT_DETERMINISTIC
+#define ABM_V_OLOG 0
+#define ABM_V_TVLOG 1
+#define ABM_V_BOOKEXT 1
+#define ABM_V_FULL 0
+#define ABM_V_MD 0
+#include "engine_device.inc"
+#undef ABM_V_TRACE
+#undef ABM_V_PHILOX
+#undef ABM_V_CLASSES
+#undef ABM_V_LAT
+#undef ABM_V_OLOG
+#undef ABM_V_TVLOG
+#undef ABM_V_BOOKEXT
+#undef ABM_V_FULL
+#undef ABM_V_MD
+}
+enum { VAR_FULL = 0, VAR_ZI_LEGACY, VAR_ZI_CUBIC, VAR_RMSC, VAR_RMSC01, VAR_RMSC02, VAR_EXEC, N_VARIANTS };
 
 // ----------------------------------------------------------------------------------------------
 // host side
@@ -607,6 +659,8 @@ int abides_create(int device, abides_handle** out) {
   CK(cudaFuncSetAttribute(v_zi_cubic::sim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ABM_CTA_WARPS * sizeof(Smem))));
   CK(cudaFuncSetAttribute(v_rmsc::sim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ABM_CTA_WARPS * sizeof(Smem))));
   CK(cudaFuncSetAttribute(v_rmsc01::sim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ABM_CTA_WARPS * sizeof(Smem))));
+  CK(cudaFuncSetAttribute(v_rmsc02::sim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ABM_CTA_WARPS * sizeof(Smem))));
+  CK(cudaFuncSetAttribute(v_exec::sim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ABM_CTA_WARPS * sizeof(Smem))));
   *out = h;
   return 0;
 }
@@ -758,6 +812,8 @@ int abides_load(abides_handle* h, const abides_batch* b) {
     else if ((class_mask & ~zi) == 0 && lat_mask == (1u << ABIDES_LAT_CUBIC)) h->variant = VAR_ZI_CUBIC;
     else if ((class_mask & ~rmsc) == 0 && lat_mask == (1u << ABIDES_LAT_DETERMINISTIC) && n_sub == 0) h->variant = VAR_RMSC;
     else if ((class_mask & ~rmsc01) == 0 && lat_mask == (1u << ABIDES_LAT_DETERMINISTIC) && n_sub == 0) h->variant = VAR_RMSC01;
+    else if ((class_mask & ~(rmsc01 | (1u << ABIDES_SUBSCRIPTION))) == 0 && lat_mask == (1u << ABIDES_LAT_DETERMINISTIC)) h->variant = VAR_RMSC02;
+    else if ((class_mask & ~(rmsc | (1u << ABIDES_SCHEDULE_EXEC))) == 0 && lat_mask == (1u << ABIDES_LAT_DETERMINISTIC) && n_sub == 0) h->variant = VAR_EXEC;
   }
   if ((rc = h2d(h, d.cfg, b->instances, (size_t)ni))) return rc;
   if ((rc = h2d(h, d.types, b->types, (size_t)b->n_types))) return rc;
@@ -811,6 +867,8 @@ int abides_run(abides_handle* h, int64_t until_time) {
     case VAR_ZI_LEGACY: v_zi_legacy::sim_kernel<<<(h->n_instances + ABM_CTA_WARPS - 1) / ABM_CTA_WARPS, dim3(32, ABM_CTA_WARPS), ABM_CTA_WARPS * sizeof(Smem), h->stream>>>((long long)until_time); break;
     case VAR_ZI_CUBIC: v_zi_cubic::sim_kernel<<<(h->n_instances + ABM_CTA_WARPS - 1) / ABM_CTA_WARPS, dim3(32, ABM_CTA_WARPS), ABM_CTA_WARPS * sizeof(Smem), h->stream>>>((long long)until_time); break;
     case VAR_RMSC01: v_rmsc01::sim_kernel<<<(h->n_instances + ABM_CTA_WARPS - 1) / ABM_CTA_WARPS, dim3(32, ABM_CTA_WARPS), ABM_CTA_WARPS * sizeof(Smem), h->stream>>>((long long)until_time); break;
+    case VAR_RMSC02: v_rmsc02::sim_kernel<<<(h->n_instances + ABM_CTA_WARPS - 1) / ABM_CTA_WARPS, dim3(32, ABM_CTA_WARPS), ABM_CTA_WARPS * sizeof(Smem), h->stream>>>((long long)until_time); break;
+    case VAR_EXEC: v_exec::sim_kernel<<<(h->n_instances + ABM_CTA_WARPS - 1) / ABM_CTA_WARPS, dim3(32, ABM_CTA_WARPS), ABM_CTA_WARPS * sizeof(Smem), h->stream>>>((long long)until_time); break;
     case VAR_RMSC: v_rmsc::sim_kernel<<<(h->n_instances + ABM_CTA_WARPS - 1) / ABM_CTA_WARPS, dim3(32, ABM_CTA_WARPS), ABM_CTA_WARPS * sizeof(Smem), h->stream>>>((long long)until_time); break;
     default: v_full::sim_kernel<<<(h->n_instances + ABM_CTA_WARPS - 1) / ABM_CTA_WARPS, dim3(32, ABM_CTA_WARPS), ABM_CTA_WARPS * sizeof(Smem), h->stream>>>((long long)until_time); break;
   }
