@@ -33,3 +33,7 @@ acc = sum(v[k] for k in names[:11])
 print("  accounted %.1f%%" % (100.0 * acc / tot))
 for k in names[11:15]:
     print("  %-12s %10d  (%.4f per event)" % (k, v[k], v[k] / msgs))
+# utilisation: a warp's busy cycles against the kernel's duration (tail = instances that finish early)
+clk = 1.965e9
+print("mean busy share of a warp: %.1f%% of the kernel's %.1f ms (the rest is the tail after its instance ended)"
+      % (100.0 * (tot / n) / (ms * 1e-3 * clk), ms))
