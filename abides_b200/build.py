@@ -17,7 +17,7 @@ NVCC_FLAGS = [
 ]
 
 
-def build_cuda(force=False, verbose=False, profile=False, cta_warps=None):
+def build_cuda(force=False, verbose=False, profile=False, cta_warps=None, time_slices=None):
     """Compile csrc/engine.cu for sm_100a.  profile=True builds the instrumented variant next to it;
     cta_warps=W builds libabides_b200_w<W>.so with W instances per CTA (experiments; the default is 1)."""
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -26,11 +26,15 @@ def build_cuda(force=False, verbose=False, profile=False, cta_warps=None):
     out = OUT_PROF if profile else OUT
     if cta_warps:
         out = out.replace(".so", "_w%d.so" % cta_warps)
+    if time_slices:
+        out = out.replace(".so", "_q%d.so" % time_slices)
     if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
         return out
     flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + (["-DABIDES_PROFILE"] if profile else [])
     if cta_warps:
         flags.append("-DABM_CTA_WARPS=%d" % cta_warps)
+    if time_slices:
+        flags.append("-DABM_TIME_SLICES=%d" % time_slices)
     cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-I", INCLUDE, "-o", out] + srcs
     print(" ".join(cmd), file=sys.stderr)
     subprocess.check_call(cmd)
@@ -40,4 +44,5 @@ def build_cuda(force=False, verbose=False, profile=False, cta_warps=None):
 if __name__ == "__main__":
     w = [a for a in sys.argv if a.startswith("--cta-warps=")]
     build_cuda(force=True, verbose="-v" in sys.argv, profile="--profile" in sys.argv,
-               cta_warps=int(w[0].split("=")[1]) if w else None)
+               cta_warps=int(w[0].split("=")[1]) if w else None,
+               time_slices=next((int(a.split("=")[1]) for a in sys.argv if a.startswith("--time-slices=")), None))

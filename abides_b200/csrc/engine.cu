@@ -194,6 +194,7 @@ struct DevBatch {
   EvKey* b_keys; EvPay* b_pay;          // [n_instances][b_cap]
   EvKey* p_keys; EvPay* p_pay;          // [n_instances][2][deep_cap] book pools
   int* p_free;                          // [n_instances][2][deep_cap] free-slot stacks of the pools
+  unsigned* task_ctr; int* slice_done;  // dynamic (slice, instance) task hand-out: next task, slices stored per instance
   SubRec* subs;                         // [n_instances][MAX_SUBS], or NULL (no subscribing agent in the batch)
   MdSnap* md;                           // [n_instances][MD_RING], or NULL
   OLogRow* olog;                        // [n_instances][OLOG_CAP] order log, or NULL (no HBL agent in the batch)
@@ -235,6 +236,11 @@ struct __align__(128) Smem { InstShared st; Run run; };
 #ifndef ABM_CTA_WARPS
 #define ABM_CTA_WARPS 1
 #endif
+// ABM_TIME_SLICES > 1: instances are run as that many time slices handed to the warps dynamically (engine_device.inc)
+#ifndef ABM_TIME_SLICES
+#define ABM_TIME_SLICES 1
+#endif
+static_assert(ABM_TIME_SLICES == 1 || ABM_CTA_WARPS == 1, "time slices need one instance per CTA");
 #if ABM_CTA_WARPS > 1
 #define SM (reinterpret_cast<Smem*>(smem_raw + threadIdx.y * (unsigned)sizeof(Smem)))
 #else
@@ -773,6 +779,8 @@ int abides_load(abides_handle* h, const abides_batch* b) {
     if ((rc = dev_alloc(h, &d.type_omp2, (size_t)b->n_types))) return rc;
     if ((rc = dev_alloc(h, &d.agents, (size_t)na))) return rc;
     if ((rc = dev_alloc(h, &d.state, (size_t)ni))) return rc;
+    if ((rc = dev_alloc(h, &d.task_ctr, (size_t)1))) return rc;
+    if ((rc = dev_alloc(h, &d.slice_done, (size_t)ni))) return rc;
     if ((rc = dev_alloc(h, &d.a_keys, (size_t)ni * A_CAP))) return rc;
     if ((rc = dev_alloc(h, &d.a_pay, (size_t)ni * A_CAP))) return rc;
     if ((rc = dev_alloc(h, &d.b_keys, (size_t)ni * d.b_cap))) return rc;
@@ -863,6 +871,10 @@ int abides_run(abides_handle* h, int64_t until_time) {
   CK(cudaSetDevice(h->device));
   CK(cudaEventRecord(h->ev0, h->stream));
   CK(cudaMemcpyToSymbolAsync(c_db, &h->db, sizeof(DevBatch), 0, cudaMemcpyHostToDevice, h->stream));
+  if (ABM_TIME_SLICES > 1) {
+    CK(cudaMemsetAsync(h->db.task_ctr, 0, sizeof(unsigned), h->stream));
+    CK(cudaMemsetAsync(h->db.slice_done, 0, sizeof(int) * (size_t)h->n_instances, h->stream));
+  }
   switch (h->variant) {
     case VAR_ZI_LEGACY: v_zi_legacy::sim_kernel<<<(h->n_instances + ABM_CTA_WARPS - 1) / ABM_CTA_WARPS, dim3(32, ABM_CTA_WARPS), ABM_CTA_WARPS * sizeof(Smem), h->stream>>>((long long)until_time); break;
     case VAR_ZI_CUBIC: v_zi_cubic::sim_kernel<<<(h->n_instances + ABM_CTA_WARPS - 1) / ABM_CTA_WARPS, dim3(32, ABM_CTA_WARPS), ABM_CTA_WARPS * sizeof(Smem), h->stream>>>((long long)until_time); break;
