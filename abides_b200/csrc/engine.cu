@@ -403,15 +403,6 @@ namespace v_full {                      // everything (tracing, Philox, every ag
 #define ABM_V_FULL 1
 #define ABM_V_MD 1
 #include "engine_device.inc"
-#undef ABM_V_TRACE
-#undef ABM_V_PHILOX
-#undef ABM_V_CLASSES
-#undef ABM_V_LAT
-#undef ABM_V_OLOG
-#undef ABM_V_TVLOG
-#undef ABM_V_BOOKEXT
-#undef ABM_V_FULL
-#undef ABM_V_MD
 }
 namespace v_zi_legacy {                 // sparse_zi_1000: ZI agents, agentLatency matrix + noise, MT19937, no trace
 #define ABM_V_TRACE 0
@@ -424,15 +415,6 @@ namespace v_zi_legacy {                 // sparse_zi_1000: ZI agents, agentLaten
 #define ABM_V_FULL 0
 #define ABM_V_MD 0
 #include "engine_device.inc"
-#undef ABM_V_TRACE
-#undef ABM_V_PHILOX
-#undef ABM_V_CLASSES
-#undef ABM_V_LAT
-#undef ABM_V_OLOG
-#undef ABM_V_TVLOG
-#undef ABM_V_BOOKEXT
-#undef ABM_V_FULL
-#undef ABM_V_MD
 }
 namespace v_zi_cubic {                  // sparse_zi_100: ZI agents, cubic latency model
 #define ABM_V_TRACE 0
@@ -445,15 +427,6 @@ namespace v_zi_cubic {                  // sparse_zi_100: ZI agents, cubic laten
 #define ABM_V_FULL 0
 #define ABM_V_MD 0
 #include "engine_device.inc"
-#undef ABM_V_TRACE
-#undef ABM_V_PHILOX
-#undef ABM_V_CLASSES
-#undef ABM_V_LAT
-#undef ABM_V_OLOG
-#undef ABM_V_TVLOG
-#undef ABM_V_BOOKEXT
-#undef ABM_V_FULL
-#undef ABM_V_MD
 }
 namespace v_rmsc {                      // rmsc03 family: noise / value / momentum / adaptive MM / POV, deterministic latency
 #define ABM_V_TRACE 0
@@ -466,15 +439,6 @@ namespace v_rmsc {                      // rmsc03 family: noise / value / moment
 #define ABM_V_FULL 0
 #define ABM_V_MD 0
 #include "engine_device.inc"
-#undef ABM_V_TRACE
-#undef ABM_V_PHILOX
-#undef ABM_V_CLASSES
-#undef ABM_V_LAT
-#undef ABM_V_OLOG
-#undef ABM_V_TVLOG
-#undef ABM_V_BOOKEXT
-#undef ABM_V_FULL
-#undef ABM_V_MD
 }
 namespace v_rmsc01 {                    // literal rmsc01: market maker (polling) / ZI / HBL / momentum, deterministic latency
 #define ABM_V_TRACE 0
@@ -487,15 +451,6 @@ namespace v_rmsc01 {                    // literal rmsc01: market maker (polling
 #define ABM_V_FULL 0
 #define ABM_V_MD 0
 #include "engine_device.inc"
-#undef ABM_V_TRACE
-#undef ABM_V_PHILOX
-#undef ABM_V_CLASSES
-#undef ABM_V_LAT
-#undef ABM_V_OLOG
-#undef ABM_V_TVLOG
-#undef ABM_V_BOOKEXT
-#undef ABM_V_FULL
-#undef ABM_V_MD
 }
 namespace v_rmsc02 {                    // rmsc02: the rmsc01 classes with market-data subscriptions
 #define ABM_V_TRACE 0
@@ -508,15 +463,6 @@ namespace v_rmsc02 {                    // rmsc02: the rmsc01 classes with marke
 #define ABM_V_FULL 0
 #define ABM_V_MD 1
 #include "engine_device.inc"
-#undef ABM_V_TRACE
-#undef ABM_V_PHILOX
-#undef ABM_V_CLASSES
-#undef ABM_V_LAT
-#undef ABM_V_OLOG
-#undef ABM_V_TVLOG
-#undef ABM_V_BOOKEXT
-#undef ABM_V_FULL
-#undef ABM_V_MD
 }
 namespace v_exec {                      // config/execution.py: the rmsc03 classes plus a TWAP / VWAP execution agent
 #define ABM_V_TRACE 0
@@ -529,15 +475,6 @@ namespace v_exec {                      // config/execution.py: the rmsc03 class
 #define ABM_V_FULL 0
 #define ABM_V_MD 0
 #include "engine_device.inc"
-#undef ABM_V_TRACE
-#undef ABM_V_PHILOX
-#undef ABM_V_CLASSES
-#undef ABM_V_LAT
-#undef ABM_V_OLOG
-#undef ABM_V_TVLOG
-#undef ABM_V_BOOKEXT
-#undef ABM_V_FULL
-#undef ABM_V_MD
 }
 enum { VAR_FULL = 0, VAR_ZI_LEGACY, VAR_ZI_CUBIC, VAR_RMSC, VAR_RMSC01, VAR_RMSC02, VAR_EXEC, N_VARIANTS };
 
@@ -875,14 +812,17 @@ int abides_run(abides_handle* h, int64_t until_time) {
     CK(cudaMemsetAsync(h->db.task_ctr, 0, sizeof(unsigned), h->stream));
     CK(cudaMemsetAsync(h->db.slice_done, 0, sizeof(int) * (size_t)h->n_instances, h->stream));
   }
+#define LAUNCH_SIM(ns)                                                                                         \
+  ns::sim_kernel<<<(h->n_instances + ABM_CTA_WARPS - 1) / ABM_CTA_WARPS, dim3(32, ABM_CTA_WARPS),              \
+                   ABM_CTA_WARPS * sizeof(Smem), h->stream>>>((long long)until_time)
   switch (h->variant) {
-    case VAR_ZI_LEGACY: v_zi_legacy::sim_kernel<<<(h->n_instances + ABM_CTA_WARPS - 1) / ABM_CTA_WARPS, dim3(32, ABM_CTA_WARPS), ABM_CTA_WARPS * sizeof(Smem), h->stream>>>((long long)until_time); break;
-    case VAR_ZI_CUBIC: v_zi_cubic::sim_kernel<<<(h->n_instances + ABM_CTA_WARPS - 1) / ABM_CTA_WARPS, dim3(32, ABM_CTA_WARPS), ABM_CTA_WARPS * sizeof(Smem), h->stream>>>((long long)until_time); break;
-    case VAR_RMSC01: v_rmsc01::sim_kernel<<<(h->n_instances + ABM_CTA_WARPS - 1) / ABM_CTA_WARPS, dim3(32, ABM_CTA_WARPS), ABM_CTA_WARPS * sizeof(Smem), h->stream>>>((long long)until_time); break;
-    case VAR_RMSC02: v_rmsc02::sim_kernel<<<(h->n_instances + ABM_CTA_WARPS - 1) / ABM_CTA_WARPS, dim3(32, ABM_CTA_WARPS), ABM_CTA_WARPS * sizeof(Smem), h->stream>>>((long long)until_time); break;
-    case VAR_EXEC: v_exec::sim_kernel<<<(h->n_instances + ABM_CTA_WARPS - 1) / ABM_CTA_WARPS, dim3(32, ABM_CTA_WARPS), ABM_CTA_WARPS * sizeof(Smem), h->stream>>>((long long)until_time); break;
-    case VAR_RMSC: v_rmsc::sim_kernel<<<(h->n_instances + ABM_CTA_WARPS - 1) / ABM_CTA_WARPS, dim3(32, ABM_CTA_WARPS), ABM_CTA_WARPS * sizeof(Smem), h->stream>>>((long long)until_time); break;
-    default: v_full::sim_kernel<<<(h->n_instances + ABM_CTA_WARPS - 1) / ABM_CTA_WARPS, dim3(32, ABM_CTA_WARPS), ABM_CTA_WARPS * sizeof(Smem), h->stream>>>((long long)until_time); break;
+    case VAR_ZI_LEGACY: LAUNCH_SIM(v_zi_legacy); break;
+    case VAR_ZI_CUBIC: LAUNCH_SIM(v_zi_cubic); break;
+    case VAR_RMSC01: LAUNCH_SIM(v_rmsc01); break;
+    case VAR_RMSC02: LAUNCH_SIM(v_rmsc02); break;
+    case VAR_EXEC: LAUNCH_SIM(v_exec); break;
+    case VAR_RMSC: LAUNCH_SIM(v_rmsc); break;
+    default: LAUNCH_SIM(v_full); break;
   }
   CK(cudaGetLastError());
   CK(cudaEventRecord(h->ev1, h->stream));
