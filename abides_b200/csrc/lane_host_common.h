@@ -1,0 +1,44 @@
+// lane_host_common.h -- host-side decisions of the lane engine shared by engine.cu and the CPU-side test harness:
+// which kernel variant covers a batch, and the per-instance capacities of its device structures.
+#ifndef ABIDES_LANE_HOST_COMMON_H
+#define ABIDES_LANE_HOST_COMMON_H
+#include "lane_types.h"
+
+namespace lane {
+
+enum { LV_NONE = -1, LV_ZI_LEGACY = 0, LV_ZI_CUBIC = 1, LV_RMSC = 2, LV_FULL = 3, LV_COUNT = 4 };
+// the variant ids reported by abides_engine_info(): the warp engine's variants are 0..6, the lane engine's follow
+constexpr int LANE_VARIANT_BASE = 16;
+
+inline int lane_top_k(int variant) { return variant == LV_RMSC ? 128 : variant == LV_FULL ? 64 : 32; }
+
+// the leanest lane variant whose feature set covers the batch, or LV_NONE (HBL agents, market-data subscriptions and
+// Philox streams run on the warp-per-instance engine)
+inline int lane_pick_variant(unsigned class_mask, unsigned lat_mask, int rng_mode, long long n_subscribers) {
+  if (rng_mode != ABIDES_RNG_MT19937 || n_subscribers > 0) return LV_NONE;
+  const unsigned zi = 1u << ABIDES_ZI;
+  const unsigned rmsc = (1u << ABIDES_NOISE) | (1u << ABIDES_VALUE) | (1u << ABIDES_MOMENTUM) | (1u << ABIDES_ADAPTIVE_MM) |
+                        (1u << ABIDES_POV_EXEC);
+  const unsigned full = zi | rmsc | (1u << ABIDES_MARKET_MAKER) | (1u << ABIDES_SCHEDULE_EXEC);
+  if ((class_mask & ~zi) == 0 && lat_mask == (1u << ABIDES_LAT_LEGACY_NOISE)) return LV_ZI_LEGACY;
+  if ((class_mask & ~zi) == 0 && lat_mask == (1u << ABIDES_LAT_CUBIC)) return LV_ZI_CUBIC;
+  if ((class_mask & ~rmsc) == 0 && lat_mask == (1u << ABIDES_LAT_DETERMINISTIC)) return LV_RMSC;
+  if ((class_mask & ~full) == 0) return LV_FULL;
+  return LV_NONE;
+}
+
+struct LaneCaps { int hcap, scap, arena_cap, deep_cap, txn_cap, unr_cap, top_k; };
+inline LaneCaps lane_caps(int max_agents, int variant, bool needs_tv) {
+  LaneCaps c;
+  c.hcap = 3 * max_agents + 4096;            // events in flight (peak seen: 2 per agent at the market-open burst)
+  c.scap = c.hcap;                           // message payload slots
+  c.arena_cap = 4 * max_agents + 4096;       // open-order entries of all agents (lists grow by doubling)
+  c.deep_cap = 2 * max_agents + 1024;        // pool slots per book side
+  c.txn_cap = needs_tv ? 1 << 15 : 0;        // transaction rows between two volume queries
+  c.unr_cap = needs_tv ? 1 << 15 : 0;        // de-duplicated rows inside the longest look-back window
+  c.top_k = lane_top_k(variant);
+  return c;
+}
+
+}  // namespace lane
+#endif

@@ -56,3 +56,51 @@ def device_run(hb, device=0):
 def agent_slices(hb, inst):
     ic = hb.instances[inst]
     return slice(ic.agent_offset, ic.agent_offset + ic.n_agents)
+
+
+def random_book_rows(seed, n_books=512, n_ops=300):
+    """Shallow random books (limit orders only) for the replay harnesses: rows int64[n, 8], offsets int64[n_books + 1]."""
+    rng = np.random.default_rng(seed)
+    rows, off = [], [0]
+    for b in range(n_books):
+        t = 0
+        for i in range(n_ops):
+            t += 1000
+            buy = int(rng.integers(0, 2))
+            price = 100000 + (-1 if buy else 1) * int(rng.integers(-30, 200))
+            rows.append((7, int(rng.integers(1, 50)), i + 1, price, int(rng.integers(1, 100)), buy, 0, t))
+        off.append(len(rows))
+    return np.array(rows, np.int64), np.array(off, np.int64)
+
+
+def fuzz_book_rows(seed, n_books=48):
+    """Deep, wide books with every message type (limit / cancel of live, dead and repeated ids / modify / market)."""
+    rng = np.random.default_rng(seed)
+    rows, off = [], [0]
+    for b in range(n_books):
+        t, next_id, placed = 0, 1, []
+        width = int(rng.choice([5, 40, 400, 3000]))
+        n_ops = int(rng.choice([400, 1500, 4000]))
+        for i in range(n_ops):
+            t += int(rng.integers(1, 1000))
+            u = rng.random()
+            agent = int(rng.integers(1, 60))
+            if u < 0.62 or not placed:                      # limit order; mostly passive, sometimes crossing
+                buy = int(rng.integers(0, 2))
+                off_px = int(rng.integers(-width // 10 - 1, width))
+                price = 100000 - off_px if buy else 100000 + off_px
+                qty = int(rng.integers(1, 400))
+                rows.append((7, agent, next_id, price, qty, buy, 0, t))
+                placed.append((next_id, price, buy, agent))
+                next_id += 1
+            elif u < 0.88:                                  # cancel (some already gone, some twice)
+                oid, price, buy, ag = placed[int(rng.integers(0, len(placed)))]
+                rows.append((9, ag, oid, price, 1, buy, 0, t))
+            elif u < 0.93:                                  # modify
+                oid, price, buy, ag = placed[int(rng.integers(0, len(placed)))]
+                rows.append((10, ag, oid, price, 1, buy, int(rng.integers(1, 500)), t))
+            else:                                           # market order
+                rows.append((8, agent, next_id, 0, int(rng.integers(1, 3000)), int(rng.integers(0, 2)), 0, t))
+                next_id += 1
+        off.append(len(rows))
+    return np.array(rows, np.int64), np.array(off, np.int64)

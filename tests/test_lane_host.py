@@ -1,0 +1,117 @@
+"""CPU: the LOGIC of the lane engine (abides_b200/csrc/lane_device.inc: one instance per thread) checked against the
+reference goldens and the C oracle through a host build of the same source (tests/hostsim/ -- test infrastructure,
+never loaded by the package).  The GPU runs of the same code are in tests/test_gpu_lane.py."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import oracle
+import hostsim
+from abides_b200 import lowering, runtime, engine as eng_mod
+from parity_util import (load_golden, first_trace_mismatch, describe_mismatch, split_device_trace, fuzz_book_rows,
+                         random_book_rows)
+from test_oracle_golden import CASES, build_case
+from test_book_replay import golden as book_golden, check as book_check
+
+# goldens whose population the lane engine carries (HBL agents and market-data subscriptions stay on the warp engine)
+LANE_CASES = ["zi100_s123456789", "zi1000_s123456789", "rmsc03_s1234_1000", "rmsc03e_s1234_1100", "rmsc01s_s77",
+              "rmsc01mm_s33", "exec_twap_s6", "exec_vwap_s5", "execution_s8_e", "value_noise_s7",
+              "random_fund_value_s7", "random_fund_diverse_s7"]
+LEAN = {"zi100_s123456789": hostsim.LV_ZI_CUBIC, "zi1000_s123456789": hostsim.LV_ZI_LEGACY,
+        "rmsc03_s1234_1000": hostsim.LV_RMSC, "rmsc03e_s1234_1100": hostsim.LV_RMSC, "rmsc01s_s77": hostsim.LV_RMSC,
+        "random_fund_value_s7": hostsim.LV_RMSC}
+
+
+def check_golden(name, res, ares, tr, g, meta):
+    assert res["status"][0] == 0
+    assert res["ttl_messages"][0] == meta["ttl_messages"]
+    assert res["delivered"][0] == meta["delivered"]
+    disp, fund = split_device_trace(tr)
+    if "trace" in g.files:
+        i = first_trace_mismatch(disp, g["trace"])
+        assert i < 0, describe_mismatch(disp, g["trace"], i, ("lane", "reference"))
+    assert hashlib.sha256(np.ascontiguousarray(disp, np.int64).tobytes()).hexdigest() == meta["trace_sha256"]
+    assert np.array_equal(fund[:, 0], g["f_time"][1:])
+    assert np.array_equal(fund[:, 3].astype(np.float64), g["f_value"][1:])
+    assert np.array_equal(ares["cash"], g["cash"])
+    assert np.array_equal(ares["holdings"], g["holdings"])
+    assert np.array_equal(ares["marked_to_market"], g["mtm"])
+    fv, gfv = ares["final_valuation"], g["final_valuation"]
+    assert np.array_equal(np.isnan(fv), np.isnan(gfv))
+    assert np.array_equal(fv[~np.isnan(fv)], gfv[~np.isnan(gfv)])
+    assert res["last_trade"][0] == meta["last_trade"]
+    assert res["final_time"][0] == meta["final_time"]
+    assert res["slowest_agent_finish_time"][0] == meta["slowest_agent_finish_time"]
+
+
+@pytest.mark.parametrize("name", LANE_CASES)
+def test_lane_logic_matches_reference_golden(name):
+    """Every dispatched event, every oracle step and every agent's final portfolio of a full stochastic run, on the
+    variant the loader picks AND on the all-classes variant."""
+    g, meta = load_golden(name)
+    cap = meta["delivered"] + len(g["f_time"]) + 64
+    hb = lowering.HostBatch([build_case(name)])
+    seen = set()
+    for variant in (-1, hostsim.LV_FULL):
+        res, ares, tr, n, var = hostsim.run(hb, variant=variant, trace_instance=0, trace_cap=cap)
+        assert n <= cap
+        if variant == -1:
+            assert var == LEAN.get(name, hostsim.LV_FULL)
+        if var in seen:
+            continue
+        seen.add(var)
+        check_golden(name, res, ares, tr, g, meta)
+
+
+def test_lane_untraced_batch_matches_oracle():
+    """A ragged batch (different populations side by side, as lanes of one warp would hold them) without tracing."""
+    specs = [build_case("zi100_s123456789")] + [s for s, _ in runtime.build_instances(
+        "sparse_zi_100", [["-s", str(s)] for s in (3, 4, 5)])]
+    hb = lowering.HostBatch(specs)
+    res, ares, _, _, var = hostsim.run(hb)
+    assert var == hostsim.LV_ZI_CUBIC
+    ores, oares = oracle.run_batch(hb)
+    o = np.frombuffer(oares, dtype=ares.dtype)
+    for i in range(hb.n_instances):
+        for f in ("ttl_messages", "delivered", "final_time", "last_trade", "final_fundamental", "n_orders", "n_fills",
+                  "traded_volume", "slowest_agent_finish_time", "status"):
+            assert res[f][i] == getattr(ores[i], f), (i, f)
+    for f in ("cash", "holdings", "marked_to_market"):
+        assert np.array_equal(ares[f], o[f])
+
+
+def _unpack(ev, cnt, st, n, k):
+    return eng_mod.unpack_replay(ev, cnt[:n], st, n, k)
+
+
+def test_lane_book_replay_matches_reference_orderbook():
+    g, sh = book_golden()
+    ops = eng_mod.make_book_ops(g["ops"])
+    n = int(g["op_offset"][-1])
+    ev, cnt, st = hostsim.replay_book(g["op_offset"], ops, sh, 64)
+    book_check(*_unpack(ev, cnt, st, n, 64), g)
+
+
+@pytest.mark.parametrize("seed", [20261020, 7])
+def test_lane_deep_book_fuzz_matches_oracle(seed):
+    """Deep, wide books with every message type: the deque's both-ends inserts and removes, spills to the pool, slot
+    reuse, refills and level sums that run into the pool, the modify index-0 overwrite, sweeping market orders."""
+    rows, offs = fuzz_book_rows(seed, n_books=24)
+    ops = eng_mod.make_book_ops(rows)
+    n = len(rows)
+    a = _unpack(*hostsim.replay_book(offs, ops, 25, 96), n, 96)
+    b = _unpack(*oracle.replay_book(offs, ops, 25, 96), n, 96)
+    assert (a[1] <= 96).all() and np.array_equal(a[1], b[1])
+    assert np.array_equal(a[2], b[2])
+    assert np.array_equal(a[0], b[0])
+    assert a[2][:, 5].max() > 100 and a[2][:, 6].max() > 100
+
+
+def test_lane_shallow_books_match_oracle():
+    rows, offs = random_book_rows(7, n_books=64)
+    ops = eng_mod.make_book_ops(rows)
+    n = len(rows)
+    a = _unpack(*hostsim.replay_book(offs, ops, 10, 64), n, 64)
+    b = _unpack(*oracle.replay_book(offs, ops, 10, 64), n, 64)
+    assert np.array_equal(a[2], b[2]) and np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
