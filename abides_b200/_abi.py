@@ -147,8 +147,13 @@ LIB_PATH = os.environ.get("ABIDES_B200_LIB") or os.path.join(_PKG_DIR, "csrc", "
 EXPORTS = [
     "abides_create", "abides_destroy", "abides_last_error", "abides_version", "abides_load",
     "abides_reset", "abides_run", "abides_read_results", "abides_read_trace", "abides_last_run_ms", "abides_last_reset_ms", "abides_read_profile",
-    "abides_replay_book",
+    "abides_replay_book", "abides_set_engine", "abides_engine_info",
 ]
+ENGINE_AUTO, ENGINE_WARP, ENGINE_LANE = 0, 1, 2        # enum abides_engine
+LANE_AUTO_MIN_INSTANCES = 4096
+VARIANT_NAMES = {0: "warp/full", 1: "warp/zi_legacy", 2: "warp/zi_cubic", 3: "warp/rmsc", 4: "warp/rmsc01",
+                 5: "warp/rmsc02", 6: "warp/exec", 16: "lane/zi_legacy", 17: "lane/zi_cubic", 18: "lane/rmsc",
+                 19: "lane/full"}
 
 _lib = None
 
@@ -192,5 +197,9 @@ def lib():
                                      C.c_int32, C.POINTER(BookEvent), C.POINTER(C.c_int32),
                                      C.POINTER(BookState)]
     L.abides_replay_book.restype = C.c_int
+    L.abides_set_engine.argtypes = [H, C.c_int32]
+    L.abides_set_engine.restype = C.c_int
+    L.abides_engine_info.argtypes = [H, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    L.abides_engine_info.restype = C.c_int
     _lib = L
     return L

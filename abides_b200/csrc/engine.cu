@@ -49,10 +49,24 @@
 
 #include "abides_b200.h"
 #include "abides_dd_math.h"
+#include "lane_host_common.h"
 
 #define FULL 0xffffffffu
 #define UNLIKELY(x) __builtin_expect(!!(x), 0)
 #define LIKELY(x) __builtin_expect(!!(x), 1)
+
+// ----------------------------------------------------------------------------------------------
+// the LANE engine (lane_device.inc): one instance per thread, used for large batches.  See lane_types.h.
+// ----------------------------------------------------------------------------------------------
+#define LN_INL __device__ __forceinline__
+#define LN_BIG __device__ __noinline__
+#define LN_KERNEL __global__
+#define LN_GRID_CONSTANT __grid_constant__
+#define LN_THREAD_INDEX() ((int)(blockIdx.x * blockDim.x + threadIdx.x))
+namespace lane {
+#include "lane_variants.inc"
+}
+constexpr int LANE_BLOCK = 32;          // threads per block: instances are independent, small blocks spread over more SMs
 
 namespace {
 
@@ -496,9 +510,10 @@ namespace {
 struct ShapeSig {
   int ni = 0, n_types = 0, rng_mode = -1, trace_cap = -1, max_agents = 0, n_mom = 0;
   bool has_hbl = false, needs_tv = false, has_md = false;
+  int lane_variant = lane::LV_NONE;     // LV_NONE: the warp-per-instance engine
   long long na = -1, n_theta = -1;
   bool operator==(const ShapeSig& o) const {
-    return ni == o.ni && n_types == o.n_types && rng_mode == o.rng_mode && trace_cap == o.trace_cap &&
+    return lane_variant == o.lane_variant && ni == o.ni && n_types == o.n_types && rng_mode == o.rng_mode && trace_cap == o.trace_cap &&
            max_agents == o.max_agents && n_mom == o.n_mom && na == o.na && n_theta == o.n_theta && has_hbl == o.has_hbl && needs_tv == o.needs_tv && has_md == o.has_md;
   }
 };
@@ -514,6 +529,9 @@ struct abides_handle {
   int n_instances = 0;
   long long n_agents_total = 0;
   int variant = VAR_FULL;               // which kernel variant the loaded batch runs on
+  int engine_pref = ABIDES_ENGINE_AUTO; // abides_set_engine
+  int lane_variant = lane::LV_NONE;     // != LV_NONE: the loaded batch runs on the lane engine
+  lane::LaneBatch lb{};
   float last_ms = 0.f, last_reset_ms = 0.f;
   int last_launches = 0;
   int launches_since_load = 0;
@@ -563,6 +581,25 @@ int launch_init(abides_handle* h) {
   CK(cudaMemsetAsync(d.mom_ring, 0, (size_t)(h->n_mom > 0 ? h->n_mom : 1) * MOM_RING * sizeof(double), h->stream));
   CK(cudaMemsetAsync(d.res, 0, (size_t)d.n_instances * sizeof(abides_instance_result), h->stream));
   CK(cudaMemsetAsync(d.prof, 0, N_PROF * sizeof(unsigned long long), h->stream));
+  if (h->lane_variant != lane::LV_NONE) {
+    const lane::LaneBatch& lb = h->lb;
+    const int tg = (d.n_types + 63) / 64, ig = (d.n_instances + LANE_BLOCK - 1) / LANE_BLOCK;
+#define LAUNCH_LANE_INIT(ns)                                                  \
+  do {                                                                        \
+    lane::ns::lane_init_types_kernel<<<tg, 64, 0, h->stream>>>(lb);           \
+    lane::ns::lane_init_kernel<<<ig, LANE_BLOCK, 0, h->stream>>>(lb);         \
+  } while (0)
+    switch (h->lane_variant) {
+      case lane::LV_ZI_LEGACY: LAUNCH_LANE_INIT(lv_zi_legacy); break;
+      case lane::LV_ZI_CUBIC: LAUNCH_LANE_INIT(lv_zi_cubic); break;
+      case lane::LV_RMSC: LAUNCH_LANE_INIT(lv_rmsc); break;
+      default: LAUNCH_LANE_INIT(lv_full); break;
+    }
+#undef LAUNCH_LANE_INIT
+    CK(cudaGetLastError());
+    h->launches_since_load += 2;
+    return 0;
+  }
   CK(cudaMemcpyToSymbolAsync(c_db, &d, sizeof(DevBatch), 0, cudaMemcpyHostToDevice, h->stream));
   init_types_kernel<<<(d.n_types + 63) / 64, 64, 0, h->stream>>>();
   init_kernel<<<d.n_instances, 32, 0, h->stream>>>();
@@ -618,6 +655,22 @@ void abides_destroy(abides_handle* h) {
   delete h;
 }
 
+
+int abides_set_engine(abides_handle* h, int32_t engine) {
+  if (!h) return fail(ABIDES_EINVAL, "NULL handle");
+  if (engine != ABIDES_ENGINE_AUTO && engine != ABIDES_ENGINE_WARP && engine != ABIDES_ENGINE_LANE)
+    return fail(ABIDES_EINVAL, "abides_set_engine: unknown engine");
+  h->engine_pref = engine;
+  return 0;
+}
+
+int abides_engine_info(abides_handle* h, int32_t* engine, int32_t* variant) {
+  if (!h || !h->loaded) return fail(ABIDES_ESTATE, "abides_engine_info: no batch loaded");
+  const bool ln = h->lane_variant != lane::LV_NONE;
+  if (engine) *engine = ln ? ABIDES_ENGINE_LANE : ABIDES_ENGINE_WARP;
+  if (variant) *variant = ln ? lane::LANE_VARIANT_BASE + h->lane_variant : h->variant;
+  return 0;
+}
 
 int abides_load(abides_handle* h, const abides_batch* b) {
   if (!h || !b) return fail(ABIDES_EINVAL, "abides_load: NULL argument");
@@ -680,6 +733,24 @@ int abides_load(abides_handle* h, const abides_batch* b) {
   const bool needs_tv = (class_mask & ((1u << ABIDES_ADAPTIVE_MM) | (1u << ABIDES_POV_EXEC))) != 0;
   sig.needs_tv = needs_tv;
   sig.has_md = n_sub > 0;
+  // which engine: the lane engine (one instance per thread) needs thousands of instances to fill the chip; below
+  // that the warp-per-instance engine is faster.  abides_set_engine / ABIDES_ENGINE override the choice.
+  int lane_variant = lane::lane_pick_variant(class_mask, lat_mask, b->rng_mode, n_sub);
+  {
+    int pref = h->engine_pref;
+    if (pref == ABIDES_ENGINE_AUTO) {
+      const char* e = getenv("ABIDES_ENGINE");
+      if (e && !strcmp(e, "lane")) pref = ABIDES_ENGINE_LANE;
+      else if (e && !strcmp(e, "warp")) pref = ABIDES_ENGINE_WARP;
+    }
+    if (pref == ABIDES_ENGINE_LANE && lane_variant == lane::LV_NONE)
+      return fail(ABIDES_EINVAL, "abides_load: the lane engine was requested but does not carry this batch (HBL agents, "
+                                 "market-data subscriptions and Philox streams run on the warp engine)");
+    if (pref == ABIDES_ENGINE_WARP || (pref == ABIDES_ENGINE_AUTO && ni < ABIDES_LANE_AUTO_MIN_INSTANCES)) lane_variant = lane::LV_NONE;
+  }
+  sig.lane_variant = lane_variant;
+  const bool use_lane = lane_variant != lane::LV_NONE;
+  const lane::LaneCaps lcap = lane::lane_caps(max_agents, lane_variant, needs_tv);
   DevBatch& d = h->db;
   int rc;
   size_t ns = (size_t)na + (size_t)ABIDES_EXTRA_STREAMS * ni;
@@ -714,6 +785,31 @@ int abides_load(abides_handle* h, const abides_batch* b) {
     }
     if ((rc = dev_alloc(h, &d.type_log1mk, (size_t)b->n_types))) return rc;
     if ((rc = dev_alloc(h, &d.type_omp2, (size_t)b->n_types))) return rc;
+    if ((rc = dev_alloc(h, &d.prof, (size_t)N_PROF))) return rc;
+    if ((rc = dev_alloc(h, &d.mom_ring, (size_t)(n_mom > 0 ? n_mom : 1) * MOM_RING))) return rc;
+    if ((rc = dev_alloc(h, &d.trace, (size_t)ni * (d.trace_cap > 0 ? d.trace_cap : 0)))) return rc;
+    if ((rc = dev_alloc(h, &d.res, (size_t)ni))) return rc;
+    if ((rc = dev_alloc(h, &d.ares, (size_t)na))) return rc;
+    memset(&h->lb, 0, sizeof h->lb);
+    if (use_lane) {
+      lane::LaneBatch& lb = h->lb;
+      lb.hcap = lcap.hcap; lb.scap = lcap.scap; lb.arena_cap = lcap.arena_cap; lb.deep_cap = lcap.deep_cap;
+      lb.txn_cap = lcap.txn_cap; lb.unr_cap = lcap.unr_cap; lb.top_k = lcap.top_k;
+      if ((rc = dev_alloc(h, &lb.agents, (size_t)na))) return rc;
+      if ((rc = dev_alloc(h, &lb.state, (size_t)ni))) return rc;
+      if ((rc = dev_alloc(h, &lb.hkeys, (size_t)ni * lane::heap_stride(lcap.hcap)))) return rc;
+      if ((rc = dev_alloc(h, &lb.hpay, (size_t)ni * lcap.scap))) return rc;
+      if ((rc = dev_alloc(h, &lb.hfree, (size_t)ni * lcap.scap))) return rc;
+      if ((rc = dev_alloc(h, &lb.top, (size_t)ni * 2 * lcap.top_k))) return rc;
+      if ((rc = dev_alloc(h, &lb.pl_price, (size_t)ni * 2 * lcap.deep_cap))) return rc;
+      if ((rc = dev_alloc(h, &lb.pl_ord, (size_t)ni * 2 * lcap.deep_cap))) return rc;
+      if ((rc = dev_alloc(h, &lb.pl_free, (size_t)ni * 2 * lcap.deep_cap))) return rc;
+      if ((rc = dev_alloc(h, &lb.arena, (size_t)ni * lcap.arena_cap))) return rc;
+      if (needs_tv) {
+        if ((rc = dev_alloc(h, &lb.txn_log, (size_t)ni * lcap.txn_cap))) return rc;
+        if ((rc = dev_alloc(h, &lb.unrolled, (size_t)ni * lcap.unr_cap))) return rc;
+      }
+    } else {
     if ((rc = dev_alloc(h, &d.agents, (size_t)na))) return rc;
     if ((rc = dev_alloc(h, &d.state, (size_t)ni))) return rc;
     if ((rc = dev_alloc(h, &d.task_ctr, (size_t)1))) return rc;
@@ -722,7 +818,6 @@ int abides_load(abides_handle* h, const abides_batch* b) {
     if ((rc = dev_alloc(h, &d.a_pay, (size_t)ni * A_CAP))) return rc;
     if ((rc = dev_alloc(h, &d.b_keys, (size_t)ni * d.b_cap))) return rc;
     if ((rc = dev_alloc(h, &d.b_pay, (size_t)ni * d.b_cap))) return rc;
-    if ((rc = dev_alloc(h, &d.prof, (size_t)N_PROF))) return rc;
     if ((rc = dev_alloc(h, &d.arena, (size_t)ni * d.arena_cap))) return rc;
     if ((rc = dev_alloc(h, &d.p_keys, (size_t)ni * 2 * d.deep_cap))) return rc;
     if ((rc = dev_alloc(h, &d.p_pay, (size_t)ni * 2 * d.deep_cap))) return rc;
@@ -739,12 +834,20 @@ int abides_load(abides_handle* h, const abides_batch* b) {
       if ((rc = dev_alloc(h, &d.txn_log, (size_t)ni * TXN_CAP))) return rc;
       if ((rc = dev_alloc(h, &d.unrolled, (size_t)ni * UNR_CAP))) return rc;
     }
-    if ((rc = dev_alloc(h, &d.mom_ring, (size_t)(n_mom > 0 ? n_mom : 1) * MOM_RING))) return rc;
-    if ((rc = dev_alloc(h, &d.trace, (size_t)ni * (d.trace_cap > 0 ? d.trace_cap : 0)))) return rc;
-    if ((rc = dev_alloc(h, &d.res, (size_t)ni))) return rc;
-    if ((rc = dev_alloc(h, &d.ares, (size_t)na))) return rc;
+    }
+    if (use_lane) {                             // the lane engine reads the shared input tables through its own descriptor
+      lane::LaneBatch& lb = h->lb;
+      lb.n_instances = ni; lb.trace_cap = d.trace_cap; lb.n_types = d.n_types;
+      lb.cfg = d.cfg; lb.types = d.types; lb.type_log1mk = d.type_log1mk; lb.type_omp2 = d.type_omp2;
+      lb.agent_type = d.agent_type; lb.lat_to = d.lat_to; lb.lat_from = d.lat_from; lb.size = d.size;
+      lb.wakeup_time = d.wakeup_time; lb.agent_theta = d.agent_theta; lb.theta = d.theta; lb.mom_index = d.mom_index;
+      lb.mt = d.mt; lb.mt_row = nullptr; lb.mt_seed = nullptr;
+      lb.mt_pos = d.mt_pos; lb.mt_has_gauss = d.mt_has_gauss; lb.mt_gauss = d.mt_gauss;
+      lb.mom_ring = d.mom_ring; lb.trace = d.trace; lb.res = d.res; lb.ares = d.ares;
+    }
     h->sig = sig;
   }
+  h->lane_variant = lane_variant;
   h->n_streams = ns; h->n_mom = n_mom;
   // kernel variant: the leanest one whose feature set covers the batch (engine_device.inc)
   h->variant = VAR_FULL;
@@ -807,6 +910,24 @@ int abides_run(abides_handle* h, int64_t until_time) {
   if (!h || !h->loaded) return fail(ABIDES_ESTATE, "abides_run: no batch loaded");
   CK(cudaSetDevice(h->device));
   CK(cudaEventRecord(h->ev0, h->stream));
+  if (h->lane_variant != lane::LV_NONE) {
+    const int grid = (h->n_instances + LANE_BLOCK - 1) / LANE_BLOCK;
+#define LAUNCH_LANE(ns) lane::ns::lane_sim_kernel<<<grid, LANE_BLOCK, 0, h->stream>>>(h->lb, (long long)until_time)
+    switch (h->lane_variant) {
+      case lane::LV_ZI_LEGACY: LAUNCH_LANE(lv_zi_legacy); break;
+      case lane::LV_ZI_CUBIC: LAUNCH_LANE(lv_zi_cubic); break;
+      case lane::LV_RMSC: LAUNCH_LANE(lv_rmsc); break;
+      default: LAUNCH_LANE(lv_full); break;
+    }
+#undef LAUNCH_LANE
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev1, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+    h->last_launches = 1;
+    h->launches_since_load += 1;
+    return 0;
+  }
   CK(cudaMemcpyToSymbolAsync(c_db, &h->db, sizeof(DevBatch), 0, cudaMemcpyHostToDevice, h->stream));
   if (ABM_TIME_SLICES > 1) {
     CK(cudaMemsetAsync(h->db.task_ctr, 0, sizeof(unsigned), h->stream));
@@ -867,8 +988,13 @@ int abides_read_trace(abides_handle* h, int32_t instance, abides_trace_rec* out,
   if (instance < 0 || instance >= h->n_instances) return fail(ABIDES_EINVAL, "abides_read_trace: bad instance");
   CK(cudaSetDevice(h->device));
   int n = 0;
+  if (h->lane_variant != lane::LV_NONE) {
+    const char* base = reinterpret_cast<const char*>(&h->lb.state[instance]);
+    CK(cudaMemcpy(&n, base + offsetof(lane::LHot, n_trace), sizeof(int), cudaMemcpyDeviceToHost));
+  } else {
   const char* base = reinterpret_cast<const char*>(&h->db.state[instance]);
   CK(cudaMemcpy(&n, base + offsetof(InstShared, hot) + offsetof(Hot, n_trace), sizeof(int), cudaMemcpyDeviceToHost));
+  }
   if (n_out) *n_out = n;
   int64_t k = n;
   if (k > h->db.trace_cap) k = h->db.trace_cap;
@@ -897,6 +1023,42 @@ int abides_replay_book(abides_handle* h, int32_t n_books, const int64_t* op_offs
     if (ops[i].price < 0 || ops[i].price > 2000000000ll || ops[i].qty > 2000000000ll || ops[i].order_id >= (1ll << 30))
       return fail(ABIDES_EINVAL, "abides_replay_book: price / quantity / order id outside the device's int32 range");
   int deep_cap = (int)(longest + 64);
+  if (h->engine_pref == ABIDES_ENGINE_LANE) {          // the lane engine's book: one thread per book
+    long long* d_off = nullptr; abides_book_op* d_ops = nullptr; abides_book_event* d_ev = nullptr; int* d_cnt = nullptr;
+    abides_book_state* d_st = nullptr;
+    lane::LaneBatch lb;
+    memset(&lb, 0, sizeof lb);
+    lb.top_k = lane::lane_top_k(lane::LV_FULL); lb.deep_cap = deep_cap;
+    auto cleanup = [&]() { cudaFree(d_off); cudaFree(d_ops); cudaFree(d_ev); cudaFree(d_cnt); cudaFree(d_st); cudaFree(lb.top);
+                           cudaFree(lb.pl_price); cudaFree(lb.pl_ord); cudaFree(lb.pl_free); };
+#define RCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return fail(ABIDES_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
+    RCK(cudaMalloc(&d_off, sizeof(long long) * (n_books + 1)));
+    RCK(cudaMalloc(&d_ops, sizeof(abides_book_op) * n_ops));
+    RCK(cudaMalloc(&d_ev, sizeof(abides_book_event) * n_ops * max_events_per_op));
+    RCK(cudaMalloc(&d_cnt, sizeof(int) * n_ops));
+    RCK(cudaMalloc(&d_st, sizeof(abides_book_state) * n_ops));
+    RCK(cudaMalloc(&lb.top, sizeof(lane::LOrd) * (size_t)n_books * 2 * lb.top_k));
+    RCK(cudaMalloc(&lb.pl_price, sizeof(int) * (size_t)n_books * 2 * deep_cap));
+    RCK(cudaMalloc(&lb.pl_ord, sizeof(lane::LOrd) * (size_t)n_books * 2 * deep_cap));
+    RCK(cudaMalloc(&lb.pl_free, sizeof(int) * (size_t)n_books * 2 * deep_cap));
+    RCK(cudaMemcpyAsync(d_off, op_offset, sizeof(long long) * (n_books + 1), cudaMemcpyHostToDevice, h->stream));
+    RCK(cudaMemcpyAsync(d_ops, ops, sizeof(abides_book_op) * n_ops, cudaMemcpyHostToDevice, h->stream));
+    RCK(cudaMemsetAsync(d_ev, 0, sizeof(abides_book_event) * n_ops * max_events_per_op, h->stream));
+    RCK(cudaEventRecord(h->ev0, h->stream));
+    lane::lv_full::lane_replay_kernel<<<(n_books + LANE_BLOCK - 1) / LANE_BLOCK, LANE_BLOCK, 0, h->stream>>>(
+        lb, n_books, d_off, d_ops, stream_history, max_events_per_op, d_ev, d_cnt, d_st);
+    RCK(cudaGetLastError());
+    RCK(cudaEventRecord(h->ev1, h->stream));
+    RCK(cudaMemcpyAsync(events_out, d_ev, sizeof(abides_book_event) * n_ops * max_events_per_op, cudaMemcpyDeviceToHost, h->stream));
+    RCK(cudaMemcpyAsync(event_count_out, d_cnt, sizeof(int) * n_ops, cudaMemcpyDeviceToHost, h->stream));
+    RCK(cudaMemcpyAsync(states_out, d_st, sizeof(abides_book_state) * n_ops, cudaMemcpyDeviceToHost, h->stream));
+    RCK(cudaStreamSynchronize(h->stream));
+    RCK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+#undef RCK
+    h->last_launches = 1;
+    cleanup();
+    return 0;
+  }
   long long* d_off = nullptr; abides_book_op* d_ops = nullptr; abides_book_event* d_ev = nullptr; int* d_cnt = nullptr;
   abides_book_state* d_st = nullptr; EvKey* d_deep = nullptr; EvPay* d_seq = nullptr; int* d_free = nullptr;
   int rc = 0;

@@ -24,8 +24,10 @@
 
 #if defined(__CUDACC__)
 #define LN_ALIGN(n) __align__(n)
+#define LN_HD __host__ __device__
 #else
 #define LN_ALIGN(n) alignas(n)
+#define LN_HD
 #endif
 
 // agent classes as preprocessor constants (the variants' class masks are tested with #if)
@@ -159,7 +161,7 @@ struct LaneBatch {
   abides_agent_result* ares;
 };
 
-inline int heap_stride(int hcap) { return (hcap + HEAP_ROOT + 1 + 7) & ~7; }      // whole 128-byte lines per instance
+LN_HD inline int heap_stride(int hcap) { return (hcap + HEAP_ROOT + 1 + 7) & ~7; }      // whole 128-byte lines per instance
 
 }  // namespace lane
 #endif

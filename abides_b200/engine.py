@@ -49,6 +49,17 @@ class Engine:
         self._ck(self._L.abides_load(self._h, C.byref(host_batch.c)), "abides_load")
         self.batch = host_batch
 
+    def set_engine(self, engine):
+        """Force the device engine of the following loads: _abi.ENGINE_AUTO / ENGINE_WARP / ENGINE_LANE, or its name."""
+        engine = {"auto": _abi.ENGINE_AUTO, "warp": _abi.ENGINE_WARP, "lane": _abi.ENGINE_LANE}.get(engine, engine)
+        self._ck(self._L.abides_set_engine(self._h, int(engine)), "abides_set_engine")
+
+    def engine_info(self):
+        """(engine, variant) the loaded batch runs on; names in _abi.VARIANT_NAMES."""
+        e, v = C.c_int32(0), C.c_int32(0)
+        self._ck(self._L.abides_engine_info(self._h, C.byref(e), C.byref(v)), "abides_engine_info")
+        return e.value, v.value
+
     def reset(self):
         """Re-arm the resident batch (no host->device traffic)."""
         self._ck(self._L.abides_reset(self._h), "abides_reset")

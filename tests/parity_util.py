@@ -44,9 +44,12 @@ def split_device_trace(tr):
     return tr[~f], tr[f]
 
 
-def device_run(hb, device=0):
+def device_run(hb, device=0, engine=None):
+    """Load + run a HostBatch through the C ABI; engine: None (the loader's choice), "warp" or "lane"."""
     from abides_b200.engine import Engine
     eng = Engine(device)
+    if engine is not None:
+        eng.set_engine(engine)
     eng.load(hb)
     eng.run()
     res, ares = eng.results_arrays()

@@ -1,0 +1,125 @@
+"""GPU: the lane engine (one instance per thread, abides_b200/csrc/lane_device.inc) through the C ABI against the
+reference goldens, the C oracle and the warp engine."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import oracle
+from abides_b200 import _abi, lowering, runtime, engine as eng_mod
+from parity_util import (load_golden, device_run, agent_slices, split_device_trace, first_trace_mismatch,
+                         describe_mismatch, fuzz_book_rows, random_book_rows)
+from test_oracle_golden import CASES, build_case
+from test_lane_host import LANE_CASES, LEAN, check_golden
+from test_book_replay import golden as book_golden, check as book_check
+
+pytestmark = pytest.mark.gpu
+LANE_BASE = 16
+
+
+@pytest.mark.parametrize("name", LANE_CASES)
+def test_lane_engine_matches_reference_golden(name):
+    """Full stochastic run on the lane engine, traced: every dispatched event, oracle step and final portfolio."""
+    g, meta = load_golden(name)
+    cap = meta["delivered"] + len(g["f_time"]) + 64
+    hb = lowering.HostBatch([build_case(name)], trace_capacity=cap)
+    eng, res, ares = device_run(hb, engine="lane")
+    e, v = eng.engine_info()
+    assert e == _abi.ENGINE_LANE and v == LANE_BASE + LEAN.get(name, 3)
+    tr, n = eng.trace(0)
+    assert n <= cap
+    check_golden(name, res, ares[agent_slices(hb, 0)], tr, g, meta)
+
+
+def _sweep(config, seeds, extra=()):
+    return [s for s, _ in runtime.build_instances(config, [list(extra) + ["-s", str(s)] for s in seeds])]
+
+
+def _same_results(res, ares, ores, oares):
+    for f in ("status", "ttl_messages", "delivered", "final_time", "last_trade", "final_fundamental", "n_orders", "n_fills",
+              "traded_volume", "slowest_agent_finish_time"):
+        assert np.array_equal(res[f], ores[f]), f
+    for f in ("cash", "holdings", "marked_to_market"):
+        assert np.array_equal(ares[f], oares[f]), f
+    fv, ofv = ares["final_valuation"], oares["final_valuation"]
+    assert np.array_equal(np.isnan(fv), np.isnan(ofv))
+    assert np.array_equal(fv[~np.isnan(fv)], ofv[~np.isnan(ofv)])
+
+
+def _oracle_arrays(hb):
+    ores, oares = oracle.run_batch(hb)
+    return (np.frombuffer(ores, dtype=eng_mod.INSTANCE_RESULT_DTYPE).copy(),
+            np.frombuffer(oares, dtype=eng_mod.AGENT_RESULT_DTYPE).copy())
+
+
+def test_lane_seed_sweep_matches_oracle_and_warp_engine():
+    """70 seeds of sparse_zi_100 (more than two warps of lanes, the last one ragged): lane == oracle == warp engine."""
+    hb = lowering.HostBatch(_sweep("sparse_zi_100", range(100, 170)))
+    eng, res, ares = device_run(hb, engine="lane")
+    assert eng.engine_info() == (_abi.ENGINE_LANE, LANE_BASE + 1)
+    ores, oares = _oracle_arrays(hb)
+    _same_results(res, ares, ores, oares)
+    eng2, wres, wares = device_run(hb, engine="warp")
+    assert eng2.engine_info()[0] == _abi.ENGINE_WARP
+    _same_results(res, ares, wres, wares)
+
+
+def test_lane_rmsc03_sweep_matches_oracle():
+    """rmsc03 09:30-10:00 x 33 seeds on the lean rmsc variant (transacted-volume log, market-maker ladders, deque of 128)."""
+    hb = lowering.HostBatch(_sweep("rmsc03", range(40, 73), ["-t", "ABM", "-d", "20200603", "--end-time", "10:00:00"]))
+    eng, res, ares = device_run(hb, engine="lane")
+    assert eng.engine_info() == (_abi.ENGINE_LANE, LANE_BASE + 2)
+    ores, oares = _oracle_arrays(hb)
+    _same_results(res, ares, ores, oares)
+
+
+def test_lane_pause_and_resume_equals_one_run():
+    hb = lowering.HostBatch(_sweep("sparse_zi_100", range(5, 9)))
+    eng, res, ares = device_run(hb, engine="lane")
+    e2 = eng_mod.Engine(0)
+    e2.set_engine("lane")
+    e2.load(hb)
+    t0 = hb.instances[0].mkt_open
+    for cut in (t0 + 3600 * 10 ** 9, t0 + 2 * 3600 * 10 ** 9, t0 + 5 * 3600 * 10 ** 9):
+        e2.run(cut)
+    e2.run()
+    r2, a2 = e2.results_arrays()
+    _same_results(res, ares, r2, a2)
+    e2.reset()
+    e2.run()
+    r3, a3 = e2.results_arrays()
+    _same_results(res, ares, r3, a3)
+
+
+def test_lane_book_replay_matches_reference_orderbook():
+    g, sh = book_golden()
+    e = eng_mod.Engine(0)
+    e.set_engine("lane")
+    events, counts, states = eng_mod.replay_book(e, g["op_offset"], g["ops"], sh, 64)
+    book_check(events, counts, states, g)
+
+
+def test_lane_deep_book_fuzz_matches_oracle():
+    rows, offs = fuzz_book_rows(20261020, n_books=48)
+    e = eng_mod.Engine(0)
+    e.set_engine("lane")
+    events, counts, states = eng_mod.replay_book(e, offs, rows, 25, 96)
+    ev2, cnt2, st2 = oracle.replay_book(offs, eng_mod.make_book_ops(rows), 25, 96)
+    events_o, counts_o, states_o = eng_mod.unpack_replay(ev2, cnt2[:len(rows)], st2, len(rows), 96)
+    assert (counts <= 96).all() and np.array_equal(counts, counts_o)
+    assert np.array_equal(states, states_o)
+    assert np.array_equal(events, events_o)
+
+
+def test_lane_many_books_property():
+    rows, offs = random_book_rows(7, n_books=512)
+    e = eng_mod.Engine(0)
+    e.set_engine("lane")
+    events, counts, states = eng_mod.replay_book(e, offs, rows, 10, 64)
+    ok = (states[:, 0] < 0) | (states[:, 2] < 0) | (states[:, 0] < states[:, 2])
+    assert ok.all()
+    ex = events[events[:, 1] == 12]
+    assert ex[ex[:, 3] == 1][:, 6].sum() == ex[ex[:, 3] == 0][:, 6].sum()
+    ev2, cnt2, st2 = oracle.replay_book(offs, eng_mod.make_book_ops(rows), 10, 64)
+    events_o, counts_o, states_o = eng_mod.unpack_replay(ev2, cnt2[:len(rows)], st2, len(rows), 64)
+    assert np.array_equal(states, states_o) and np.array_equal(events, events_o)

@@ -46,6 +46,46 @@ def test_device_matches_reference_golden(name):
     assert res["slowest_agent_finish_time"][0] == meta["slowest_agent_finish_time"]
 
 
+# the kernel variant each golden's population lands on when it is loaded untraced (abides_engine_info)
+WARP_VARIANT = {"zi100_s123456789": 2, "zi1000_s123456789": 1, "rmsc03_s1234_1000": 3, "rmsc03e_s1234_1100": 3,
+                "rmsc01s_s77": 3, "rmsc01mm_s33": 4, "rmsc01_s33_1100": 4, "rmsc01_s34_1100": 4, "exec_twap_s6": 6,
+                "exec_vwap_s5": 6, "execution_s8_e": 6, "rmsc02_s22": 5, "rmsc02sub_s21_1100": 5, "rmsc02fast_s23_1100": 5,
+                "value_noise_s7": 0, "random_fund_value_s7": 3, "random_fund_diverse_s7": 0}
+LANE_VARIANT = {"zi100_s123456789": 17, "zi1000_s123456789": 16, "rmsc03_s1234_1000": 18, "rmsc03e_s1234_1100": 18,
+                "rmsc01s_s77": 18, "rmsc01mm_s33": 19, "exec_twap_s6": 19, "exec_vwap_s5": 19, "execution_s8_e": 19,
+                "value_noise_s7": 19, "random_fund_value_s7": 18, "random_fund_diverse_s7": 19}
+
+
+@pytest.mark.parametrize("engine", ["warp", "lane"])
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_untraced_lean_variant_matches_reference_golden(name, engine):
+    """The kernels the bench runs, pinned to the reference directly: each golden loaded WITHOUT a trace lands on its
+    lean kernel variant (asserted through abides_engine_info); ttl_messages, deliveries, every agent's final
+    portfolio and the last trade must equal what the unmodified reference produced (Kernel.py:204,:318-322)."""
+    if engine == "lane" and name not in LANE_VARIANT:
+        pytest.skip("population runs on the warp engine only (HBL agents / market-data subscriptions)")
+    g, meta = load_golden(name)
+    spec = build_case(name)
+    hb = lowering.HostBatch([spec, spec, spec])             # a small homogeneous batch
+    eng, res, ares = device_run(hb, engine=engine)
+    e, v = eng.engine_info()
+    assert v == (WARP_VARIANT if engine == "warp" else LANE_VARIANT)[name], (e, v)
+    for i in range(3):
+        assert res["status"][i] == 0
+        assert res["ttl_messages"][i] == meta["ttl_messages"]
+        assert res["delivered"][i] == meta["delivered"]
+        assert res["last_trade"][i] == meta["last_trade"]
+        assert res["final_time"][i] == meta["final_time"]
+        assert res["slowest_agent_finish_time"][i] == meta["slowest_agent_finish_time"]
+        sl = agent_slices(hb, i)
+        assert np.array_equal(ares["cash"][sl], g["cash"])
+        assert np.array_equal(ares["holdings"][sl], g["holdings"])
+        assert np.array_equal(ares["marked_to_market"][sl], g["mtm"])
+        fv, gfv = ares["final_valuation"][sl], g["final_valuation"]
+        assert np.array_equal(np.isnan(fv), np.isnan(gfv))
+        assert np.allclose(fv[~np.isnan(fv)], gfv[~np.isnan(gfv)], rtol=1e-9, atol=0)
+
+
 def _compare_with_oracle(hb, res, ares):
     ores, oares = oracle.run_batch(hb)
     for i in range(hb.n_instances):
