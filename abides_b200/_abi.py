@@ -49,6 +49,7 @@ class AgentType(C.Structure):
         ("exec_quantity", C.c_double), ("exec_is_buy", C.c_int32), ("exec_trade", C.c_int32),
         ("mm_min_size", C.c_int64), ("mm_max_size", C.c_int64), ("mm_num_levels", C.c_int32), ("hbl_L", C.c_int32),
         ("subscribe", C.c_int32), ("sub_levels", C.c_int32), ("subscribe_freq", C.c_double),
+        ("sigma_pv", C.c_double),
     ]
 
 
@@ -90,7 +91,14 @@ class Batch(C.Structure):
         ("mt_pos", C.POINTER(C.c_int32)),
         ("mt_has_gauss", C.POINTER(C.c_int32)),
         ("mt_gauss", C.POINTER(C.c_double)),
+        ("mt_key_row", C.POINTER(C.c_int32)),
+        ("mt_seed", C.POINTER(C.c_uint32)),
+        ("n_mt_rows", C.c_int64),
+        ("draw_flags", C.c_int32), ("reserved0", C.c_int32),
     ]
+
+
+DRAW_ZI_THETA, DRAW_MOMENTUM_SIZE = 1, 2               # enum abides_draw_flags
 
 
 class InstanceResult(C.Structure):

@@ -66,6 +66,16 @@
 namespace lane {
 #include "lane_variants.inc"
 }
+// load-time RNG work shared by both engines: seeding of streams described by their seed, constructor-time draws
+namespace rngsetup {
+#include "rng_setup_device.inc"
+__global__ void rng_materialize_kernel(const __grid_constant__ RngSetup p) {
+  rng_materialize_one(p, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x);
+}
+__global__ void rng_ctor_draws_kernel(const __grid_constant__ RngSetup p) {
+  rng_ctor_draws_one(p, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x);
+}
+}  // namespace rngsetup
 constexpr int LANE_BLOCK = 32;          // threads per block: instances are independent, small blocks spread over more SMs
 
 namespace {
@@ -511,9 +521,10 @@ struct ShapeSig {
   int ni = 0, n_types = 0, rng_mode = -1, trace_cap = -1, max_agents = 0, n_mom = 0;
   bool has_hbl = false, needs_tv = false, has_md = false;
   int lane_variant = lane::LV_NONE;     // LV_NONE: the warp-per-instance engine
-  long long na = -1, n_theta = -1;
+  long long na = -1, n_theta = -1, n_dev_rows = -1;
+  bool seeded = false;
   bool operator==(const ShapeSig& o) const {
-    return lane_variant == o.lane_variant && ni == o.ni && n_types == o.n_types && rng_mode == o.rng_mode && trace_cap == o.trace_cap &&
+    return lane_variant == o.lane_variant && n_dev_rows == o.n_dev_rows && seeded == o.seeded && ni == o.ni && n_types == o.n_types && rng_mode == o.rng_mode && trace_cap == o.trace_cap &&
            max_agents == o.max_agents && n_mom == o.n_mom && na == o.na && n_theta == o.n_theta && has_hbl == o.has_hbl && needs_tv == o.needs_tv && has_md == o.has_md;
   }
 };
@@ -535,8 +546,9 @@ struct abides_handle {
   float last_ms = 0.f, last_reset_ms = 0.f;
   int last_launches = 0;
   int launches_since_load = 0;
+  unsigned* d_mt_seed = nullptr; int* d_key_row = nullptr; int* d_dev_row = nullptr;   // compact stream description (seeded batches)
   unsigned* mt_pristine = nullptr;
-  size_t n_streams = 0;
+  size_t n_streams = 0, n_dev_rows = 0; // streams of the batch; MT19937 states resident on the device (seed-only streams have none)
   int n_mom = 0;
   ShapeSig sig;
 };
@@ -577,7 +589,7 @@ int h2d(abides_handle* h, const T* dst, const T* src, size_t count) {
 int launch_init(abides_handle* h) {
   DevBatch& d = h->db;
   if (d.rng_mode == ABIDES_RNG_MT19937)
-    CK(cudaMemcpyAsync(d.mt, h->mt_pristine, h->n_streams * ABIDES_MT_N * sizeof(unsigned), cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(d.mt, h->mt_pristine, h->n_dev_rows * ABIDES_MT_N * sizeof(unsigned), cudaMemcpyDeviceToDevice, h->stream));
   CK(cudaMemsetAsync(d.mom_ring, 0, (size_t)(h->n_mom > 0 ? h->n_mom : 1) * MOM_RING * sizeof(double), h->stream));
   CK(cudaMemsetAsync(d.res, 0, (size_t)d.n_instances * sizeof(abides_instance_result), h->stream));
   CK(cudaMemsetAsync(d.prof, 0, N_PROF * sizeof(unsigned long long), h->stream));
@@ -677,8 +689,14 @@ int abides_load(abides_handle* h, const abides_batch* b) {
   if (b->n_instances <= 0 || !b->instances || !b->types || !b->agent_type || !b->lat_to_exch || !b->lat_from_exch ||
       !b->agent_size || !b->agent_wakeup_time || !b->agent_theta)
     return fail(ABIDES_EINVAL, "abides_load: missing table");
-  if (b->rng_mode == ABIDES_RNG_MT19937 && (!b->mt_key || !b->mt_pos || !b->mt_has_gauss || !b->mt_gauss))
+  const bool seeded = b->mt_key_row != nullptr;
+  if (b->rng_mode == ABIDES_RNG_MT19937 && (!b->mt_pos || !b->mt_has_gauss || !b->mt_gauss || (!seeded && !b->mt_key)))
     return fail(ABIDES_EINVAL, "abides_load: MT19937 mode needs mt_key/mt_pos/mt_has_gauss/mt_gauss");
+  if (seeded && (b->rng_mode != ABIDES_RNG_MT19937 || !b->mt_seed || b->n_mt_rows < 0 || (b->n_mt_rows > 0 && !b->mt_key)))
+    return fail(ABIDES_EINVAL, "abides_load: mt_key_row needs MT19937 mode, mt_seed and n_mt_rows rows of mt_key");
+  if (b->draw_flags & ~(ABIDES_DRAW_ZI_THETA | ABIDES_DRAW_MOMENTUM_SIZE)) return fail(ABIDES_EINVAL, "abides_load: unknown draw_flags");
+  if (b->draw_flags && b->rng_mode != ABIDES_RNG_MT19937) return fail(ABIDES_EINVAL, "abides_load: draw_flags need MT19937 streams");
+  const bool draw_theta = (b->draw_flags & ABIDES_DRAW_ZI_THETA) != 0;
   if (b->rng_mode != ABIDES_RNG_MT19937 && b->rng_mode != ABIDES_RNG_PHILOX) return fail(ABIDES_EINVAL, "abides_load: bad rng_mode");
   CK(cudaSetDevice(h->device));
   int ni = b->n_instances;
@@ -714,7 +732,10 @@ int abides_load(abides_handle* h, const abides_batch* b) {
         n_sub++;
       } else if (k == ABIDES_SUBSCRIPTION) return fail(ABIDES_EINVAL, "abides_load: SubscriptionAgent without subscribe");
       if (k == ABIDES_MOMENTUM) mom_index[off + a] = n_mom++;
-      if ((k == ABIDES_ZI || k == ABIDES_HBL) && (b->agent_theta[off + a] < 0 || !b->theta)) return fail(ABIDES_EINVAL, "abides_load: ZI / HBL agent without theta");
+      if ((k == ABIDES_ZI || k == ABIDES_HBL) && (b->agent_theta[off + a] < 0 || (!b->theta && !draw_theta))) return fail(ABIDES_EINVAL, "abides_load: ZI / HBL agent without theta");
+      if ((k == ABIDES_ZI || k == ABIDES_HBL) && draw_theta && (!(b->types[t].sigma_pv >= 0) || b->types[t].q_max < 1 ||
+          ic.theta_offset + b->agent_theta[off + a] + 2ll * b->types[t].q_max > b->n_theta_total))
+        return fail(ABIDES_EINVAL, "abides_load: ABIDES_DRAW_ZI_THETA needs sigma_pv, q_max and room for 2 q_max values per agent");
       if (k == ABIDES_SCHEDULE_EXEC && b->types[t].exec_trade) {
         const abides_agent_type& ty = b->types[t];
         if (ty.wake_up_freq <= 0 || ty.exec_end_time < ty.exec_start_time + 2 * ty.wake_up_freq ||
@@ -750,6 +771,22 @@ int abides_load(abides_handle* h, const abides_batch* b) {
   }
   sig.lane_variant = lane_variant;
   const bool use_lane = lane_variant != lane::LV_NONE;
+  // MT19937 states on the device: one row per stream, except that the lane engine keeps NOISE agents' seeded streams
+  // as their seed only (they draw one or two words a day, NoiseAgent.py:162)
+  const size_t ns_all = (size_t)na + (size_t)ABIDES_EXTRA_STREAMS * ni;
+  std::vector<int> dev_row;
+  size_t n_dev_rows = ns_all;
+  if (seeded) {
+    for (size_t s2 = 0; s2 < ns_all; s2++)
+      if (b->mt_key_row[s2] >= b->n_mt_rows || b->mt_key_row[s2] < -1 || (b->mt_key_row[s2] < 0 && b->mt_pos[s2] < 0))
+        return fail(ABIDES_EINVAL, "abides_load: bad mt_key_row / mt_pos");
+    if (use_lane) {
+      n_dev_rows = lane::lane_assign_rows(b, dev_row);
+      if (n_dev_rows > 0x7fffffffull) return fail(ABIDES_EINVAL, "abides_load: too many streams");
+    }
+  }
+  sig.seeded = seeded;
+  sig.n_dev_rows = (long long)n_dev_rows;
   const lane::LaneCaps lcap = lane::lane_caps(max_agents, lane_variant, needs_tv);
   DevBatch& d = h->db;
   int rc;
@@ -776,8 +813,13 @@ int abides_load(abides_handle* h, const abides_batch* b) {
     d.agent_theta = dath; d.theta = dth; d.mom_index = dmi;
     if (b->rng_mode == ABIDES_RNG_MT19937) {
       int *dpos, *dhg; double* dg;
-      if ((rc = dev_alloc(h, &d.mt, ns * ABIDES_MT_N))) return rc;
-      if ((rc = dev_alloc(h, &h->mt_pristine, ns * ABIDES_MT_N))) return rc;
+      if ((rc = dev_alloc(h, &d.mt, n_dev_rows * ABIDES_MT_N))) return rc;
+      if ((rc = dev_alloc(h, &h->mt_pristine, n_dev_rows * ABIDES_MT_N))) return rc;
+      if (seeded) {
+        if ((rc = dev_alloc(h, &h->d_mt_seed, ns))) return rc;
+        if ((rc = dev_alloc(h, &h->d_key_row, ns))) return rc;
+        if (use_lane) { if ((rc = dev_alloc(h, &h->d_dev_row, ns))) return rc; }
+      }
       if ((rc = dev_alloc(h, &dpos, ns))) return rc;
       if ((rc = dev_alloc(h, &dhg, ns))) return rc;
       if ((rc = dev_alloc(h, &dg, ns))) return rc;
@@ -841,14 +883,14 @@ int abides_load(abides_handle* h, const abides_batch* b) {
       lb.cfg = d.cfg; lb.types = d.types; lb.type_log1mk = d.type_log1mk; lb.type_omp2 = d.type_omp2;
       lb.agent_type = d.agent_type; lb.lat_to = d.lat_to; lb.lat_from = d.lat_from; lb.size = d.size;
       lb.wakeup_time = d.wakeup_time; lb.agent_theta = d.agent_theta; lb.theta = d.theta; lb.mom_index = d.mom_index;
-      lb.mt = d.mt; lb.mt_row = nullptr; lb.mt_seed = nullptr;
+      lb.mt = d.mt; lb.mt_row = seeded ? h->d_dev_row : nullptr; lb.mt_seed = seeded ? h->d_mt_seed : nullptr;
       lb.mt_pos = d.mt_pos; lb.mt_has_gauss = d.mt_has_gauss; lb.mt_gauss = d.mt_gauss;
       lb.mom_ring = d.mom_ring; lb.trace = d.trace; lb.res = d.res; lb.ares = d.ares;
     }
     h->sig = sig;
   }
   h->lane_variant = lane_variant;
-  h->n_streams = ns; h->n_mom = n_mom;
+  h->n_streams = ns; h->n_mom = n_mom; h->n_dev_rows = n_dev_rows;
   // kernel variant: the leanest one whose feature set covers the batch (engine_device.inc)
   h->variant = VAR_FULL;
   if (b->rng_mode == ABIDES_RNG_MT19937 && b->trace_capacity == 0) {
@@ -871,13 +913,48 @@ int abides_load(abides_handle* h, const abides_batch* b) {
   if ((rc = h2d(h, d.size, reinterpret_cast<const long long*>(b->agent_size), (size_t)na))) return rc;
   if ((rc = h2d(h, d.wakeup_time, reinterpret_cast<const long long*>(b->agent_wakeup_time), (size_t)na))) return rc;
   if ((rc = h2d(h, d.agent_theta, b->agent_theta, (size_t)na))) return rc;
-  if ((rc = h2d(h, d.theta, b->theta, (size_t)(b->n_theta_total > 0 ? b->n_theta_total : 0)))) return rc;
+  if (!draw_theta && (rc = h2d(h, d.theta, b->theta, (size_t)(b->n_theta_total > 0 ? b->n_theta_total : 0)))) return rc;
   if ((rc = h2d(h, d.mom_index, mom_index.data(), (size_t)na))) return rc;
   if (b->rng_mode == ABIDES_RNG_MT19937) {
-    if ((rc = h2d(h, (const unsigned*)h->mt_pristine, b->mt_key, ns * ABIDES_MT_N))) return rc;
+    unsigned* staging = nullptr;
+    if (!seeded) {
+      if ((rc = h2d(h, (const unsigned*)h->mt_pristine, b->mt_key, ns * ABIDES_MT_N))) return rc;
+    } else if (b->n_mt_rows > 0) {
+      if (use_lane) {                           // uploaded rows keep their index: straight into place
+        if ((rc = h2d(h, (const unsigned*)h->mt_pristine, b->mt_key, (size_t)b->n_mt_rows * ABIDES_MT_N))) return rc;
+      } else {                                  // the warp engine indexes rows by stream: scatter from a staging copy
+        cudaError_t e = cudaMalloc(&staging, (size_t)b->n_mt_rows * ABIDES_MT_N * sizeof(unsigned));
+        if (e != cudaSuccess) return fail(ABIDES_ENOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+        if ((rc = h2d(h, (const unsigned*)staging, b->mt_key, (size_t)b->n_mt_rows * ABIDES_MT_N))) { cudaFree(staging); return rc; }
+      }
+    }
     if ((rc = h2d(h, d.mt_pos, b->mt_pos, ns))) return rc;
     if ((rc = h2d(h, d.mt_has_gauss, b->mt_has_gauss, ns))) return rc;
     if ((rc = h2d(h, d.mt_gauss, b->mt_gauss, ns))) return rc;
+    if (seeded) {
+      if ((rc = h2d(h, (const unsigned*)h->d_mt_seed, b->mt_seed, ns))) return rc;
+      if ((rc = h2d(h, (const int*)h->d_key_row, b->mt_key_row, ns))) return rc;
+      if (use_lane && (rc = h2d(h, (const int*)h->d_dev_row, dev_row.data(), ns))) return rc;
+    }
+    if (seeded || b->draw_flags) {
+      // seed / fast-forward the described streams, then the agents' constructor draws: once, into the pristine copy
+      rngsetup::RngSetup p;
+      memset(&p, 0, sizeof p);
+      p.n_instances = ni; p.draw_flags = b->draw_flags;
+      p.cfg = d.cfg; p.types = d.types; p.agent_type = d.agent_type; p.agent_theta = d.agent_theta;
+      p.theta = const_cast<int*>(d.theta); p.size = const_cast<long long*>(d.size);
+      p.mt = h->mt_pristine; p.staging = staging;
+      p.key_row = seeded ? h->d_key_row : nullptr; p.dev_row = (seeded && use_lane) ? h->d_dev_row : nullptr;
+      p.seed = h->d_mt_seed;
+      p.pos = const_cast<int*>(d.mt_pos); p.has_gauss = const_cast<int*>(d.mt_has_gauss); p.gauss = const_cast<double*>(d.mt_gauss);
+      const dim3 grid((max_agents + ABIDES_EXTRA_STREAMS + 63) / 64, ni);
+      if (seeded) rngsetup::rng_materialize_kernel<<<grid, 64, 0, h->stream>>>(p);
+      if (b->draw_flags) rngsetup::rng_ctor_draws_kernel<<<grid, 64, 0, h->stream>>>(p);
+      cudaError_t e = cudaGetLastError();
+      if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+      if (staging) cudaFree(staging);
+      if (e != cudaSuccess) return fail(ABIDES_ECUDA, std::string("rng setup: ") + cudaGetErrorString(e));
+    }
   }
   h->launches_since_load = 0;
   if ((rc = launch_init(h))) return rc;

@@ -2,6 +2,7 @@
 // which kernel variant covers a batch, and the per-instance capacities of its device structures.
 #ifndef ABIDES_LANE_HOST_COMMON_H
 #define ABIDES_LANE_HOST_COMMON_H
+#include <vector>
 #include "lane_types.h"
 
 namespace lane {
@@ -25,6 +26,28 @@ inline int lane_pick_variant(unsigned class_mask, unsigned lat_mask, int rng_mod
   if ((class_mask & ~rmsc) == 0 && lat_mask == (1u << ABIDES_LAT_DETERMINISTIC)) return LV_RMSC;
   if ((class_mask & ~full) == 0) return LV_FULL;
   return LV_NONE;
+}
+
+// Device rows of the MT19937 states of a batch whose streams are described by their seeds (abides_batch.mt_key_row):
+// uploaded rows keep their index, seeded streams follow, except that NOISE agents' seeded streams get no row at all
+// (-1): they draw one or two words a day (NoiseAgent.py:162), which the lane engine recomputes from the seed.
+inline size_t lane_assign_rows(const abides_batch* b, std::vector<int>& dev_row) {
+  const size_t ns = (size_t)b->n_agents_total + (size_t)ABIDES_EXTRA_STREAMS * b->n_instances;
+  dev_row.assign(ns, -1);
+  size_t next = (size_t)b->n_mt_rows;
+  for (int i = 0; i < b->n_instances; i++) {
+    const abides_instance_cfg& ic = b->instances[i];
+    const size_t s0 = (size_t)ic.agent_offset + (size_t)ABIDES_EXTRA_STREAMS * i;
+    for (int a = 0; a < ic.n_agents + ABIDES_EXTRA_STREAMS; a++) {
+      const size_t s = s0 + a;
+      if (b->mt_key_row[s] >= 0) { dev_row[s] = b->mt_key_row[s]; continue; }
+      const bool lazy = a > 0 && a < ic.n_agents &&
+                        b->types[ic.type_base + b->agent_type[ic.agent_offset + a]].klass == ABIDES_NOISE &&
+                        b->mt_pos[s] < LAZY_MAX_WORDS / 2;
+      dev_row[s] = lazy ? -1 : (int)next++;
+    }
+  }
+  return next;
 }
 
 struct LaneCaps { int hcap, scap, arena_cap, deep_cap, txn_cap, unr_cap, top_k; };

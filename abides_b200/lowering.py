@@ -188,6 +188,8 @@ class InstanceSpec:
         self.mt_gauss = None
         self.agent_names = []
         self.agent_type_names = []
+        self.device_draws = {}     # constructor arguments the device needs when IT performs the agents' own-stream
+                                   # constructor draws (sweep.SeededBatch): sigma_pv, momentum_size_range
 
     @property
     def n_agents(self):
@@ -237,6 +239,10 @@ def lower_instance(agents, startTime, stopTime, defaultComputationDelay=1, defau
         if k == _abi.NOISE:
             wt = a.wakeup_time
             wake[i] = _ns(wt[0] if isinstance(wt, tuple) else wt)
+        if k in (_abi.ZI, _abi.HBL):
+            spec.device_draws["sigma_pv"] = float(a.sigma_pv)
+        if k == _abi.MOMENTUM:
+            spec.device_draws["momentum_size_range"] = (int(a.min_size), int(a.max_size))
         if k in (_abi.ZI, _abi.HBL):
             th = [int(x) for x in a.theta]
             if len(th) != 2 * int(a.q_max):

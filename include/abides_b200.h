@@ -99,6 +99,8 @@ typedef struct abides_agent_type {
   int32_t subscribe;
   int32_t sub_levels;
   double  subscribe_freq;
+  double  sigma_pv;           /* ZI / HBL private-value variance (ZeroIntelligenceAgent.py:46-50); only read when the
+                                 device draws theta itself (ABIDES_DRAW_ZI_THETA) */
 } abides_agent_type;
 #define ABIDES_MD_MAX_LEVELS 8
 
@@ -145,11 +147,33 @@ typedef struct abides_batch {
   /* MT19937 mode: one stream per agent row plus ABIDES_EXTRA_STREAMS per instance, laid out as
    * stream(inst, s) = agent_offset + ABIDES_EXTRA_STREAMS*inst + s, s < n_agents for agent streams,
    * s = n_agents + ABIDES_STREAM_* for the extra ones.  NULL in Philox mode. */
-  const uint32_t* mt_key;                 /* [n_streams][624] */
+  const uint32_t* mt_key;                 /* [n_streams][624] ([n_mt_rows][624] when mt_key_row is given) */
   const int32_t*  mt_pos;                 /* [n_streams] */
   const int32_t*  mt_has_gauss;           /* [n_streams] */
   const double*   mt_gauss;               /* [n_streams] */
+  /* Compact stream description (optional; NULL / 0 = every stream carries its full state, row = stream).  A seed sweep
+   * of n instances of a 1000-agent config has 10^3 n streams of 2.5 KB each, but every one of them is
+   * np.random.RandomState(seed) after a known number of draws -- so the host may hand over the seed and the device
+   * runs init_genrand and the draws itself:
+   *   mt_key_row[s] >= 0 : row of stream s's 624-word state in mt_key (mt_pos = numpy's position in it);
+   *   mt_key_row[s] == -1: stream s is RandomState(seed = mt_seed[s]) from which mt_pos[s] 32-bit words have been
+   *                        drawn so far; mt_has_gauss / mt_gauss are numpy's cached gaussian at that point. */
+  const int32_t*  mt_key_row;             /* [n_streams] or NULL */
+  const uint32_t* mt_seed;                /* [n_streams] or NULL */
+  int64_t n_mt_rows;                      /* rows of mt_key when mt_key_row is given */
+  /* constructor-time draws the device performs from the agents' own (seeded) streams, enum abides_draw_flags */
+  int32_t draw_flags;
+  int32_t reserved0;
 } abides_batch;
+
+enum abides_draw_flags {
+  /* `theta` is not given (agent_theta holds the layout only): every ZI / HBL agent draws
+   * sorted(round(random_state.normal(0, sqrt(sigma_pv), 2 * q_max)), reverse=True)   ZeroIntelligenceAgent.py:46-50 */
+  ABIDES_DRAW_ZI_THETA = 1,
+  /* agent_size of momentum agents is not given: size = random_state.randint(mm_min_size, mm_max_size)
+   * (agent/examples/MomentumAgent.py:21; the type row's mm_min_size / mm_max_size carry min_size / max_size) */
+  ABIDES_DRAW_MOMENTUM_SIZE = 2
+};
 
 /* Per-instance result (the record gathered at the end). */
 typedef struct abides_instance_result {

@@ -13,7 +13,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np                                    # noqa: E402
-from abides_b200 import lowering, runtime             # noqa: E402
+from abides_b200 import lowering, runtime, sweep      # noqa: E402
 from abides_b200.engine import Engine                 # noqa: E402
 import bench                                          # noqa: E402
 
@@ -31,13 +31,16 @@ def main():
     cfg, extra = bench.WORKLOADS[workload]
     seeds = runtime.parallel_seeds(20261019, n)
     t0 = time.time()
-    specs = runtime.build_specs_parallel(cfg, [list(extra) + ["-s", s] for s in seeds])
-    need = 2 * sum(s.mt_key.nbytes for s in specs[:1]) * n / 1e9
-    if need > 0.6 * mem_available_gb():
-        print(json.dumps({"workload": workload, "instances": n, "skipped": "needs %.0f GB of host memory" % need}))
-        return
-    hb = lowering.HostBatch(specs)
-    del specs
+    if sweep.supported(cfg) and not os.environ.get("ABIDES_FULL_STATE_UPLOAD"):
+        hb = sweep.build_sweep(cfg, seeds, extra)             # streams by seed, vectorised config-time draws
+    else:
+        specs = runtime.build_specs_parallel(cfg, [list(extra) + ["-s", s] for s in seeds])
+        need = 2 * sum(s.mt_key.nbytes for s in specs[:1]) * n / 1e9
+        if need > 0.6 * mem_available_gb():
+            print(json.dumps({"workload": workload, "instances": n, "skipped": "needs %.0f GB of host memory" % need}))
+            return
+        hb = lowering.HostBatch(specs)
+        del specs
     build_s = time.time() - t0
     digests = {}
     for name in engines:

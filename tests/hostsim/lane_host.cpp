@@ -25,6 +25,9 @@ namespace lane {
 static thread_local int g_thread_index = 0;
 #include "lane_variants.inc"
 }  // namespace lane
+namespace rngsetup {
+#include "rng_setup_device.inc"
+}
 
 using namespace lane;
 
@@ -84,12 +87,39 @@ int hostsim_run(const abides_batch* b, int force_variant, abides_instance_result
   lb.type_log1mk = own.keep(zalloc<abm_dd>(b->n_types));
   lb.type_omp2 = own.keep(zalloc<double>(b->n_types));
   lb.agent_type = b->agent_type; lb.lat_to = b->lat_to_exch; lb.lat_from = b->lat_from_exch;
-  lb.size = (const long long*)b->agent_size; lb.wakeup_time = (const long long*)b->agent_wakeup_time;
-  lb.agent_theta = b->agent_theta; lb.theta = b->theta;
+  lb.wakeup_time = (const long long*)b->agent_wakeup_time;
+  lb.agent_theta = b->agent_theta;
   lb.mom_index = mom_index.data();
-  lb.mt = own.keep(dup<unsigned>(b->mt_key, ns * ABIDES_MT_N));
-  lb.mt_row = nullptr; lb.mt_seed = nullptr;
-  lb.mt_pos = b->mt_pos; lb.mt_has_gauss = b->mt_has_gauss; lb.mt_gauss = b->mt_gauss;
+  // the loader's RNG work (abides_load): rows, seeding, constructor draws -- on writable copies of the tables
+  const bool seeded = b->mt_key_row != nullptr;
+  std::vector<int> dev_row;
+  size_t n_rows = ns;
+  if (seeded) n_rows = lane_assign_rows(b, dev_row);
+  unsigned* mt = own.keep(zalloc<unsigned>(n_rows * ABIDES_MT_N));
+  if (b->mt_key) memcpy(mt, b->mt_key, (seeded ? (size_t)b->n_mt_rows : ns) * ABIDES_MT_N * sizeof(unsigned));
+  int* pos = own.keep(dup<int>(b->mt_pos, ns));
+  int* hg = own.keep(dup<int>(b->mt_has_gauss, ns));
+  double* gs = own.keep(dup<double>(b->mt_gauss, ns));
+  int* theta = own.keep(zalloc<int>((size_t)b->n_theta_total + 1));
+  if (!(b->draw_flags & ABIDES_DRAW_ZI_THETA) && b->theta) memcpy(theta, b->theta, (size_t)b->n_theta_total * sizeof(int));
+  long long* size = own.keep(dup<long long>((const long long*)b->agent_size, (size_t)na));
+  if (seeded || b->draw_flags) {
+    rngsetup::RngSetup p;
+    memset(&p, 0, sizeof p);
+    p.n_instances = ni; p.draw_flags = b->draw_flags; p.cfg = b->instances; p.types = b->types;
+    p.agent_type = b->agent_type; p.agent_theta = b->agent_theta; p.theta = theta; p.size = size;
+    p.mt = mt; p.staging = nullptr; p.key_row = b->mt_key_row; p.dev_row = seeded ? dev_row.data() : nullptr;
+    p.seed = b->mt_seed; p.pos = pos; p.has_gauss = hg; p.gauss = gs;
+    for (int i = 0; i < ni; i++) {
+      const int n = b->instances[i].n_agents + ABIDES_EXTRA_STREAMS;
+      if (seeded) for (int a = 0; a < n; a++) rngsetup::rng_materialize_one(p, i, a);
+      if (b->draw_flags) for (int a = 0; a < n; a++) rngsetup::rng_ctor_draws_one(p, i, a);
+    }
+  }
+  lb.theta = theta; lb.size = size;
+  lb.mt = mt;
+  lb.mt_row = seeded ? dev_row.data() : nullptr; lb.mt_seed = b->mt_seed;
+  lb.mt_pos = pos; lb.mt_has_gauss = hg; lb.mt_gauss = gs;
   lb.agents = own.keep((LAgent*)aligned_alloc(128, sizeof(LAgent) * (size_t)(na ? na : 1)));
   lb.state = own.keep(zalloc<LHot>(ni));
   lb.hkeys = own.keep(zalloc<LKey>((size_t)ni * heap_stride(cap.hcap)));

@@ -123,3 +123,19 @@ def test_lane_many_books_property():
     ev2, cnt2, st2 = oracle.replay_book(offs, eng_mod.make_book_ops(rows), 10, 64)
     events_o, counts_o, states_o = eng_mod.unpack_replay(ev2, cnt2[:len(rows)], st2, len(rows), 64)
     assert np.array_equal(states, states_o) and np.array_equal(events, events_o)
+
+
+@pytest.mark.parametrize("engine", ["lane", "warp"])
+@pytest.mark.parametrize("config, extra, seeds", [
+    ("sparse_zi_100", [], list(range(200, 240))), ("sparse_zi_1000", [], [5, 6, 7]),
+    ("rmsc03", ["-t", "ABM", "-d", "20200603", "--end-time", "10:00:00"], list(range(40, 45)))])
+def test_seeded_sweep_equals_config_built_instances_on_device(config, extra, seeds, engine):
+    """Streams handed over as seeds (abides_batch.mt_seed): the device seeds them, fast-forwards the global stream past
+    the N x N latency draw, draws the ZI private values and momentum sizes, and -- on the lane engine -- keeps the
+    noise agents' streams as seeds.  Same days as the config-built, fully uploaded batch, on both engines."""
+    from abides_b200 import sweep
+    sb = sweep.build_sweep(config, seeds, extra)
+    eng, res, ares = device_run(sb, engine=engine)
+    hb = lowering.HostBatch(_sweep(config, seeds, extra))
+    ores, oares = _oracle_arrays(hb)
+    _same_results(res, ares, ores, oares)

@@ -115,3 +115,48 @@ def test_lane_shallow_books_match_oracle():
     a = _unpack(*hostsim.replay_book(offs, ops, 10, 64), n, 64)
     b = _unpack(*oracle.replay_book(offs, ops, 10, 64), n, 64)
     assert np.array_equal(a[2], b[2]) and np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+SWEEPS = [("sparse_zi_100", [], [11, 12, 13]), ("sparse_zi_1000", [], [5, 6]),
+          ("rmsc03", ["-t", "ABM", "-d", "20200603", "--end-time", "10:00:00"], [40, 41, 42])]
+
+
+@pytest.mark.parametrize("config, extra, seeds", SWEEPS)
+def test_seeded_sweep_equals_config_built_instances(config, extra, seeds):
+    """sweep.build_sweep (vectorised config-time draws, streams handed over as seeds, ZI private values / momentum
+    sizes / noise agents' few words drawn by the engine itself) runs exactly the days that executing the config
+    module once per seed and uploading every MT19937 state does."""
+    from abides_b200 import sweep
+    sb = sweep.build_sweep(config, seeds, extra)
+    assert sb.h2d_bytes() < 80 * sb.n_agents_total + 4096                   # no 2.5 KB states travel
+    res, ares, _, _, var = hostsim.run(sb)
+    specs = [s for s, _ in runtime.build_instances(config, [list(extra) + ["-s", str(s)] for s in seeds])]
+    hb = lowering.HostBatch(specs)
+    res2, ares2, _, _, var2 = hostsim.run(hb)
+    assert var == var2 and (res["status"] == 0).all()
+    for f in res.dtype.names:
+        if f != "reserved":
+            assert np.array_equal(res[f], res2[f]), f
+    for f in ("cash", "holdings", "marked_to_market"):
+        assert np.array_equal(ares[f], ares2[f]), f
+    # and the oracle agrees on the config-built batch
+    ores, oares = oracle.run_batch(hb)
+    assert [int(ores[i].ttl_messages) for i in range(len(seeds))] == [int(x) for x in res["ttl_messages"]]
+
+
+def test_vec_random_state_is_numpy_legacy_random_state():
+    from abides_b200.vecrng import VecRandomState
+    seeds = np.random.RandomState(5).randint(0, 2 ** 32, size=32, dtype='uint64')
+    v = VecRandomState(seeds)
+    refs = [np.random.RandomState(seed=s) for s in seeds]
+    for it in range(160):
+        assert np.array_equal(v.randint(0, 2 ** 32), [r.randint(0, 2 ** 32, dtype='uint64') for r in refs])
+        assert np.array_equal(v.rand(), [r.rand() for r in refs])
+        assert np.array_equal(v.randint(0, 100), [r.randint(0, 100) for r in refs])
+        assert np.array_equal(v.randint(20, 50), [r.randint(20, 50) for r in refs])
+        assert np.array_equal(v.uniform(21000, 13000000), [r.uniform(21000, 13000000) for r in refs])
+        assert np.array_equal(v.normal(1e3, np.sqrt(5e4)), [r.normal(1e3, np.sqrt(5e4)) for r in refs])
+        assert np.array_equal(v.exponential(3.6e12), [r.exponential(3.6e12) for r in refs])
+    for i in (0, 31):
+        st, mine = refs[i].get_state(), v.numpy_state(i)
+        assert np.array_equal(st[1], mine[1]) and tuple(st[2:]) == tuple(mine[2:])
