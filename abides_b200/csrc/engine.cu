@@ -70,10 +70,60 @@ namespace lane {
 namespace rngsetup {
 #include "rng_setup_device.inc"
 __global__ void rng_materialize_kernel(const __grid_constant__ RngSetup p) {
-  rng_materialize_one(p, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x);
+  rng_materialize_one(p, blockIdx.x, blockIdx.y * blockDim.x + threadIdx.x);
 }
 __global__ void rng_ctor_draws_kernel(const __grid_constant__ RngSetup p) {
-  rng_ctor_draws_one(p, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x);
+  rng_ctor_draws_one(p, blockIdx.x, blockIdx.y * blockDim.x + threadIdx.x);
+}
+// Streams from which the config drew millions of words before the simulation starts (the sparse_zi configs draw an
+// N x N latency matrix from the global stream and read one row of it): one WARP per stream, state in shared memory,
+// every generation step of 624 words done by the 32 lanes together.
+constexpr int SKIP_MIN_WORDS = 16 * ABIDES_MT_N;
+constexpr int SKIP_WARPS = 4;
+__device__ __forceinline__ void coop_twist(unsigned* mt, int lane) {
+  const unsigned U = 0x80000000u, L = 0x7fffffffu, MAG = 0x9908b0dfu;
+#pragma unroll 1
+  for (int base = 0; base < 227; base += 32) {
+    const int k = base + lane; const bool act = k < 227; unsigned v = 0;
+    if (act) { const unsigned y = (mt[k] & U) | (mt[k + 1] & L); v = mt[k + 397] ^ (y >> 1) ^ ((y & 1u) ? MAG : 0u); }
+    __syncwarp();
+    if (act) mt[k] = v;
+    __syncwarp();
+  }
+#pragma unroll 1
+  for (int base = 227; base < 623; base += 32) {
+    const int k = base + lane; const bool act = k < 623; unsigned v = 0;
+    if (act) { const unsigned y = (mt[k] & U) | (mt[k + 1] & L); v = mt[k - 227] ^ (y >> 1) ^ ((y & 1u) ? MAG : 0u); }
+    __syncwarp();
+    if (act) mt[k] = v;
+    __syncwarp();
+  }
+  if (lane == 0) { const unsigned y = (mt[623] & U) | (mt[0] & L); mt[623] = mt[396] ^ (y >> 1) ^ ((y & 1u) ? MAG : 0u); }
+  __syncwarp();
+}
+__global__ void __launch_bounds__(32 * SKIP_WARPS) rng_skip_kernel(const __grid_constant__ RngSetup p, const int* list, int n) {
+  __shared__ unsigned s_mt[SKIP_WARPS][ABIDES_MT_N];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int i = blockIdx.x * SKIP_WARPS + w;
+  if (i >= n) return;
+  const long long s = list[i];
+  const long long row = p.dev_row ? (long long)p.dev_row[s] : s;
+  if (row < 0) return;
+  unsigned* mt = s_mt[w];
+  if (lane == 0) {
+    unsigned x = p.seed[s];
+    mt[0] = x;
+    for (int j = 1; j < ABIDES_MT_N; j++) { x = 1812433253u * (x ^ (x >> 30)) + (unsigned)j; mt[j] = x; }
+  }
+  __syncwarp();
+  const long long k = p.pos[s];
+  const long long twists = (k + ABIDES_MT_N - 1) / ABIDES_MT_N;
+#pragma unroll 1
+  for (long long t = 0; t < twists; t++) coop_twist(mt, lane);
+  unsigned* out = p.mt + (size_t)row * ABIDES_MT_N;
+  for (int j = lane; j < ABIDES_MT_N; j += 32) out[j] = mt[j];
+  __syncwarp();
+  if (lane == 0) p.pos[s] = (int)(k - (twists - 1) * ABIDES_MT_N);
 }
 }  // namespace rngsetup
 constexpr int LANE_BLOCK = 32;          // threads per block: instances are independent, small blocks spread over more SMs
@@ -521,10 +571,10 @@ struct ShapeSig {
   int ni = 0, n_types = 0, rng_mode = -1, trace_cap = -1, max_agents = 0, n_mom = 0;
   bool has_hbl = false, needs_tv = false, has_md = false;
   int lane_variant = lane::LV_NONE;     // LV_NONE: the warp-per-instance engine
-  long long na = -1, n_theta = -1, n_dev_rows = -1;
+  long long na = -1, n_theta = -1, n_dev_rows = -1, n_mt_rows = 0, n_skip = 0;
   bool seeded = false;
   bool operator==(const ShapeSig& o) const {
-    return lane_variant == o.lane_variant && n_dev_rows == o.n_dev_rows && seeded == o.seeded && ni == o.ni && n_types == o.n_types && rng_mode == o.rng_mode && trace_cap == o.trace_cap &&
+    return lane_variant == o.lane_variant && n_dev_rows == o.n_dev_rows && seeded == o.seeded && n_mt_rows == o.n_mt_rows && n_skip == o.n_skip && ni == o.ni && n_types == o.n_types && rng_mode == o.rng_mode && trace_cap == o.trace_cap &&
            max_agents == o.max_agents && n_mom == o.n_mom && na == o.na && n_theta == o.n_theta && has_hbl == o.has_hbl && needs_tv == o.needs_tv && has_md == o.has_md;
   }
 };
@@ -547,6 +597,12 @@ struct abides_handle {
   int last_launches = 0;
   int launches_since_load = 0;
   unsigned* d_mt_seed = nullptr; int* d_key_row = nullptr; int* d_dev_row = nullptr;   // compact stream description (seeded batches)
+  // seeded batches without uploaded rows keep no pristine copy of the states: every (re)initialisation seeds them again
+  bool rematerialize = false;
+  rngsetup::RngSetup rs{};
+  int *pos0 = nullptr, *hg0 = nullptr; double* g0 = nullptr;    // the uploaded per-stream tables (rng setup rewrites the live ones)
+  int* d_skip_list = nullptr; int n_skip = 0;
+  int max_agents = 0;
   unsigned* mt_pristine = nullptr;
   size_t n_streams = 0, n_dev_rows = 0; // streams of the batch; MT19937 states resident on the device (seed-only streams have none)
   int n_mom = 0;
@@ -586,9 +642,34 @@ int h2d(abides_handle* h, const T* dst, const T* src, size_t count) {
   if (count) CK(cudaMemcpyAsync(const_cast<T*>(dst), src, count * sizeof(T), cudaMemcpyHostToDevice, h->stream));
   return 0;
 }
+// seed / fast-forward the streams the host described by their seeds, then the agents' constructor draws, into `mt`
+int run_rng_setup(abides_handle* h, unsigned* mt, const unsigned* staging) {
+  DevBatch& d = h->db;
+  rngsetup::RngSetup p = h->rs;
+  p.mt = mt; p.staging = staging;
+  if (h->rematerialize) {
+    const size_t ns = h->n_streams;
+    CK(cudaMemcpyAsync(const_cast<int*>(d.mt_pos), h->pos0, ns * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(const_cast<int*>(d.mt_has_gauss), h->hg0, ns * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(const_cast<double*>(d.mt_gauss), h->g0, ns * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  }
+  const dim3 grid(d.n_instances, (h->max_agents + ABIDES_EXTRA_STREAMS + 63) / 64);
+  if (p.key_row) {
+    rngsetup::rng_materialize_kernel<<<grid, 64, 0, h->stream>>>(p);
+    if (h->n_skip > 0)
+      rngsetup::rng_skip_kernel<<<(h->n_skip + rngsetup::SKIP_WARPS - 1) / rngsetup::SKIP_WARPS, 32 * rngsetup::SKIP_WARPS, 0, h->stream>>>(
+          p, h->d_skip_list, h->n_skip);
+    h->launches_since_load += 1 + (h->n_skip > 0);
+  }
+  if (p.draw_flags) { rngsetup::rng_ctor_draws_kernel<<<grid, 64, 0, h->stream>>>(p); h->launches_since_load += 1; }
+  CK(cudaGetLastError());
+  return 0;
+}
+
 int launch_init(abides_handle* h) {
   DevBatch& d = h->db;
-  if (d.rng_mode == ABIDES_RNG_MT19937)
+  if (d.rng_mode == ABIDES_RNG_MT19937 && h->rematerialize) { int rc = run_rng_setup(h, d.mt, nullptr); if (rc) return rc; }
+  else if (d.rng_mode == ABIDES_RNG_MT19937)
     CK(cudaMemcpyAsync(d.mt, h->mt_pristine, h->n_dev_rows * ABIDES_MT_N * sizeof(unsigned), cudaMemcpyDeviceToDevice, h->stream));
   CK(cudaMemsetAsync(d.mom_ring, 0, (size_t)(h->n_mom > 0 ? h->n_mom : 1) * MOM_RING * sizeof(double), h->stream));
   CK(cudaMemsetAsync(d.res, 0, (size_t)d.n_instances * sizeof(abides_instance_result), h->stream));
@@ -786,6 +867,13 @@ int abides_load(abides_handle* h, const abides_batch* b) {
     }
   }
   sig.seeded = seeded;
+  sig.n_mt_rows = seeded ? b->n_mt_rows : 0;
+  const bool rematerialize = seeded && b->n_mt_rows == 0;
+  std::vector<int> skip_list;                   // streams fast-forwarded by a warp each
+  if (seeded)
+    for (size_t s2 = 0; s2 < ns_all; s2++)
+      if (b->mt_key_row[s2] < 0 && b->mt_pos[s2] >= rngsetup::SKIP_MIN_WORDS && (!use_lane || dev_row[s2] >= 0)) skip_list.push_back((int)s2);
+  sig.n_skip = (long long)skip_list.size();
   sig.n_dev_rows = (long long)n_dev_rows;
   const lane::LaneCaps lcap = lane::lane_caps(max_agents, lane_variant, needs_tv);
   DevBatch& d = h->db;
@@ -814,7 +902,14 @@ int abides_load(abides_handle* h, const abides_batch* b) {
     if (b->rng_mode == ABIDES_RNG_MT19937) {
       int *dpos, *dhg; double* dg;
       if ((rc = dev_alloc(h, &d.mt, n_dev_rows * ABIDES_MT_N))) return rc;
-      if ((rc = dev_alloc(h, &h->mt_pristine, n_dev_rows * ABIDES_MT_N))) return rc;
+      h->mt_pristine = nullptr; h->pos0 = nullptr; h->hg0 = nullptr; h->g0 = nullptr; h->d_skip_list = nullptr;
+      if (!rematerialize) { if ((rc = dev_alloc(h, &h->mt_pristine, n_dev_rows * ABIDES_MT_N))) return rc; }
+      else {
+        if ((rc = dev_alloc(h, &h->pos0, ns))) return rc;
+        if ((rc = dev_alloc(h, &h->hg0, ns))) return rc;
+        if ((rc = dev_alloc(h, &h->g0, ns))) return rc;
+      }
+      if (!skip_list.empty()) { if ((rc = dev_alloc(h, &h->d_skip_list, skip_list.size()))) return rc; }
       if (seeded) {
         if ((rc = dev_alloc(h, &h->d_mt_seed, ns))) return rc;
         if ((rc = dev_alloc(h, &h->d_key_row, ns))) return rc;
@@ -891,6 +986,7 @@ int abides_load(abides_handle* h, const abides_batch* b) {
   }
   h->lane_variant = lane_variant;
   h->n_streams = ns; h->n_mom = n_mom; h->n_dev_rows = n_dev_rows;
+  h->rematerialize = rematerialize; h->max_agents = max_agents; h->n_skip = (int)skip_list.size();
   // kernel variant: the leanest one whose feature set covers the batch (engine_device.inc)
   h->variant = VAR_FULL;
   if (b->rng_mode == ABIDES_RNG_MT19937 && b->trace_capacity == 0) {
@@ -928,31 +1024,34 @@ int abides_load(abides_handle* h, const abides_batch* b) {
         if ((rc = h2d(h, (const unsigned*)staging, b->mt_key, (size_t)b->n_mt_rows * ABIDES_MT_N))) { cudaFree(staging); return rc; }
       }
     }
-    if ((rc = h2d(h, d.mt_pos, b->mt_pos, ns))) return rc;
-    if ((rc = h2d(h, d.mt_has_gauss, b->mt_has_gauss, ns))) return rc;
-    if ((rc = h2d(h, d.mt_gauss, b->mt_gauss, ns))) return rc;
+    if (rematerialize) {
+      if ((rc = h2d(h, (const int*)h->pos0, b->mt_pos, ns))) return rc;
+      if ((rc = h2d(h, (const int*)h->hg0, b->mt_has_gauss, ns))) return rc;
+      if ((rc = h2d(h, (const double*)h->g0, b->mt_gauss, ns))) return rc;
+    } else {
+      if ((rc = h2d(h, d.mt_pos, b->mt_pos, ns))) return rc;
+      if ((rc = h2d(h, d.mt_has_gauss, b->mt_has_gauss, ns))) return rc;
+      if ((rc = h2d(h, d.mt_gauss, b->mt_gauss, ns))) return rc;
+    }
     if (seeded) {
       if ((rc = h2d(h, (const unsigned*)h->d_mt_seed, b->mt_seed, ns))) return rc;
       if ((rc = h2d(h, (const int*)h->d_key_row, b->mt_key_row, ns))) return rc;
       if (use_lane && (rc = h2d(h, (const int*)h->d_dev_row, dev_row.data(), ns))) return rc;
+      if (!skip_list.empty() && (rc = h2d(h, (const int*)h->d_skip_list, skip_list.data(), skip_list.size()))) return rc;
     }
-    if (seeded || b->draw_flags) {
-      // seed / fast-forward the described streams, then the agents' constructor draws: once, into the pristine copy
-      rngsetup::RngSetup p;
-      memset(&p, 0, sizeof p);
-      p.n_instances = ni; p.draw_flags = b->draw_flags;
-      p.cfg = d.cfg; p.types = d.types; p.agent_type = d.agent_type; p.agent_theta = d.agent_theta;
-      p.theta = const_cast<int*>(d.theta); p.size = const_cast<long long*>(d.size);
-      p.mt = h->mt_pristine; p.staging = staging;
-      p.key_row = seeded ? h->d_key_row : nullptr; p.dev_row = (seeded && use_lane) ? h->d_dev_row : nullptr;
-      p.seed = h->d_mt_seed;
-      p.pos = const_cast<int*>(d.mt_pos); p.has_gauss = const_cast<int*>(d.mt_has_gauss); p.gauss = const_cast<double*>(d.mt_gauss);
-      const dim3 grid((max_agents + ABIDES_EXTRA_STREAMS + 63) / 64, ni);
-      if (seeded) rngsetup::rng_materialize_kernel<<<grid, 64, 0, h->stream>>>(p);
-      if (b->draw_flags) rngsetup::rng_ctor_draws_kernel<<<grid, 64, 0, h->stream>>>(p);
-      cudaError_t e = cudaGetLastError();
-      if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    rngsetup::RngSetup& p = h->rs;
+    memset(&p, 0, sizeof p);
+    p.n_instances = ni; p.draw_flags = b->draw_flags; p.skip_min = skip_list.empty() ? 0 : rngsetup::SKIP_MIN_WORDS;
+    p.cfg = d.cfg; p.types = d.types; p.agent_type = d.agent_type; p.agent_theta = d.agent_theta;
+    p.theta = const_cast<int*>(d.theta); p.size = const_cast<long long*>(d.size);
+    p.key_row = seeded ? h->d_key_row : nullptr; p.dev_row = (seeded && use_lane) ? h->d_dev_row : nullptr;
+    p.seed = h->d_mt_seed;
+    p.pos = const_cast<int*>(d.mt_pos); p.has_gauss = const_cast<int*>(d.mt_has_gauss); p.gauss = const_cast<double*>(d.mt_gauss);
+    if (!rematerialize && (seeded || b->draw_flags)) {         // once, into the pristine copy every reset restores
+      rc = run_rng_setup(h, h->mt_pristine, staging);
+      cudaError_t e = rc ? cudaSuccess : cudaStreamSynchronize(h->stream);
       if (staging) cudaFree(staging);
+      if (rc) return rc;
       if (e != cudaSuccess) return fail(ABIDES_ECUDA, std::string("rng setup: ") + cudaGetErrorString(e));
     }
   }
@@ -988,8 +1087,8 @@ int abides_run(abides_handle* h, int64_t until_time) {
   CK(cudaSetDevice(h->device));
   CK(cudaEventRecord(h->ev0, h->stream));
   if (h->lane_variant != lane::LV_NONE) {
-    const int grid = (h->n_instances + LANE_BLOCK - 1) / LANE_BLOCK;
-#define LAUNCH_LANE(ns) lane::ns::lane_sim_kernel<<<grid, LANE_BLOCK, 0, h->stream>>>(h->lb, (long long)until_time)
+    const int grid = (h->n_instances + lane::LANE_CTA - 1) / lane::LANE_CTA;
+#define LAUNCH_LANE(ns) lane::ns::lane_sim_kernel<<<grid, lane::LANE_CTA, 0, h->stream>>>(h->lb, (long long)until_time)
     switch (h->lane_variant) {
       case lane::LV_ZI_LEGACY: LAUNCH_LANE(lv_zi_legacy); break;
       case lane::LV_ZI_CUBIC: LAUNCH_LANE(lv_zi_cubic); break;

@@ -48,6 +48,8 @@ static_assert(LN_CLS_ZI == ABIDES_ZI && LN_CLS_VALUE == ABIDES_VALUE && LN_CLS_N
 
 namespace lane {
 
+constexpr int LANE_CTA = 128;                // instances (threads) per CTA of the event loop
+constexpr int LANE_KINDS = 128;              // handler classes the CTA regroups popped events by
 constexpr int HEAP_ROOT = 3;                 // children of node i: 4 * (i - 2) .. + 3; parent of j: j / 4 + 2
 constexpr int OUTBOX_CAP = 6;                // messages / wakeups an event may emit before the outbox is flushed early
 constexpr int MOM_RING = 64;                 // >= 51 prefix sums (MomentumAgent)
