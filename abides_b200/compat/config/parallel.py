@@ -7,7 +7,8 @@ draws from np.random after `np.random.seed(seed)`) become ONE batch: every seed'
 all instances run in a single launch on the GPU, and each simulation then gets what its own process would have left
 behind: the end-of-run summary lines and ./log/<log_folder>_seed_<seed>/summary_log.bz2.  Flags this driver does not
 know (e.g. `-t ABM -d 20200603` for rmsc03) are passed on to the config, which the reference's driver cannot do;
-`--num_parallel` is accepted and ignored (the batch is the parallelism)."""
+`--num_parallel` is accepted and ignored (the batch is the parallelism); `--gpus N` spreads the batch over N GPUs of
+the box (one worker thread per GPU taking chunks of instances from a ticket counter)."""
 import argparse
 import datetime as dt
 import os
@@ -32,6 +33,7 @@ def main(argv=None):
     ap.add_argument('--num_parallel', type=int, default=None, help='(ignored: all simulations form one GPU batch)')
     ap.add_argument('--config', required=True, help='Name of config file to execute')
     ap.add_argument('--log_folder', required=True, help='Log directory name')
+    ap.add_argument('--gpus', type=int, default=1, help='GPUs of this box to spread the simulations over')
     ap.add_argument('-v', '--verbose', action='store_true', help='Maximum verbosity!')
     args, passthrough = ap.parse_known_args(argv)
     t0 = dt.datetime.now()
@@ -41,7 +43,8 @@ def main(argv=None):
     print(f'Global Seeds: {seeds}')
     arg_lists = [passthrough + ["-s", s, "-l", "{}_seed_{}".format(args.log_folder, s)] + (["-v"] if args.verbose else [])
                  for s in seeds]
-    out, kernels = runtime.run_config_batch(args.config, arg_lists, allow_status=(_abi.ESTATE,))
+    out, kernels = runtime.run_config_batch(args.config, arg_lists, allow_status=(_abi.ESTATE,),
+                                            devices=list(range(args.gpus)) if args.gpus > 1 else None)
     for i, (seed, kernel) in enumerate(zip(seeds, kernels)):
         print(f'--- seed {seed} ---')
         if out.res["status"][i] == _abi.ESTATE:

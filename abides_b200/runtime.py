@@ -18,6 +18,7 @@ from .engine import Engine
 COMPAT_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "compat")
 _capture = None
 _engines = {}
+_BUILD_LOCK = __import__("threading").RLock()
 
 
 def capturing():
@@ -45,29 +46,129 @@ def engine(device=0):
 
 
 class RunOutput:
-    def __init__(self, hb, res, ares, kernel_ms, wall_s):
+    """Results of a run: `res` per instance, `ares` per agent (instances concatenated in input order)."""
+
+    def __init__(self, hb, res, ares, kernel_ms, wall_s, agent_offsets=None, placement=None):
         self.hb, self.res, self.ares, self.kernel_ms, self.wall_s = hb, res, ares, kernel_ms, wall_s
+        if agent_offsets is None:
+            agent_offsets = [(hb.instances[i].agent_offset, hb.instances[i].n_agents) for i in range(hb.n_instances)]
+        self.agent_offsets = agent_offsets
+        self.placement = placement              # multi-device runs: [(device, first instance, count, kernel ms)] per chunk
 
     def agents(self, inst):
-        ic = self.hb.instances[inst]
-        return self.ares[ic.agent_offset:ic.agent_offset + ic.n_agents]
+        off, n = self.agent_offsets[inst]
+        return self.ares[off:off + n]
 
 
-def run_specs(specs, device=0, rng_mode=_abi.RNG_MT19937, trace_capacity=0, allow_status=()):
+def _check_status(res, allow_status):
+    bad = np.nonzero((res["status"] != 0) & ~np.isin(res["status"], list(allow_status)))[0]
+    if len(bad):
+        raise RuntimeError("device reported status %d for instance %d (see enum abides_error)"
+                           % (int(res["status"][bad[0]]), int(bad[0])))
+
+
+def run_specs(specs, device=0, rng_mode=_abi.RNG_MT19937, trace_capacity=0, allow_status=(), devices=None,
+              chunk_instances=None, engine_name=None):
     """Kernel.runner for a list of lowered instances: H2D, run to completion, D2H.  An instance that ends with a
-    status outside `allow_status` raises (ABIDES_ESTATE marks a run in which the reference itself raises)."""
+    status outside `allow_status` raises (ABIDES_ESTATE marks a run in which the reference itself raises).
+    `devices` (a list of CUDA device indices) spreads the instances over several GPUs: see run_chunks."""
+    if devices is not None and len(devices) > 1:
+        n = len(specs)
+        chunk = chunk_instances or max(1, -(-n // (2 * len(devices))))
+        bounds = [(lo, min(n, lo + chunk)) for lo in range(0, n, chunk)]
+        return run_chunks([(lambda lo=lo, hi=hi: lowering.HostBatch(specs[lo:hi], rng_mode=rng_mode)) for lo, hi in bounds],
+                          [hi - lo for lo, hi in bounds], devices, allow_status=allow_status, engine_name=engine_name)
+    if devices:
+        device = devices[0]
     hb = lowering.HostBatch(specs, rng_mode=rng_mode, trace_capacity=trace_capacity)
     eng = engine(device)
+    if engine_name is not None:
+        eng.set_engine(engine_name)
     t0 = time.perf_counter()
     eng.load(hb)
     eng.run()
     res, ares = eng.results_arrays()
     wall = time.perf_counter() - t0
-    bad = np.nonzero((res["status"] != 0) & ~np.isin(res["status"], list(allow_status)))[0]
-    if len(bad):
-        raise RuntimeError("device reported status %d for instance %d (see enum abides_error)"
-                           % (int(res["status"][bad[0]]), int(bad[0])))
+    _check_status(res, allow_status)
     return RunOutput(hb, res.copy(), ares.copy(), eng.last_run_ms()[0], wall)
+
+
+def run_chunks(builders, counts, devices, allow_status=(), engine_name=None):
+    """The box-wide sweep driver (reference: config/parallel.py:14-18 keeps `num_parallel` processes busy with the
+    next seed).  `builders[i]()` returns the host batch of chunk i (`counts[i]` instances); one worker thread per
+    device takes the next chunk as soon as its GPU is free -- a ticket counter, so faster GPUs and shorter chunks even
+    out -- loads it, runs it and reads the results back.  ctypes releases the GIL during the C calls, so the GPUs
+    run concurrently from this one process.  Results come back in chunk (= input) order."""
+    import threading
+    n_chunks = len(builders)
+    out = [None] * n_chunks
+    errors = []
+    ticket = [0]
+    lock = threading.Lock()
+    t0 = time.perf_counter()
+
+    def worker(dev):
+        try:
+            eng = engine(dev)
+            if engine_name is not None:
+                eng.set_engine(engine_name)
+            while True:
+                with lock:
+                    i = ticket[0]
+                    ticket[0] += 1
+                if i >= n_chunks or errors:
+                    return
+                hb = builders[i]()
+                eng.load(hb)
+                eng.run()
+                res, ares = eng.results_arrays()
+                out[i] = (dev, res.copy(), ares.copy(), eng.last_run_ms()[0],
+                          [hb.instances[k].n_agents for k in range(hb.n_instances)])
+        except Exception as e:                                 # surfaced by the caller
+            errors.append(e)
+
+    threads = [threading.Thread(target=worker, args=(d,)) for d in devices]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    res = np.concatenate([o[1] for o in out])
+    ares = np.concatenate([o[2] for o in out])
+    _check_status(res, allow_status)
+    offsets, off = [], 0
+    for o in out:
+        for n in o[4]:
+            offsets.append((off, n))
+            off += n
+    placement, first = [], 0
+    for o, c in zip(out, counts):
+        placement.append((o[0], first, c, o[3]))
+        first += c
+    return RunOutput(None, res, ares, max(sum(p[3] for p in placement if p[0] == d) for d in devices),
+                     time.perf_counter() - t0, agent_offsets=offsets, placement=placement)
+
+
+def run_sweep(config, seeds, extra_args=(), devices=(0,), chunk_instances=None, allow_status=(_abi.ESTATE,),
+              engine_name=None):
+    """Seed sweep of `config` over the GPUs in `devices` from one process.  Chunks are built with the vectorised sweep
+    builder where one exists (abides_b200/sweep.py: streams travel as seeds) and by executing the config module per
+    seed otherwise.  Returns a RunOutput whose rows follow `seeds`."""
+    from . import sweep as sweep_mod
+    seeds = [int(s) for s in seeds]
+    n = len(seeds)
+    chunk = chunk_instances or max(1, -(-n // (2 * len(devices)))) if len(devices) > 1 else (chunk_instances or n)
+    bounds = [(lo, min(n, lo + chunk)) for lo in range(0, n, chunk)]
+
+    def builder(lo, hi):
+        if sweep_mod.supported(config):
+            return lambda: sweep_mod.build_sweep(config, seeds[lo:hi], extra_args)
+        return lambda: lowering.HostBatch([s for s, _ in build_instances(
+            config, [list(extra_args) + ["-s", str(x)] for x in seeds[lo:hi]])])
+
+    return run_chunks([builder(lo, hi) for lo, hi in bounds], [hi - lo for lo, hi in bounds], list(devices),
+                      allow_status=allow_status, engine_name=engine_name)
 
 
 def write_back(kernel, out, inst):
@@ -225,7 +326,8 @@ def build_instances(config, arg_lists, quiet=True):
     returns [(InstanceSpec, Kernel)]."""
     path = find_config(config)
     out = []
-    with _compat_path(), capture() as cap:
+    # a config body is process-global state (sys.argv, sys.path, the np.random stream): one at a time
+    with _BUILD_LOCK, _compat_path(), capture() as cap:
         for args in arg_lists:
             _reset_process_globals()
             argv, sys.argv = sys.argv, ["abides.py", "-c", config] + [str(a) for a in args]
@@ -269,12 +371,13 @@ def parallel_seeds(seed, num_simulations):
     return [int(s) for s in rs.randint(low=0, high=2 ** 32, size=num_simulations)]
 
 
-def run_config_batch(config, arg_lists, device=0, write=True, allow_status=()):
-    """Seed sweep / parameter grid in one launch.  Returns (RunOutput, [Kernel])."""
+def run_config_batch(config, arg_lists, device=0, write=True, allow_status=(), devices=None):
+    """Seed sweep / parameter grid in one launch (or, with `devices`, spread over several GPUs of the box).
+    Returns (RunOutput, [Kernel])."""
     built = build_instances(config, arg_lists)
     specs = [s for s, _ in built]
     kernels = [k for _, k in built]
-    out = run_specs(specs, device=device, allow_status=allow_status)
+    out = run_specs(specs, device=device, allow_status=allow_status, devices=devices)
     if write:
         for i, k in enumerate(kernels):
             write_back(k, out, i)

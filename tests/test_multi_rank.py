@@ -62,3 +62,52 @@ def test_two_rank_gloo_gather_equals_single_process():
     res, _ = oracle.run_batch(lowering.HostBatch(specs), n_threads=2)
     want = [res[i].ttl_messages for i in range(n_total)]
     assert got == want and len(set(want)) > 1
+
+
+class _HostEngine:
+    """Stands in for abides_b200.engine.Engine in the CPU suite: same calls, computed by the host build of the lane
+    engine (tests/hostsim).  What is under test is the sweep driver around it: chunking, the ticket counter, merging."""
+    calls = []
+
+    def __init__(self, device):
+        self.device, self.hb, self.out = device, None, None
+
+    def set_engine(self, name):
+        pass
+
+    def load(self, hb):
+        self.hb = hb
+
+    def run(self):
+        import hostsim
+        res, ares, _, _, _ = hostsim.run(self.hb)
+        self.out = (res, ares)
+        _HostEngine.calls.append((self.device, self.hb.n_instances))
+
+    def results_arrays(self):
+        return self.out
+
+    def last_run_ms(self):
+        return 1.0, 1
+
+
+def test_multi_device_sweep_driver_returns_single_batch_results(monkeypatch):
+    """runtime.run_sweep over two devices (chunks handed out by a ticket counter, one worker thread per device) returns,
+    in seed order, exactly what one batch on one device returns."""
+    import hostsim
+    from abides_b200 import runtime, sweep
+    engines = {}
+    monkeypatch.setattr(runtime, "engine", lambda dev=0: engines.setdefault(dev, _HostEngine(dev)))
+    _HostEngine.calls = []
+    seeds = runtime.parallel_seeds(9, 11)
+    out = runtime.run_sweep("sparse_zi_100", seeds, devices=(0, 1), chunk_instances=3)
+    assert sum(n for _, n in _HostEngine.calls) == 11 and len(_HostEngine.calls) == 4
+    assert [p[1:3] for p in out.placement] == [(0, 3), (3, 3), (6, 3), (9, 2)]
+    res1, ares1, _, _, _ = hostsim.run(sweep.build_sweep("sparse_zi_100", seeds))
+    assert np.array_equal(out.res["ttl_messages"], res1["ttl_messages"]) and len(set(out.res["ttl_messages"])) > 1
+    assert np.array_equal(out.ares["cash"], ares1["cash"])
+    assert np.array_equal(out.agents(7)["holdings"], ares1["holdings"][7 * 101:8 * 101])
+    # the config-built path (any config) through the same driver
+    specs = [s for s, _ in runtime.build_instances("sparse_zi_100", [["-s", s] for s in seeds[:5]])]
+    out2 = runtime.run_specs(specs, devices=[0, 1], chunk_instances=2)
+    assert np.array_equal(out2.res["ttl_messages"], res1["ttl_messages"][:5])
