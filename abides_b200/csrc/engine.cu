@@ -980,7 +980,7 @@ int abides_load(abides_handle* h, const abides_batch* b) {
       lb.wakeup_time = d.wakeup_time; lb.agent_theta = d.agent_theta; lb.theta = d.theta; lb.mom_index = d.mom_index;
       lb.mt = d.mt; lb.mt_row = seeded ? h->d_dev_row : nullptr; lb.mt_seed = seeded ? h->d_mt_seed : nullptr;
       lb.mt_pos = d.mt_pos; lb.mt_has_gauss = d.mt_has_gauss; lb.mt_gauss = d.mt_gauss;
-      lb.mom_ring = d.mom_ring; lb.trace = d.trace; lb.res = d.res; lb.ares = d.ares;
+      lb.mom_ring = d.mom_ring; lb.trace = d.trace; lb.res = d.res; lb.ares = d.ares; lb.prof = d.prof;
     }
     h->sig = sig;
   }

@@ -19,6 +19,7 @@
 #define ABIDES_LANE_TYPES_H
 
 #include <stdint.h>
+#include <stddef.h>
 #include "abides_b200.h"
 #include "abides_dd_math.h"
 
@@ -50,6 +51,7 @@ namespace lane {
 
 constexpr int LANE_CTA = 128;                // instances (threads) per CTA of the event loop
 constexpr int LANE_KINDS = 128;              // handler classes the CTA regroups popped events by
+constexpr int LANE_PROF_SLOTS = 8;            // rounds, pop cycles, sort cycles, handle cycles, events, ...
 constexpr int HEAP_ROOT = 3;                 // children of node i: 4 * (i - 2) .. + 3; parent of j: j / 4 + 2
 constexpr int OUTBOX_CAP = 6;                // messages / wakeups an event may emit before the outbox is flushed early
 constexpr int MOM_RING = 64;                 // >= 51 prefix sums (MomentumAgent)
@@ -101,26 +103,33 @@ struct LN_ALIGN(128) LAgent {           // 128 bytes = four 32-byte sectors; sec
 };
 static_assert(sizeof(LAgent) == 128, "LAgent must be 128 bytes");
 
-struct LHot {                           // per-instance scalars: thread-local while the kernel runs, persisted between launches
-  long long now, ttl, delivered, n_fills, volume;
-  long long exch_busy, exch_cd, exch_cur_time, additional_delay;
+struct LN_ALIGN(16) LHot {              // per-instance scalars, in HBM; staged in thread-local memory while a half runs
+  // first 64 bytes: everything the pop half reads or writes (loaded / stored as four 16-byte vectors)
+  long long now, ttl, delivered, exch_busy;
+  int hn;                               // events in the heap
+  int n_hfree, slot_bump, spare_slot;   // payload slots: free stack, never-used frontier, one cached free slot
+  int status, done, n_trace, queue_peak;
+  // the rest: only the handle half (and kernelStopping)
+  long long n_fills, volume;
+  long long exch_cd, exch_cur_time, additional_delay;
   long long or_pt; double or_pv; long long ms_time; double ms_value;
   long long next_order_id;
   long long log_len, log_mark, unr_len;
   long long book_update_ts;
   unsigned long long pb[2];             // per side: lower bound of every pool key (price rank << 32 | arrival)
   unsigned uniq;
-  int hn;                               // events in the heap
-  int n_hfree, slot_bump, spare_slot;   // payload slots: free stack, never-used frontier, one cached free slot
   int hd[2], n_top[2];                  // book deques: physical index of the best entry, entries
   int pl_total[2], pl_live[2], n_pfree[2];
   int last_hint;                        // pool slot + 1 of the order book_enter just placed (0: in the deque)
   unsigned book_arr;                    // arrival counter of resting orders (time priority)
   int last_trade, has_last_trade;
-  int arena_top, status, n_trace, queue_peak, book_peak_orders, done;
+  int arena_top, book_peak_orders;
   int hist_B, tv_prev_len;
+  int pad_[3];
   RngState rs[ABIDES_EXTRA_STREAMS];
 };
+constexpr int LHOT_POP_BYTES = 64;
+static_assert(sizeof(LHot) % 16 == 0 && offsetof(LHot, n_fills) == LHOT_POP_BYTES, "LHot layout");
 
 // everything a launch needs; passed BY VALUE as a __grid_constant__ kernel parameter (no __constant__ symbol shared
 // between handles)
@@ -161,6 +170,7 @@ struct LaneBatch {
   abides_trace_rec* trace;
   abides_instance_result* res;
   abides_agent_result* ares;
+  unsigned long long* prof;             // [LANE_PROF_SLOTS] phase cycle counters (profiling builds) or NULL
 };
 
 LN_HD inline int heap_stride(int hcap) { return (hcap + HEAP_ROOT + 1 + 7) & ~7; }      // whole 128-byte lines per instance
