@@ -975,6 +975,7 @@ int abides_load(abides_handle* h, const abides_batch* b) {
     if (use_lane) {                             // the lane engine reads the shared input tables through its own descriptor
       lane::LaneBatch& lb = h->lb;
       lb.n_instances = ni; lb.trace_cap = d.trace_cap; lb.n_types = d.n_types;
+      { const char* ra = getenv("ABIDES_LANE_RUN_AHEAD"); lb.run_ahead = ra ? atoi(ra) : 6; if (lb.run_ahead < 0) lb.run_ahead = 0; }
       lb.cfg = d.cfg; lb.types = d.types; lb.type_log1mk = d.type_log1mk; lb.type_omp2 = d.type_omp2;
       lb.agent_type = d.agent_type; lb.lat_to = d.lat_to; lb.lat_from = d.lat_from; lb.size = d.size;
       lb.wakeup_time = d.wakeup_time; lb.agent_theta = d.agent_theta; lb.theta = d.theta; lb.mom_index = d.mom_index;

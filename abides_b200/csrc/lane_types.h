@@ -136,6 +136,7 @@ static_assert(sizeof(LHot) % 16 == 0 && offsetof(LHot, n_fills) == LHOT_POP_BYTE
 struct LaneBatch {
   int n_instances, trace_cap, n_types, top_k;
   int hcap, scap, arena_cap, deep_cap, txn_cap, unr_cap;
+  int run_ahead;                        // light events an instance may run past its sorted one per round
   const abides_instance_cfg* cfg;
   const abides_agent_type* types;
   abm_dd* type_log1mk;
