@@ -17,17 +17,19 @@ NVCC_FLAGS = [
 ]
 
 
-def build_cuda(force=False, verbose=False, profile=False, cta_warps=None, time_slices=None):
+def build_cuda(force=False, verbose=False, profile=False, cta_warps=None, time_slices=None, lane_cta=None):
     """Compile csrc/engine.cu for sm_100a.  profile=True builds the instrumented variant next to it;
     cta_warps=W builds libabides_b200_w<W>.so with W instances per CTA (experiments; the default is 1)."""
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    deps = srcs + [os.path.join(CSRC, "engine_device.inc")] + [os.path.join(INCLUDE, h) for h in ("abides_b200.h", "abides_dd_math.h", "abides_math_tables.h")]
+    deps = srcs + [os.path.join(CSRC, f) for f in ("engine_device.inc", "lane_device.inc", "lane_types.h", "lane_variants.inc", "lane_host_common.h", "rng_setup_device.inc")] + [os.path.join(INCLUDE, h) for h in ("abides_b200.h", "abides_dd_math.h", "abides_math_tables.h")]
     out = OUT_PROF if profile else OUT
     if cta_warps:
         out = out.replace(".so", "_w%d.so" % cta_warps)
     if time_slices:
         out = out.replace(".so", "_q%d.so" % time_slices)
+    if lane_cta:
+        out = out.replace(".so", "_l%d.so" % lane_cta)
     if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
         return out
     flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + (["-DABIDES_PROFILE"] if profile else [])
@@ -35,6 +37,8 @@ def build_cuda(force=False, verbose=False, profile=False, cta_warps=None, time_s
         flags.append("-DABM_CTA_WARPS=%d" % cta_warps)
     if time_slices:
         flags.append("-DABM_TIME_SLICES=%d" % time_slices)
+    if lane_cta:
+        flags.append("-DLANE_CTA_THREADS=%d" % lane_cta)
     cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-I", INCLUDE, "-o", out] + srcs
     print(" ".join(cmd), file=sys.stderr)
     subprocess.check_call(cmd)
@@ -45,4 +49,5 @@ if __name__ == "__main__":
     w = [a for a in sys.argv if a.startswith("--cta-warps=")]
     build_cuda(force=True, verbose="-v" in sys.argv, profile="--profile" in sys.argv,
                cta_warps=int(w[0].split("=")[1]) if w else None,
-               time_slices=next((int(a.split("=")[1]) for a in sys.argv if a.startswith("--time-slices=")), None))
+               time_slices=next((int(a.split("=")[1]) for a in sys.argv if a.startswith("--time-slices=")), None),
+               lane_cta=next((int(a.split("=")[1]) for a in sys.argv if a.startswith("--lane-cta=")), None))

@@ -596,6 +596,7 @@ struct abides_handle {
   float last_ms = 0.f, last_reset_ms = 0.f;
   int last_launches = 0;
   int launches_since_load = 0;
+  long long launches_total = 0;          // kernel launches of earlier loads (abides_launch_count)
   unsigned* d_mt_seed = nullptr; int* d_key_row = nullptr; int* d_dev_row = nullptr;   // compact stream description (seeded batches)
   // seeded batches without uploaded rows keep no pristine copy of the states: every (re)initialisation seeds them again
   bool rematerialize = false;
@@ -770,13 +771,15 @@ int abides_load(abides_handle* h, const abides_batch* b) {
   if (b->n_instances <= 0 || !b->instances || !b->types || !b->agent_type || !b->lat_to_exch || !b->lat_from_exch ||
       !b->agent_size || !b->agent_wakeup_time || !b->agent_theta)
     return fail(ABIDES_EINVAL, "abides_load: missing table");
-  const bool seeded = b->mt_key_row != nullptr;
+  const bool seeded = b->mt_key_row != nullptr && b->rng_mode == ABIDES_RNG_MT19937;
   if (b->rng_mode == ABIDES_RNG_MT19937 && (!b->mt_pos || !b->mt_has_gauss || !b->mt_gauss || (!seeded && !b->mt_key)))
     return fail(ABIDES_EINVAL, "abides_load: MT19937 mode needs mt_key/mt_pos/mt_has_gauss/mt_gauss");
   if (seeded && (b->rng_mode != ABIDES_RNG_MT19937 || !b->mt_seed || b->n_mt_rows < 0 || (b->n_mt_rows > 0 && !b->mt_key)))
     return fail(ABIDES_EINVAL, "abides_load: mt_key_row needs MT19937 mode, mt_seed and n_mt_rows rows of mt_key");
   if (b->draw_flags & ~(ABIDES_DRAW_ZI_THETA | ABIDES_DRAW_MOMENTUM_SIZE)) return fail(ABIDES_EINVAL, "abides_load: unknown draw_flags");
-  if (b->draw_flags && b->rng_mode != ABIDES_RNG_MT19937) return fail(ABIDES_EINVAL, "abides_load: draw_flags need MT19937 streams");
+  if (b->draw_flags && (!b->mt_seed && b->mt_key_row)) return fail(ABIDES_EINVAL, "abides_load: draw_flags with mt_key_row need mt_seed");
+  if (b->draw_flags && b->rng_mode == ABIDES_RNG_PHILOX && (!b->mt_key_row || !b->mt_seed || !b->mt_pos || !b->mt_has_gauss || !b->mt_gauss))
+    return fail(ABIDES_EINVAL, "abides_load: in Philox mode the constructor draws need every agent stream described by its seed");
   const bool draw_theta = (b->draw_flags & ABIDES_DRAW_ZI_THETA) != 0;
   if (b->rng_mode != ABIDES_RNG_MT19937 && b->rng_mode != ABIDES_RNG_PHILOX) return fail(ABIDES_EINVAL, "abides_load: bad rng_mode");
   CK(cudaSetDevice(h->device));
@@ -974,8 +977,8 @@ int abides_load(abides_handle* h, const abides_batch* b) {
     }
     if (use_lane) {                             // the lane engine reads the shared input tables through its own descriptor
       lane::LaneBatch& lb = h->lb;
-      lb.n_instances = ni; lb.trace_cap = d.trace_cap; lb.n_types = d.n_types;
-      { const char* ra = getenv("ABIDES_LANE_RUN_AHEAD"); lb.run_ahead = ra ? atoi(ra) : 6; if (lb.run_ahead < 0) lb.run_ahead = 0; }
+      lb.n_instances = ni; lb.trace_cap = d.trace_cap; lb.n_types = d.n_types; lb.rng_mode = b->rng_mode;
+      { const char* ra = getenv("ABIDES_LANE_RUN_AHEAD"); lb.run_ahead = ra ? atoi(ra) : 0; if (lb.run_ahead < 0) lb.run_ahead = 0; }
       lb.cfg = d.cfg; lb.types = d.types; lb.type_log1mk = d.type_log1mk; lb.type_omp2 = d.type_omp2;
       lb.agent_type = d.agent_type; lb.lat_to = d.lat_to; lb.lat_from = d.lat_from; lb.size = d.size;
       lb.wakeup_time = d.wakeup_time; lb.agent_theta = d.agent_theta; lb.theta = d.theta; lb.mom_index = d.mom_index;
@@ -1056,6 +1059,36 @@ int abides_load(abides_handle* h, const abides_batch* b) {
       if (e != cudaSuccess) return fail(ABIDES_ECUDA, std::string("rng setup: ") + cudaGetErrorString(e));
     }
   }
+  if (b->rng_mode == ABIDES_RNG_PHILOX && b->draw_flags) {
+    // Philox streams carry the run, but the agents' constructor draws still come from RandomState(seed): once, from
+    // throw-away generators (rng_setup_device.inc)
+    const size_t ns2 = (size_t)na + (size_t)ABIDES_EXTRA_STREAMS * ni;
+    unsigned* dseed = nullptr; int *dpos = nullptr, *dhg = nullptr; double* dg = nullptr;
+    auto cleanup = [&]() { cudaFree(dseed); cudaFree(dpos); cudaFree(dhg); cudaFree(dg); };
+    cudaError_t e = cudaMalloc(&dseed, ns2 * sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMalloc(&dpos, ns2 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&dhg, ns2 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&dg, ns2 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dseed, b->mt_seed, ns2 * sizeof(unsigned), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dpos, b->mt_pos, ns2 * sizeof(int), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dhg, b->mt_has_gauss, ns2 * sizeof(int), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dg, b->mt_gauss, ns2 * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) {
+      rngsetup::RngSetup p;
+      memset(&p, 0, sizeof p);
+      p.n_instances = ni; p.draw_flags = b->draw_flags;
+      p.cfg = d.cfg; p.types = d.types; p.agent_type = d.agent_type; p.agent_theta = d.agent_theta;
+      p.theta = const_cast<int*>(d.theta); p.size = const_cast<long long*>(d.size);
+      p.seed = dseed; p.pos = dpos; p.has_gauss = dhg; p.gauss = dg;
+      const dim3 grid(ni, (max_agents + ABIDES_EXTRA_STREAMS + 63) / 64);
+      rngsetup::rng_ctor_draws_kernel<<<grid, 64, 0, h->stream>>>(p);
+      e = cudaGetLastError();
+      if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    }
+    cleanup();
+    if (e != cudaSuccess) return fail(ABIDES_ECUDA, std::string("constructor draws: ") + cudaGetErrorString(e));
+  }
+  h->launches_total += h->launches_since_load;
   h->launches_since_load = 0;
   if ((rc = launch_init(h))) return rc;
   CK(cudaStreamSynchronize(h->stream));      // mom_index (a local vector) must outlive the copy
@@ -1137,6 +1170,12 @@ int abides_read_profile(abides_handle* h, uint64_t* out, int32_t n) {
   unsigned long long tmp[N_PROF];
   CK(cudaMemcpy(tmp, h->db.prof, sizeof tmp, cudaMemcpyDeviceToHost));
   for (int i = 0; i < n; i++) out[i] = i < N_PROF ? tmp[i] : 0;
+  return 0;
+}
+
+int abides_launch_count(abides_handle* h, int64_t* n) {
+  if (!h || !n) return fail(ABIDES_EINVAL, "NULL argument");
+  *n = h->launches_total + h->launches_since_load;
   return 0;
 }
 

@@ -13,10 +13,11 @@ constexpr int LANE_VARIANT_BASE = 16;
 
 inline int lane_top_k(int variant) { return variant == LV_RMSC ? 128 : variant == LV_FULL ? 64 : 32; }
 
-// the leanest lane variant whose feature set covers the batch, or LV_NONE (HBL agents, market-data subscriptions and
-// Philox streams run on the warp-per-instance engine)
+// the leanest lane variant whose feature set covers the batch, or LV_NONE (HBL agents and market-data subscriptions
+// run on the warp-per-instance engine)
 inline int lane_pick_variant(unsigned class_mask, unsigned lat_mask, int rng_mode, long long n_subscribers) {
-  if (rng_mode != ABIDES_RNG_MT19937 || n_subscribers > 0) return LV_NONE;
+  (void)rng_mode;                            // MT19937 and Philox streams both run on every variant
+  if (n_subscribers > 0) return LV_NONE;
   const unsigned zi = 1u << ABIDES_ZI;
   const unsigned rmsc = (1u << ABIDES_NOISE) | (1u << ABIDES_VALUE) | (1u << ABIDES_MOMENTUM) | (1u << ABIDES_ADAPTIVE_MM) |
                         (1u << ABIDES_POV_EXEC);

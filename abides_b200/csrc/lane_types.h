@@ -49,11 +49,14 @@ static_assert(LN_CLS_ZI == ABIDES_ZI && LN_CLS_VALUE == ABIDES_VALUE && LN_CLS_N
 
 namespace lane {
 
-constexpr int LANE_CTA = 128;                // instances (threads) per CTA of the event loop
+#ifndef LANE_CTA_THREADS
+#define LANE_CTA_THREADS 128
+#endif
+constexpr int LANE_CTA = LANE_CTA_THREADS;   // instances (threads) per CTA of the event loop
 constexpr int LANE_KINDS = 128;              // handler classes the CTA regroups popped events by
 constexpr int LANE_PROF_SLOTS = 8;            // rounds, pop cycles, sort cycles, handle cycles, events, ...
 constexpr int HEAP_ROOT = 3;                 // children of node i: 4 * (i - 2) .. + 3; parent of j: j / 4 + 2
-constexpr int OUTBOX_CAP = 6;                // messages / wakeups an event may emit before the outbox is flushed early
+constexpr int OUTBOX_CAP = 4;                // messages / wakeups an event may emit before the outbox is flushed early
 constexpr int MOM_RING = 64;                 // >= 51 prefix sums (MomentumAgent)
 constexpr int DEAD_PRICE = INT32_MIN;        // tombstone in a pool's price array
 constexpr int LAZY_MAX_WORDS = 227;          // a seed-only stream can hand out this many 32-bit words
@@ -136,6 +139,7 @@ static_assert(sizeof(LHot) % 16 == 0 && offsetof(LHot, n_fills) == LHOT_POP_BYTE
 struct LaneBatch {
   int n_instances, trace_cap, n_types, top_k;
   int hcap, scap, arena_cap, deep_cap, txn_cap, unr_cap;
+  int rng_mode;                         // enum abides_rng_mode
   int run_ahead;                        // light events an instance may run past its sorted one per round
   const abides_instance_cfg* cfg;
   const abides_agent_type* types;

@@ -60,6 +60,12 @@ class Engine:
         self._ck(self._L.abides_engine_info(self._h, C.byref(e), C.byref(v)), "abides_engine_info")
         return e.value, v.value
 
+    def launch_count(self):
+        """Kernels launched through this handle so far."""
+        n = C.c_int64(0)
+        self._ck(self._L.abides_launch_count(self._h, C.byref(n)), "abides_launch_count")
+        return n.value
+
     def reset(self):
         """Re-arm the resident batch (no host->device traffic)."""
         self._ck(self._L.abides_reset(self._h), "abides_reset")

@@ -237,7 +237,7 @@ def sweep_rmsc03(seeds, extra_args=("-t", "ABM", "-d", "20200603")):
 class SeededBatch:
     """Host tables of a sweep (the same interface as lowering.HostBatch: .c, .instances, .n_instances, ...)."""
 
-    def __init__(self, groups, trace_capacity=0):
+    def __init__(self, groups, trace_capacity=0, rng_mode=_abi.RNG_MT19937):
         self.groups = groups
         ni = sum(g.n for g in groups)
         na_total = sum(g.n * g.n_agents for g in groups)
@@ -299,7 +299,7 @@ class SeededBatch:
         b = _abi.Batch()
         b.n_instances, b.n_types = ni, len(type_rows)
         b.n_agents_total, b.n_theta_total = na_total, t_off
-        b.rng_mode, b.trace_capacity = _abi.RNG_MT19937, trace_capacity
+        b.rng_mode, b.trace_capacity = rng_mode, trace_capacity
         b.instances = C.cast(self.instances, C.POINTER(_abi.InstanceCfg))
         b.types = C.cast(self.types, C.POINTER(_abi.AgentType))
         p = lambda arr, ct: arr.ctypes.data_as(C.POINTER(ct))
@@ -313,7 +313,7 @@ class SeededBatch:
         b.n_mt_rows = 0
         b.draw_flags = draw_flags
         self.c = b
-        self.rng_mode = _abi.RNG_MT19937
+        self.rng_mode = rng_mode
 
     def _fill_device_draw_parameters(self, groups):
         """The constructor arguments the device needs for its own draws: sigma_pv of the ZI agents, min / max order
@@ -347,9 +347,10 @@ def supported(config):
     return config in SPARSE_ZI or config == "rmsc03"
 
 
-def build_sweep(config, seeds, extra_args=(), trace_capacity=0):
-    """SeededBatch of `config` for every seed (same flags for all); raises NotImplementedError for other configs."""
-    return SeededBatch([build_group(config, seeds, extra_args)], trace_capacity=trace_capacity)
+def build_sweep(config, seeds, extra_args=(), trace_capacity=0, rng_mode=_abi.RNG_MT19937):
+    """SeededBatch of `config` for every seed (same flags for all); raises NotImplementedError for other configs.
+    rng_mode=_abi.RNG_PHILOX keeps the seeds for the constructor draws only: the run itself uses counter-based streams."""
+    return SeededBatch([build_group(config, seeds, extra_args)], trace_capacity=trace_capacity, rng_mode=rng_mode)
 
 
 def build_group(config, seeds, extra_args=()):

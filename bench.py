@@ -1,18 +1,22 @@
 #!/usr/bin/env python
 """bench.py -- simulated messages/sec (and market-days/sec) of the batched ABIDES hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload sparse_zi_1000] [--instances 1024] [--rng mt|philox]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload rmsc03]
+                    [--instances 16384] [--scaling weak|strong] [--rng mt|philox] [--engine auto|lane|warp]
 
-One "step" = one pass of the hot path over one batch: `--instances` independent market days of the
-workload (one seed each, seeds drawn as config/parallel.py:11 does) simulated from midnight to the
-kernel stop time.  `value` = ttl_messages (Kernel.py:204) of all instances on all ranks / device time,
-inputs resident in HBM; `e2e` = the same through abides_load -> abides_run -> abides_read_results with
-host buffers.  Under torchrun each rank owns one GPU and its own `--instances` seeds (weak scaling);
-the only collective is the final gather of per-instance summaries.
+One "step" = one pass of the hot path over one batch: `--instances` independent market days of the workload (one seed
+each, seeds drawn as config/parallel.py:11 does) simulated from midnight to the kernel stop time.  `value` =
+ttl_messages (Kernel.py:204) of all instances on all ranks / device time, inputs resident in HBM; `e2e` = the same
+through abides_load -> abides_run -> abides_read_results with HOST buffers (pinned), copies inside the timed region.
+Under torchrun each rank owns one GPU and its own `--instances` seeds (weak scaling; `--scaling strong` splits a fixed
+total of `--instances` over the ranks); the only collective is the final gather of per-instance summaries.
 
-`--impl reference` times the CPU restatement of the reference (oracle/, all host threads) on a bounded
-sample of the same workload; the Python reference itself cannot travel to the GPU box.
+The headline workload is rmsc03 (BASELINE.json configs[3], the one the north star is quoted on); `also` carries
+sparse_zi_1000 (configs[1]) measured the same way with fewer steps.  `--workload rmsc03_grid` is configs[4]: a
+heterogeneous parameter grid (population sizes x market-maker parameters x seeds) in one batch.
+
+`--impl reference` times the CPU restatement of the reference (oracle/, all host threads) on a bounded sample of the
+same workload; the Python reference itself cannot travel to the GPU box.
 """
 import argparse
 import json
@@ -25,28 +29,32 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-CPU_TTL = []
 ALGO_BYTES_PER_MESSAGE = 160          # pop 16 + payload 16 + agent state r/w 80 + emit 32 + book 16
-BASELINE_PUBLISHED = {"sparse_zi_1000": 3100.4, "sparse_zi_100": 3585.4}   # BASELINE.md section 1 (1 core i7)
 REFERENCE_NOTE = ("the reference arm / cpu_baseline is the C restatement of the reference (oracle/abides_oracle.c) on all "
-                  "host threads; the Python reference itself cannot travel to the GPU box and runs 14.7 k (sparse_zi_1000) "
-                  "and 4-5 k (rmsc03) messages/s per core in the build container (BASELINE.md section 2), i.e. the C port "
-                  "is ~400x the reference per core")
+                  "host threads, one instance per thread; the Python reference itself cannot travel to the GPU box and "
+                  "runs 14.7 k (sparse_zi_1000) and 4-5 k (rmsc03) messages/s per core in the build container "
+                  "(BASELINE.md section 2), i.e. the C port is ~400x the reference per core")
+RMSC03 = ["-t", "ABM", "-d", "20200603"]
 WORKLOADS = {
     "sparse_zi_100": ("sparse_zi_100", []),
     "sparse_zi_1000": ("sparse_zi_1000", []),
-    "rmsc03": ("rmsc03", ["-t", "ABM", "-d", "20200603", "--end-time", "16:00:00"]),
-    "rmsc03_2h": ("rmsc03", ["-t", "ABM", "-d", "20200603"]),
+    "rmsc03": ("rmsc03", RMSC03),                                  # config/rmsc03.py defaults: 09:30-11:30
+    "rmsc03_2h": ("rmsc03", RMSC03),
+    "rmsc03_day": ("rmsc03", RMSC03 + ["--end-time", "16:00:00"]),
     # BASELINE configs[2] "rmsc01: value + noise agents + market maker", from the supported classes
-    "rmsc01": ("rmsc03", ["-t", "ABM", "-d", "20200603", "--end-time", "16:00:00", "--num-noise", "50",
-                          "--num-value", "25", "--num-momentum", "24"]),
-    # the reference's literal config/rmsc01.py population: 1 MarketMaker + 50 ZI + 25 HBL + 24 momentum
+    "rmsc01": ("rmsc03", RMSC03 + ["--end-time", "16:00:00", "--num-noise", "50", "--num-value", "25", "--num-momentum", "24"]),
+    # the reference's literal config/rmsc01.py population: 1 MarketMaker + 50 ZI + 25 HBL + 24 momentum (warp engine)
     "rmsc01_literal": ("rmsc01", []),
-    # config/rmsc02.py: the same population with the market maker and momentum agents on market-data subscriptions
     "rmsc02": ("rmsc02", []),
-    # config/execution.py -e: the rmsc03 market 09:30-11:30 with a TWAP agent buying 1.2 M shares
-    "execution": ("execution", ["-t", "ABM", "-d", "20200603", "-e"]),
+    "execution": ("execution", RMSC03 + ["-e"]),
 }
+# BASELINE configs[4]: util/make_grid.py-style sweep of agent counts / market-maker parameters x seeds, one batch
+GRID = {"--num-noise": [2500, 5000], "--num-value": [50, 100], "--mm-pov": [0.025, 0.05], "--mm-num-ticks": [10, 20]}
+HOURS = {"rmsc03": "09:30-11:30, kernel 00:00-11:31", "rmsc03_2h": "09:30-11:30, kernel 00:00-11:31",
+         "rmsc03_grid": "09:30-11:30, kernel 00:00-11:31", "execution": "09:30-11:30, kernel 00:00-11:31",
+         "sparse_zi_100": "09:30-16:00, kernel 00:00-17:00", "sparse_zi_1000": "09:30-16:00, kernel 00:00-17:00"}
+DEFAULT_INSTANCES = {"rmsc03": 16384, "rmsc03_2h": 16384, "rmsc03_grid": 16384, "sparse_zi_1000": 32768,
+                     "sparse_zi_100": 65536}
 
 
 class ClockSampler(threading.Thread):
@@ -86,23 +94,29 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-def ncu_traffic(workload, instances):
-    """DRAM bytes per sim_kernel launch from the committed ncu capture of the same workload (profiles/), or None."""
-    try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r1_roofline.json")))
-        e = t.get("%s_x%d" % (workload, instances))
-        return float(e["dram_bytes_per_launch"]) if e else None
-    except Exception:
-        return None
+def ncu_traffic(workload, instances, engine):
+    """DRAM bytes per message of the dominant kernel from the committed ncu capture of the workload (profiles/), or None."""
+    for name in ("r2_roofline.json", "r1_roofline.json"):
+        try:
+            t = json.load(open(os.path.join(ROOT, "profiles", name)))
+        except Exception:
+            continue
+        for key in ("%s_%s_x%d" % (workload, engine, instances), "%s_%s" % (workload, engine), "%s_x%d" % (workload, instances)):
+            e = t.get(key)
+            if e:
+                return e
+    return None
 
 
-def pin_host_batch(hb):
+def pin_arrays(hb):
     """Page-lock the big host tables so the e2e leg copies from pinned memory (done once, outside the timed region)."""
     import torch
     rt = torch.cuda.cudart()
     n = 0
-    for a in (hb.mt_key, hb.lat_to, hb.lat_from, hb.size, hb.wakeup_time, hb.agent_type, hb.agent_theta, hb.theta):
-        if a is not None and a.nbytes >= (1 << 20):
+    for name in ("mt_key", "lat_to", "lat_from", "size", "wakeup_time", "agent_type", "agent_theta", "theta", "mt_seed",
+                 "mt_pos", "mt_has_gauss", "mt_gauss", "mt_key_row", "cfg"):
+        a = getattr(hb, name, None)
+        if a is not None and getattr(a, "nbytes", 0) >= (1 << 20):
             if int(rt.cudaHostRegister(a.ctypes.data, a.nbytes, 0)) == 0:
                 n += a.nbytes
     return n
@@ -116,36 +130,92 @@ def measured_hbm_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def build_batch(workload, seeds, rng_mode):
-    from abides_b200 import runtime, lowering
-    cfg, extra = WORKLOADS[workload]
+def grid_groups(seeds_per_point, seed):
+    """(extra flags, seeds) per grid point, heaviest populations first (a CTA then holds instances of one point)."""
+    import itertools
+    from abides_b200 import runtime
+    keys = list(GRID)
+    points = list(itertools.product(*[GRID[k] for k in keys]))
+    all_seeds = runtime.parallel_seeds(seed, seeds_per_point * len(points))
+    out = []
+    for j, combo in enumerate(points):
+        extra = list(RMSC03)
+        for k, v in zip(keys, combo):
+            extra += [k, str(v)]
+        out.append((extra, all_seeds[j * seeds_per_point:(j + 1) * seeds_per_point]))
+    out.sort(key=lambda g: -(int(g[0][g[0].index("--num-noise") + 1]) + int(g[0][g[0].index("--num-value") + 1])))
+    return out
+
+
+def build_batch(workload, seeds, rng_mode, seed0=0):
+    """Host tables of one rank's batch.  The sweep builder (abides_b200/sweep.py) where one exists: config-time draws
+    vectorised over the seeds, streams handed over as seeds; else the config module once per seed."""
+    from abides_b200 import runtime, lowering, sweep
     t0 = time.perf_counter()
-    specs = runtime.build_specs_parallel(cfg, [["-s", s] + extra for s in seeds])
-    hb = lowering.HostBatch(specs, rng_mode=rng_mode)
+    if workload == "rmsc03_grid":
+        n_points = 1
+        for v in GRID.values():
+            n_points *= len(v)
+        per = max(1, len(seeds) // n_points)
+        groups = [sweep.build_group("rmsc03", s, extra) for extra, s in grid_groups(per, seed0)]
+        hb = sweep.SeededBatch(groups, rng_mode=rng_mode)
+    else:
+        cfg, extra = WORKLOADS[workload]
+        if sweep.supported(cfg):
+            hb = sweep.build_sweep(cfg, seeds, extra, rng_mode=rng_mode)
+        else:
+            specs = runtime.build_specs_parallel(cfg, [["-s", s] + extra for s in seeds])
+            hb = lowering.HostBatch(specs, rng_mode=rng_mode)
     return hb, time.perf_counter() - t0
 
 
-def cpu_baseline(hb, n_sample, threads):
-    """The oracle port on the host cores over the first n_sample instances (bounded sample)."""
+def build_cpu_sample(workload, seeds, n_sample):
+    """The first n_sample instances of the batch as config-built, fully uploaded instances: what the oracle reads."""
+    from abides_b200 import runtime, lowering
+    if workload == "rmsc03_grid":
+        extra, gseeds = grid_groups(max(1, n_sample), 0)[0]
+        cfg, seeds = "rmsc03", gseeds[:n_sample]
+    else:
+        cfg, extra = WORKLOADS[workload]
+    specs = runtime.build_specs_parallel(cfg, [["-s", s] + list(extra) for s in seeds[:n_sample]])
+    return lowering.HostBatch(specs)
+
+
+def cpu_run(hb, n_sample, threads):
+    """The oracle port on the host cores over the first n_sample instances; returns (messages, seconds, ttl list)."""
     import oracle
     t0 = time.perf_counter()
     res, _ = oracle.run_batch(hb, n_threads=threads, first=0, count=n_sample)
     dt = time.perf_counter() - t0
-    global CPU_TTL
-    CPU_TTL = [int(res[i].ttl_messages) for i in range(n_sample)]      # also a parity spot check against the device
-    msgs = sum(CPU_TTL)
-    return msgs, dt
+    ttl = [int(res[i].ttl_messages) for i in range(n_sample)]
+    return sum(ttl), dt, ttl
 
 
-def bounded_sample(hb, limit, threads, budget_s=20.0):
-    """How many instances the CPU leg takes: one instance per host thread is timed first, and the sample grows from
-    there only as far as about `budget_s` seconds of wall time allow (the whole batch for the ZI workloads, one
-    round of `threads` instances for rmsc03-sized ones).  Returns (n_sample, messages, seconds) of the probe if the
-    probe already is the sample, else (n_sample, None, None)."""
-    probe = min(limit, threads)
-    m, dt = cpu_baseline(hb, probe, threads)
-    n = min(limit, max(probe, int(budget_s / max(dt, 1e-3)) * probe))
-    return (n, m, dt) if n == probe else (n, None, None)
+def cpu_sample_size(workload, cores):
+    # about 10-30 s of CPU: one rmsc03-sized instance takes ~0.3 s (2 h) per thread, a sparse_zi_1000 day ~0.05 s
+    per_thread = {"sparse_zi_100": 64, "sparse_zi_1000": 32, "rmsc01": 8, "rmsc01_literal": 4}.get(workload, 4)
+    return cores * per_thread
+
+
+def measure(eng, hb, steps, warmup, barrier, gather):
+    """W warm-up and K timed steps on the resident batch; returns (device ms, kernel ms, wall ms, launches, res)."""
+    for _ in range(warmup):
+        eng.reset()
+        eng.run()
+    res, _ = eng.results_arrays()
+    barrier()
+    t0 = time.perf_counter()
+    l0 = eng.launch_count()
+    dev_ms = kern_ms = 0.0
+    for _ in range(steps):
+        eng.reset()
+        eng.run()
+        r, _ = eng.results_arrays()
+        gather(r)
+        dev_ms += eng.last_reset_ms() + eng.last_run_ms()[0]
+        kern_ms += eng.last_run_ms()[0]
+    barrier()
+    return dev_ms, kern_ms, 1e3 * (time.perf_counter() - t0), eng.launch_count() - l0, res.copy()
 
 
 def main():
@@ -154,12 +224,15 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="sparse_zi_1000", choices=sorted(WORKLOADS))
-    ap.add_argument("--instances", type=int, default=1024, help="instances per GPU")
+    ap.add_argument("--workload", default="rmsc03", choices=sorted(WORKLOADS) + ["rmsc03_grid"])
+    ap.add_argument("--instances", type=int, default=0, help="instances per GPU (weak) or in total (strong); 0 = default")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--rng", default="mt", choices=["mt", "philox"])
+    ap.add_argument("--engine", default="auto", choices=["auto", "lane", "warp"])
     ap.add_argument("--seed", type=int, default=20261019)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-sample", type=int, default=0, help="instances in the CPU baseline sample (0 = auto)")
+    ap.add_argument("--also", default="sparse_zi_1000", help="second workload reported under `also` ('' = none)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -168,34 +241,40 @@ def main():
     from abides_b200 import _abi, runtime
     rng_mode = _abi.RNG_MT19937 if args.rng == "mt" else _abi.RNG_PHILOX
     cores = host_cores()
-    hours = {"rmsc03_2h": "09:30-11:30, kernel 00:00-11:31", "execution": "09:30-11:30, kernel 00:00-11:31",
-             "sparse_zi_100": "09:30-16:00, kernel 00:00-17:00", "sparse_zi_1000": "09:30-16:00, kernel 00:00-17:00"
-             }.get(args.workload, "09:30-16:00, kernel 00:00-16:01")
-    config = {"workload": "%s x %d seeds per GPU, one market day each (%s)" % (args.workload, args.instances, hours),
-              "instances_per_gpu": args.instances, "rng": args.rng,
-              "l2": "per-step working set (agent records + RNG state + queues) exceeds the 126 MB L2",
+    n_default = DEFAULT_INSTANCES.get(args.workload, 2048)
+    if args.scaling == "strong":
+        total = args.instances or n_default
+        lo, hi = runtime.shard_bounds(total, world, rank)
+        per_rank = hi - lo
+    else:
+        per_rank = args.instances or n_default
+        total = per_rank * world
+        lo, hi = rank * per_rank, (rank + 1) * per_rank
+    hours = HOURS.get(args.workload, "09:30-16:00, kernel 00:00-16:01")
+    config = {"workload": "%s x %d seeds %s, one market day each (%s)"
+                          % (args.workload, per_rank if args.scaling == "weak" else total,
+                             "per GPU" if args.scaling == "weak" else "in total, split over the GPUs", hours),
+              "instances_per_gpu": per_rank, "instances_total": total, "rng": args.rng,
+              "l2": "per-step working set (agent records + RNG state + queues, several GB) exceeds the 126 MB L2",
               "seeds": "np.random.RandomState(%d).randint(0, 2**32, n) as config/parallel.py:11" % args.seed}
 
     if args.impl == "reference":
         if rank != 0:
             return 0
-        seeds = runtime.parallel_seeds(args.seed, args.cpu_sample or args.instances)
-        hb, build_s = build_batch(args.workload, seeds, _abi.RNG_MT19937)
-        # one batch per step where that is a few seconds of CPU (the ZI workloads), else one instance per thread;
-        # the sizing probe doubles as the warm-up
-        n_sample = args.cpu_sample or bounded_sample(hb, len(seeds), cores)[0]
-        msgs = 0
-        t = 0.0
+        n_sample = args.cpu_sample or cpu_sample_size(args.workload, cores)
+        seeds = runtime.parallel_seeds(args.seed, max(n_sample, 1))
+        hb = build_cpu_sample(args.workload, seeds, n_sample)
+        cpu_run(hb, min(n_sample, cores), cores)                      # warm-up
+        msgs, t = 0, 0.0
         for _ in range(args.steps):
-            m, dt = cpu_baseline(hb, n_sample, cores)
+            m, dt, _ = cpu_run(hb, n_sample, cores)
             msgs += m
             t += dt
         v = msgs / t
         line = {"impl": "reference", "metric": "simulated order messages/sec", "value": v, "unit": "messages/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": v / BASELINE_PUBLISHED[args.workload] if args.workload in BASELINE_PUBLISHED else None,
-                "dtype": "int64+f64", "data": "synthetic", "config": config,
+                "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": args.scaling,
+                "vs_baseline": None, "dtype": "int64+f64", "data": "synthetic", "config": config,
                 "market_days_per_s": n_sample * args.steps / t,
                 "cpu_baseline": {"value": v, "unit": "messages/s", "cores": cores, "kind": "port",
                                  "sample": "%d instances of %s per step on %d host threads (C restatement of the "
@@ -205,10 +284,14 @@ def main():
         print(json.dumps(line), flush=True)
         return 0
 
-    # ---- our arm: build the host batch BEFORE touching CUDA (the builder forks a process pool) ----
-    seeds_all = runtime.parallel_seeds(args.seed, args.instances * world)
-    seeds = seeds_all[rank * args.instances:(rank + 1) * args.instances]
-    hb, build_s = build_batch(args.workload, seeds, rng_mode)
+    # ---- our arm: build the host batch BEFORE touching CUDA (the config-built path forks a process pool) ----
+    seeds_all = runtime.parallel_seeds(args.seed, total)
+    hb, build_s = build_batch(args.workload, seeds_all[lo:hi], rng_mode, args.seed)
+    cpu_hb = None
+    if world == 1:
+        n_sample = args.cpu_sample or cpu_sample_size(args.workload, cores)
+        n_sample = min(n_sample, per_rank)
+        cpu_hb = build_cpu_sample(args.workload, seeds_all[lo:hi], n_sample)
 
     import torch
     import numpy as np
@@ -219,21 +302,24 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     eng = Engine(local_rank)
+    eng.set_engine(args.engine)
+    pinned = pin_arrays(hb)
     eng.load(hb)
+    engine_id, variant = eng.engine_info()
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def gather_summaries(res):
+    def gather(res):
         """K6: the final gather of per-instance summary records (the path's only collective)."""
         return runtime.gather_summaries(res, dist, device=torch.device("cuda", local_rank))
 
-    for _ in range(args.warmup):
-        eng.reset()
-        eng.run()
-    res, _ = eng.results_arrays()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    dev_ms, kern_ms, wall_ms, launches, res = measure(eng, hb, args.steps, args.warmup, barrier, gather)
+    clocks = sampler.stop()
     # ABIDES_ESTATE (-4) marks an instance in which the REFERENCE itself would raise (e.g. AdaptiveMarketMakerAgent
     # placing orders before it has ever seen a two-sided book: int(None), AdaptiveMarketMakerAgent.py:226-231);
     # such instances stop there and are reported, anything else is a device error
@@ -243,44 +329,39 @@ def main():
                                                                       np.unique(res["status"]).tolist()))
     msgs_rank = int(res["ttl_messages"].sum())
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    barrier()
-    t0 = time.perf_counter()
-    dev_ms = 0.0
-    kern_ms = 0.0
-    for _ in range(args.steps):
-        eng.reset()
-        eng.run()
-        r, _ = eng.results_arrays()
-        gather_summaries(r)
-        dev_ms += eng.last_reset_ms() + eng.last_run_ms()[0]
-        kern_ms += eng.last_run_ms()[0]
-    barrier()
-    wall = time.perf_counter() - t0
-    clocks = sampler.stop()
-
-    # e2e: host buffers -> abides_load (H2D) -> abides_run -> abides_read_results (D2H)
-    pinned = pin_host_batch(hb)
+    # end to end through the public API with host buffers: H2D of every table, run, D2H of the results, gather
     barrier()
     t1 = time.perf_counter()
     for _ in range(args.e2e_steps):
         eng.load(hb)
         eng.run()
         r, a = eng.results_arrays()
-        gather_summaries(r)
+        gather(r)
     barrier()
-    e2e_wall = time.perf_counter() - t1
+    e2e_ms = 1e3 * (time.perf_counter() - t1)
     h2d = hb.h2d_bytes()
-    d2h = r.nbytes + a.nbytes
+    d2h = int(r.nbytes + a.nbytes)
 
-    tt = torch.tensor([dev_ms, wall * 1e3, e2e_wall * 1e3, kern_ms], dtype=torch.float64, device="cuda")
-    mm = torch.tensor([float(msgs_rank)], dtype=torch.float64, device="cuda")
+    tt = torch.tensor([dev_ms, wall_ms, e2e_ms, kern_ms], dtype=torch.float64, device="cuda")
+    mm = torch.tensor([float(msgs_rank), float(n_estate), float(per_rank)], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dist.all_reduce(mm, op=dist.ReduceOp.SUM)
     dev_ms, wall_ms, e2e_ms, kern_ms = [float(x) for x in tt.tolist()]
-    msgs_total = float(mm.item())
+    msgs_total, n_estate_total, inst_total = [float(x) for x in mm.tolist()]
+
+    also = None
+    if rank == 0 and world == 1 and args.also and args.also != args.workload:
+        # the second BASELINE config measured the same way (fewer steps): resident-input throughput only
+        w2 = args.also
+        n2 = DEFAULT_INSTANCES.get(w2, 4096)
+        hb2, _ = build_batch(w2, runtime.parallel_seeds(args.seed, n2), rng_mode, args.seed)
+        eng.load(hb2)
+        d2, k2, _, _, res2 = measure(eng, hb2, 1, 1, barrier, lambda r_: r_)
+        m2 = float(res2["ttl_messages"].sum())
+        also = {w2: {"value": m2 / (d2 / 1e3), "unit": "messages/s", "instances": n2, "steps": 1, "warmup": 1,
+                     "market_days_per_s": n2 / (d2 / 1e3), "engine": _abi.VARIANT_NAMES.get(eng.engine_info()[1]),
+                     "roofline_frac": m2 * ALGO_BYTES_PER_MESSAGE / (k2 / 1e3) / 1e9 / measured_hbm_peak()[0]}}
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -289,38 +370,39 @@ def main():
     peak, peak_src = measured_hbm_peak()
     value = msgs_total * args.steps / (dev_ms / 1e3)
     achieved = msgs_rank * args.steps * ALGO_BYTES_PER_MESSAGE / (kern_ms / 1e3) / 1e9
+    traffic = ncu_traffic(args.workload, per_rank, "lane" if engine_id == _abi.ENGINE_LANE else "warp")
     line = {
         "metric": "simulated order messages/sec", "value": value, "unit": "messages/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-        "scaling": "weak",
-        "vs_baseline": value / BASELINE_PUBLISHED[args.workload] if args.workload in BASELINE_PUBLISHED else None,
+        "scaling": args.scaling, "vs_baseline": None,
         "dtype": "int64+f64", "data": "synthetic", "config": config,
-        "market_days_per_s": args.instances * world * args.steps / (dev_ms / 1e3),
+        "engine": _abi.VARIANT_NAMES.get(variant, str(variant)),
+        "market_days_per_s": inst_total * args.steps / (dev_ms / 1e3),
         "messages_per_step": msgs_total, "wall_ms_per_step": wall_ms / args.steps, "host_build_s": build_s,
-        "clocks": clocks, "instances_stopped_where_reference_raises": n_estate,
+        "clocks": clocks, "instances_stopped_where_reference_raises": int(n_estate_total),
         "e2e": {"value": msgs_total * args.e2e_steps / (e2e_ms / 1e3), "unit": "messages/s",
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
                 "pinned_host_bytes": pinned,
-                "path": "Engine.load (abides_load, H2D of every table) -> Engine.run (abides_run) -> "
-                        "Engine.results_arrays (abides_read_results, D2H) -> summary gather"},
-        "gpu_launches": 3 * args.steps,
+                "path": "Engine.load (abides_load: H2D of every table from pinned host memory, device-side seeding of "
+                        "the RNG streams) -> Engine.run (abides_run) -> Engine.results_arrays (abides_read_results, "
+                        "D2H) -> summary gather"},
+        "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": ncu_traffic(args.workload, args.instances), "peak_source": peak_src,
-                     "kernel_ms_per_launch": kern_ms / args.steps,
-                     "note": "dominant kernel sim_kernel: %d B algorithmic per message x messages per launch / "
-                             "CUDA-event time of the launch (events on the library's launch stream). The kernel is "
-                             "instruction-fetch bound, not HBM bound: see DESIGN.md and profiles/"
-                             % ALGO_BYTES_PER_MESSAGE},
+                     "traffic": None if not traffic else traffic.get("dram_bytes_per_message", 0) * msgs_rank,
+                     "traffic_source": None if not traffic else traffic.get("source"),
+                     "peak_source": peak_src, "kernel_ms_per_launch": kern_ms / args.steps,
+                     "note": "dominant kernel lane_sim_kernel / sim_kernel: %d B algorithmic per message x messages per "
+                             "launch / CUDA-event time of the launch (events on the library's launch stream); `traffic` = "
+                             "ncu DRAM bytes per message of the committed capture x messages per launch. The kernel is "
+                             "latency bound, not HBM bound: see DESIGN.md and profiles/" % ALGO_BYTES_PER_MESSAGE},
+        "reference_note": REFERENCE_NOTE,
     }
-    line["reference_note"] = REFERENCE_NOTE
-    if world == 1:
-        if args.cpu_sample:
-            n_sample, m, dt = args.cpu_sample, None, None
-        else:
-            n_sample, m, dt = bounded_sample(hb, args.instances, cores)    # the whole batch when that takes seconds
-        if m is None:
-            m, dt = cpu_baseline(hb, n_sample, cores)
-        line["cpu_sample_ttl_messages_match"] = bool(CPU_TTL == [int(x) for x in res["ttl_messages"][:n_sample]])
+    if also:
+        line["also"] = also
+    if cpu_hb is not None:
+        m, dt, ttl = cpu_run(cpu_hb, n_sample, cores)
+        line["cpu_sample_ttl_messages_match"] = bool(ttl == [int(x) for x in res["ttl_messages"][:n_sample]]) \
+            if args.workload != "rmsc03_grid" and args.rng == "mt" else None
         line["cpu_baseline"] = {"value": m / dt, "unit": "messages/s", "cores": cores, "kind": "port",
                                 "sample": "first %d instances of the same batch on %d host threads, %.1f s "
                                           "(oracle/abides_oracle.c)" % (n_sample, cores, dt)}

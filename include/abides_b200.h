@@ -293,6 +293,8 @@ int  abides_read_trace(abides_handle* h, int32_t instance, abides_trace_rec* out
 /* device-side timing of the last abides_run (CUDA events on the launching stream), ms */
 int  abides_last_run_ms(abides_handle* h, float* ms, int32_t* n_launches);
 int  abides_last_reset_ms(abides_handle* h, float* ms);
+/* kernels this handle has launched since abides_create (loads, resets and runs) */
+int  abides_launch_count(abides_handle* h, int64_t* n);
 /* per-phase cycle / event counters summed over instances since the last load / reset (all zero unless the
  * library was built with -DABIDES_PROFILE; slots: see enum P_* in csrc/engine.cu) */
 int  abides_read_profile(abides_handle* h, uint64_t* out, int32_t n);

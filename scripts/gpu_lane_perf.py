@@ -13,7 +13,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np                                    # noqa: E402
-from abides_b200 import lowering, runtime, sweep      # noqa: E402
+from abides_b200 import _abi, lowering, runtime, sweep   # noqa: E402
 from abides_b200.engine import Engine                 # noqa: E402
 import bench                                          # noqa: E402
 
@@ -32,7 +32,8 @@ def main():
     seeds = runtime.parallel_seeds(20261019, n)
     t0 = time.time()
     if sweep.supported(cfg) and not os.environ.get("ABIDES_FULL_STATE_UPLOAD"):
-        hb = sweep.build_sweep(cfg, seeds, extra)             # streams by seed, vectorised config-time draws
+        rng = _abi.RNG_PHILOX if os.environ.get("ABIDES_PERF_RNG") == "philox" else _abi.RNG_MT19937
+        hb = sweep.build_sweep(cfg, seeds, extra, rng_mode=rng)    # streams by seed, vectorised config-time draws
     else:
         specs = runtime.build_specs_parallel(cfg, [list(extra) + ["-s", s] for s in seeds])
         need = 2 * sum(s.mt_key.nbytes for s in specs[:1]) * n / 1e9

@@ -29,8 +29,9 @@ def main():
     eng._ck(eng._L.abides_read_profile(eng._h, out, 16), "abides_read_profile")
     rounds, pop, sort, handle, wait, events = [int(out[i]) for i in range(6)]
     res, _ = eng.results_arrays()
-    n_cta = (n + 127) // 128
-    print(json.dumps({"workload": workload, "instances": n, "run_ms": ms, "messages": int(res["ttl_messages"].sum()),
+    cta = int(os.environ.get("ABIDES_LANE_CTA", "128"))
+    n_cta = (n + cta - 1) // cta
+    print(json.dumps({"lib": os.path.basename(os.environ["ABIDES_B200_LIB"]), "workload": workload, "instances": n, "run_ms": ms, "messages": int(res["ttl_messages"].sum()),
                       "delivered": int(res["delivered"].sum()), "ctas": n_cta, "rounds_per_cta": rounds / n_cta,
                       "events_per_round": events / max(rounds, 1),
                       "cycles_per_round": {"pop": pop / max(rounds, 1), "sort": sort / max(rounds, 1),

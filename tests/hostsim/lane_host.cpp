@@ -81,7 +81,8 @@ int hostsim_run(const abides_batch* b, int force_variant, abides_instance_result
   LaneBatch lb;
   memset(&lb, 0, sizeof lb);
   lb.n_instances = ni; lb.trace_cap = (int)trace_capacity; lb.n_types = b->n_types; lb.top_k = cap.top_k;
-  lb.run_ahead = getenv("ABIDES_LANE_RUN_AHEAD") ? atoi(getenv("ABIDES_LANE_RUN_AHEAD")) : 6;
+  lb.rng_mode = b->rng_mode;
+  lb.run_ahead = getenv("ABIDES_LANE_RUN_AHEAD") ? atoi(getenv("ABIDES_LANE_RUN_AHEAD")) : 0;
   lb.hcap = cap.hcap; lb.scap = cap.scap; lb.arena_cap = cap.arena_cap; lb.deep_cap = cap.deep_cap;
   lb.txn_cap = cap.txn_cap; lb.unr_cap = cap.unr_cap;
   lb.cfg = b->instances; lb.types = b->types;
@@ -92,15 +93,16 @@ int hostsim_run(const abides_batch* b, int force_variant, abides_instance_result
   lb.agent_theta = b->agent_theta;
   lb.mom_index = mom_index.data();
   // the loader's RNG work (abides_load): rows, seeding, constructor draws -- on writable copies of the tables
-  const bool seeded = b->mt_key_row != nullptr;
+  const bool philox = b->rng_mode == ABIDES_RNG_PHILOX;
+  const bool seeded = b->mt_key_row != nullptr && !philox;
   std::vector<int> dev_row;
-  size_t n_rows = ns;
+  size_t n_rows = philox ? 0 : ns;
   if (seeded) n_rows = lane_assign_rows(b, dev_row);
-  unsigned* mt = own.keep(zalloc<unsigned>(n_rows * ABIDES_MT_N));
-  if (b->mt_key) memcpy(mt, b->mt_key, (seeded ? (size_t)b->n_mt_rows : ns) * ABIDES_MT_N * sizeof(unsigned));
-  int* pos = own.keep(dup<int>(b->mt_pos, ns));
-  int* hg = own.keep(dup<int>(b->mt_has_gauss, ns));
-  double* gs = own.keep(dup<double>(b->mt_gauss, ns));
+  unsigned* mt = philox ? nullptr : own.keep(zalloc<unsigned>(n_rows * ABIDES_MT_N));
+  if (b->mt_key && !philox) memcpy(mt, b->mt_key, (seeded ? (size_t)b->n_mt_rows : ns) * ABIDES_MT_N * sizeof(unsigned));
+  int* pos = own.keep(b->mt_pos ? dup<int>(b->mt_pos, ns) : zalloc<int>(ns));
+  int* hg = own.keep(b->mt_has_gauss ? dup<int>(b->mt_has_gauss, ns) : zalloc<int>(ns));
+  double* gs = own.keep(b->mt_gauss ? dup<double>(b->mt_gauss, ns) : zalloc<double>(ns));
   int* theta = own.keep(zalloc<int>((size_t)b->n_theta_total + 1));
   if (!(b->draw_flags & ABIDES_DRAW_ZI_THETA) && b->theta) memcpy(theta, b->theta, (size_t)b->n_theta_total * sizeof(int));
   long long* size = own.keep(dup<long long>((const long long*)b->agent_size, (size_t)na));
@@ -109,7 +111,7 @@ int hostsim_run(const abides_batch* b, int force_variant, abides_instance_result
     memset(&p, 0, sizeof p);
     p.n_instances = ni; p.draw_flags = b->draw_flags; p.cfg = b->instances; p.types = b->types;
     p.agent_type = b->agent_type; p.agent_theta = b->agent_theta; p.theta = theta; p.size = size;
-    p.mt = mt; p.staging = nullptr; p.key_row = b->mt_key_row; p.dev_row = seeded ? dev_row.data() : nullptr;
+    p.mt = mt; p.staging = nullptr; p.key_row = seeded ? b->mt_key_row : nullptr; p.dev_row = seeded ? dev_row.data() : nullptr;
     p.seed = b->mt_seed; p.pos = pos; p.has_gauss = hg; p.gauss = gs;
     for (int i = 0; i < ni; i++) {
       const int n = b->instances[i].n_agents + ABIDES_EXTRA_STREAMS;

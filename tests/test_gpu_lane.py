@@ -139,3 +139,22 @@ def test_seeded_sweep_equals_config_built_instances_on_device(config, extra, see
     hb = lowering.HostBatch(_sweep(config, seeds, extra))
     ores, oares = _oracle_arrays(hb)
     _same_results(res, ares, ores, oares)
+
+
+@pytest.mark.parametrize("engine", ["lane", "warp"])
+def test_philox_throughput_mode_on_device_matches_oracle(engine):
+    """Philox4x32-10 keyed streams: lane engine == warp engine == oracle; and the seeded sweep batch in Philox mode
+    (no MT19937 state on the device at all) runs the same days."""
+    from abides_b200 import sweep
+    seeds = list(range(300, 340))
+    hb = lowering.HostBatch(_sweep("sparse_zi_100", seeds), rng_mode=_abi.RNG_PHILOX)
+    for i, sd in enumerate(seeds):
+        hb.instances[i].seed = sd
+    eng, res, ares = device_run(hb, engine=engine)
+    ores, oares = _oracle_arrays(hb)
+    _same_results(res, ares, ores, oares)
+    if engine == "lane":
+        sb = sweep.build_sweep("sparse_zi_100", seeds, rng_mode=_abi.RNG_PHILOX)
+        assert sb.h2d_bytes() < 100 * sb.n_agents_total
+        eng2, res2, ares2 = device_run(sb, engine="lane")
+        _same_results(res2, ares2, res, ares)

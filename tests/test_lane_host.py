@@ -160,3 +160,26 @@ def test_vec_random_state_is_numpy_legacy_random_state():
     for i in (0, 31):
         st, mine = refs[i].get_state(), v.numpy_state(i)
         assert np.array_equal(st[1], mine[1]) and tuple(st[2:]) == tuple(mine[2:])
+
+
+@pytest.mark.parametrize("config, extra, seeds", [SWEEPS[0], SWEEPS[2]])
+def test_lane_philox_streams_match_oracle(config, extra, seeds):
+    """Throughput mode: counter-based Philox4x32-10 streams keyed by (instance seed, stream).  The lane engine, the
+    oracle and the seeded sweep batch (constructor draws still from RandomState(seed), by throw-away generators)
+    implement the same keyed streams, so their runs are bit-identical to each other."""
+    from abides_b200 import sweep, _abi
+    specs = [s for s, _ in runtime.build_instances(config, [list(extra) + ["-s", str(s)] for s in seeds])]
+    hb = lowering.HostBatch(specs, rng_mode=_abi.RNG_PHILOX)
+    for i, sd in enumerate(seeds):
+        hb.instances[i].seed = sd                                # the sweep builder keys each instance by its config seed
+    res, ares, _, _, _ = hostsim.run(hb)
+    ores, oares = oracle.run_batch(hb)
+    o = np.frombuffer(oares, dtype=ares.dtype)
+    assert [int(ores[i].ttl_messages) for i in range(len(seeds))] == [int(x) for x in res["ttl_messages"]]
+    assert (res["status"] == 0).all()
+    for f in ("cash", "holdings", "marked_to_market"):
+        assert np.array_equal(ares[f], o[f]), f
+    sb = sweep.build_sweep(config, seeds, extra, rng_mode=_abi.RNG_PHILOX)
+    res2, ares2, _, _, _ = hostsim.run(sb)
+    assert np.array_equal(res2["ttl_messages"], res["ttl_messages"]) and np.array_equal(ares2["cash"], ares["cash"])
+    assert len(set(int(x) for x in res["ttl_messages"])) > 1
