@@ -50,22 +50,17 @@
 #include "abides_b200.h"
 #include "abides_dd_math.h"
 #include "lane_host_common.h"
+#include "lane_kernels.h"
 
 #define FULL 0xffffffffu
 #define UNLIKELY(x) __builtin_expect(!!(x), 0)
 #define LIKELY(x) __builtin_expect(!!(x), 1)
 
 // ----------------------------------------------------------------------------------------------
-// the LANE engine (lane_device.inc): one instance per thread, used for large batches.  See lane_types.h.
+// the LANE engine (lane_kernels.cu / lane_device.inc): one instance per thread, used for large batches
 // ----------------------------------------------------------------------------------------------
 #define LN_INL __device__ __forceinline__
 #define LN_BIG __device__ __noinline__
-#define LN_KERNEL __global__
-#define LN_GRID_CONSTANT __grid_constant__
-#define LN_THREAD_INDEX() ((int)(blockIdx.x * blockDim.x + threadIdx.x))
-namespace lane {
-#include "lane_variants.inc"
-}
 // load-time RNG work shared by both engines: seeding of streams described by their seed, constructor-time draws
 namespace rngsetup {
 #include "rng_setup_device.inc"
@@ -126,7 +121,6 @@ __global__ void __launch_bounds__(32 * SKIP_WARPS) rng_skip_kernel(const __grid_
   if (lane == 0) p.pos[s] = (int)(k - (twists - 1) * ABIDES_MT_N);
 }
 }  // namespace rngsetup
-constexpr int LANE_BLOCK = 32;          // threads per block: instances are independent, small blocks spread over more SMs
 
 namespace {
 
@@ -676,20 +670,7 @@ int launch_init(abides_handle* h) {
   CK(cudaMemsetAsync(d.res, 0, (size_t)d.n_instances * sizeof(abides_instance_result), h->stream));
   CK(cudaMemsetAsync(d.prof, 0, N_PROF * sizeof(unsigned long long), h->stream));
   if (h->lane_variant != lane::LV_NONE) {
-    const lane::LaneBatch& lb = h->lb;
-    const int tg = (d.n_types + 63) / 64, ig = (d.n_instances + LANE_BLOCK - 1) / LANE_BLOCK;
-#define LAUNCH_LANE_INIT(ns)                                                  \
-  do {                                                                        \
-    lane::ns::lane_init_types_kernel<<<tg, 64, 0, h->stream>>>(lb);           \
-    lane::ns::lane_init_kernel<<<ig, LANE_BLOCK, 0, h->stream>>>(lb);         \
-  } while (0)
-    switch (h->lane_variant) {
-      case lane::LV_ZI_LEGACY: LAUNCH_LANE_INIT(lv_zi_legacy); break;
-      case lane::LV_ZI_CUBIC: LAUNCH_LANE_INIT(lv_zi_cubic); break;
-      case lane::LV_RMSC: LAUNCH_LANE_INIT(lv_rmsc); break;
-      default: LAUNCH_LANE_INIT(lv_full); break;
-    }
-#undef LAUNCH_LANE_INIT
+    CK(lane::launch_init(h->lane_variant, h->lb, h->stream));
     CK(cudaGetLastError());
     h->launches_since_load += 2;
     return 0;
@@ -1121,15 +1102,7 @@ int abides_run(abides_handle* h, int64_t until_time) {
   CK(cudaSetDevice(h->device));
   CK(cudaEventRecord(h->ev0, h->stream));
   if (h->lane_variant != lane::LV_NONE) {
-    const int grid = (h->n_instances + lane::LANE_CTA - 1) / lane::LANE_CTA;
-#define LAUNCH_LANE(ns) lane::ns::lane_sim_kernel<<<grid, lane::LANE_CTA, 0, h->stream>>>(h->lb, (long long)until_time)
-    switch (h->lane_variant) {
-      case lane::LV_ZI_LEGACY: LAUNCH_LANE(lv_zi_legacy); break;
-      case lane::LV_ZI_CUBIC: LAUNCH_LANE(lv_zi_cubic); break;
-      case lane::LV_RMSC: LAUNCH_LANE(lv_rmsc); break;
-      default: LAUNCH_LANE(lv_full); break;
-    }
-#undef LAUNCH_LANE
+    CK(lane::launch_sim(h->lane_variant, h->lb, (long long)until_time, h->stream));
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev1, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -1261,8 +1234,7 @@ int abides_replay_book(abides_handle* h, int32_t n_books, const int64_t* op_offs
     RCK(cudaMemcpyAsync(d_ops, ops, sizeof(abides_book_op) * n_ops, cudaMemcpyHostToDevice, h->stream));
     RCK(cudaMemsetAsync(d_ev, 0, sizeof(abides_book_event) * n_ops * max_events_per_op, h->stream));
     RCK(cudaEventRecord(h->ev0, h->stream));
-    lane::lv_full::lane_replay_kernel<<<(n_books + LANE_BLOCK - 1) / LANE_BLOCK, LANE_BLOCK, 0, h->stream>>>(
-        lb, n_books, d_off, d_ops, stream_history, max_events_per_op, d_ev, d_cnt, d_st);
+    RCK(lane::launch_replay(lb, n_books, d_off, d_ops, stream_history, max_events_per_op, d_ev, d_cnt, d_st, h->stream));
     RCK(cudaGetLastError());
     RCK(cudaEventRecord(h->ev1, h->stream));
     RCK(cudaMemcpyAsync(events_out, d_ev, sizeof(abides_book_event) * n_ops * max_events_per_op, cudaMemcpyDeviceToHost, h->stream));

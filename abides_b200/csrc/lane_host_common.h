@@ -53,13 +53,18 @@ inline size_t lane_assign_rows(const abides_batch* b, std::vector<int>& dev_row)
 
 struct LaneCaps { int hcap, scap, arena_cap, deep_cap, txn_cap, unr_cap, top_k; };
 inline LaneCaps lane_caps(int max_agents, int variant, bool needs_tv) {
+  // Capacities are per instance and decide how many instances fit in HBM, i.e. the engine's throughput; every one of
+  // them is checked on the device (ABIDES_EOVERFLOW stops the instance, never silently).
   LaneCaps c;
-  c.hcap = 3 * max_agents + 4096;            // events in flight (peak seen: 2 per agent at the market-open burst)
+  const int n = max_agents;
+  c.hcap = 2 * n + 4096;                     // events in flight: peak 2 n - 1 at the opening handshake
   c.scap = c.hcap;                           // message payload slots
-  c.arena_cap = 4 * max_agents + 4096;       // open-order entries of all agents (lists grow by doubling)
-  c.deep_cap = 2 * max_agents + 1024;        // pool slots per book side
-  c.txn_cap = needs_tv ? 1 << 15 : 0;        // transaction rows between two volume queries
-  c.unr_cap = needs_tv ? 1 << 15 : 0;        // de-duplicated rows inside the longest look-back window
+  c.arena_cap = 4 * n + 4096;                // open-order entries of all agents (lists grow by doubling)
+  // pool slots per book side: the rmsc populations rest at most a few hundred orders (the deque of 128 holds nearly
+  // all of them); a ZI population rests up to one order per agent, spread over thousands of ticks
+  c.deep_cap = variant == LV_RMSC ? n / 4 + 1024 : n + 1024;
+  c.txn_cap = needs_tv ? 1 << 14 : 0;        // transaction rows between two volume queries
+  c.unr_cap = needs_tv ? 1 << 14 : 0;        // de-duplicated rows inside the longest look-back window
   c.top_k = lane_top_k(variant);
   return c;
 }

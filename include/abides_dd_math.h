@@ -28,7 +28,11 @@
 
 #if defined(__CUDACC__)
 #define ABM_HD __host__ __device__ __forceinline__
+#ifdef ABM_INLINE_BIG
+#define ABM_HD_BIG __host__ __device__ __forceinline__   /* lane engine: a fetched instruction serves 32 instances */
+#else
 #define ABM_HD_BIG __host__ __device__ __noinline__      /* keep the big bodies out of every call site */
+#endif
 #define ABM_FMA(a, b, c) fma((a), (b), (c))
 #else
 #define ABM_HD static inline

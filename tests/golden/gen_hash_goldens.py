@@ -43,8 +43,14 @@ def one(job):
     name, seed, ref_args = job
     out = tempfile.mkdtemp(prefix="abides_hash_")
     tag = "%s_%d" % (name, seed)
-    subprocess.run([sys.executable, os.path.join(HERE, "gen_golden.py"), "--name", tag, "--out", out, "--"] + ref_args +
-                   ["-s", str(seed)], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    run = subprocess.run([sys.executable, os.path.join(HERE, "gen_golden.py"), "--name", tag, "--out", out, "--"] + ref_args +
+                         ["-s", str(seed)], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
+    if run.returncode != 0:
+        # the reference itself raised (e.g. AdaptiveMarketMakerAgent.receiveMessage before the book has ever been
+        # two-sided: UnboundLocalError, AdaptiveMarketMakerAgent.py:141-176): the engines must stop such an instance
+        # with ABIDES_ESTATE
+        last = [ln for ln in run.stderr.strip().splitlines() if ln.strip()][-1]
+        return name, seed, dict(reference_raises=last.split(":")[0].strip())
     g = np.load(os.path.join(out, tag + ".golden.npz"))
     meta = json.loads(str(g["meta"]))
     rec = dict(ttl_messages=meta["ttl_messages"], delivered=meta["delivered"], last_trade=meta["last_trade"],

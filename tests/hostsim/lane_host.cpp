@@ -13,6 +13,7 @@
 
 #define LN_INL static inline
 #define LN_BIG static
+#define LN_HOT static inline
 #define LN_KERNEL static
 #define LN_GRID_CONSTANT
 #define LN_THREAD_INDEX() g_thread_index
@@ -75,7 +76,17 @@ int hostsim_run(const abides_batch* b, int force_variant, abides_instance_result
   }
   if (variant_out) *variant_out = variant;
   const bool needs_tv = (class_mask & ((1u << ABIDES_ADAPTIVE_MM) | (1u << ABIDES_POV_EXEC))) != 0;
-  const LaneCaps cap = lane_caps(max_agents, variant, needs_tv);
+  LaneCaps cap = lane_caps(max_agents, variant, needs_tv);
+  if (const char* ov = getenv("HOSTSIM_CAPS")) {       // tests of the overflow paths: "hcap,scap,arena,deep,txn,unr" (0 = keep)
+    int v[6] = {0, 0, 0, 0, 0, 0};
+    sscanf(ov, "%d,%d,%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5]);
+    if (v[0]) cap.hcap = v[0];
+    if (v[1]) cap.scap = v[1];
+    if (v[2]) cap.arena_cap = v[2];
+    if (v[3]) cap.deep_cap = v[3];
+    if (v[4] && needs_tv) cap.txn_cap = v[4];
+    if (v[5] && needs_tv) cap.unr_cap = v[5];
+  }
   const size_t ns = (size_t)na + (size_t)ABIDES_EXTRA_STREAMS * ni;
   Owned own;
   LaneBatch lb;

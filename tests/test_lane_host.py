@@ -183,3 +183,42 @@ def test_lane_philox_streams_match_oracle(config, extra, seeds):
     res2, ares2, _, _, _ = hostsim.run(sb)
     assert np.array_equal(res2["ttl_messages"], res["ttl_messages"]) and np.array_equal(ares2["cash"], ares["cash"])
     assert len(set(int(x) for x in res["ttl_messages"])) > 1
+
+
+@pytest.mark.parametrize("caps, name", [
+    ("150,0,0,0,0,0", "zi100_s123456789"),        # event heap: 2 n - 1 events at the opening handshake do not fit in 150
+    ("0,60,0,0,0,0", "zi100_s123456789"),         # message payload slots
+    ("0,0,40,0,0,0", "zi100_s123456789"),         # open-order arena
+    ("0,0,0,8,0,0", "zi100_s123456789"),          # book pool: a ZI book rests far more than 32 + 8 orders per side
+    ("0,0,0,0,16,0", "rmsc03_s1234_1000"),        # transaction rows between two volume queries
+    ("0,0,0,0,0,16", "rmsc03_s1234_1000"),        # unrolled rows inside the look-back window
+])
+def test_lane_capacity_overflow_stops_the_instance_loudly(caps, name, monkeypatch):
+    """Every fixed capacity of the lane engine is checked where it is consumed: an instance that outgrows one ends with
+    ABIDES_EOVERFLOW (never a silent wrap or a write past the end), and its neighbours in the batch are unaffected."""
+    g, meta = load_golden(name)
+    spec = build_case(name)
+    hb = lowering.HostBatch([spec])
+    monkeypatch.setenv("HOSTSIM_CAPS", caps)
+    res, ares, _, _, _ = hostsim.run(hb)
+    assert res["status"][0] == _abi_mod().EOVERFLOW
+    assert res["ttl_messages"][0] < meta["ttl_messages"]
+    monkeypatch.delenv("HOSTSIM_CAPS")
+    res, ares, _, _, _ = hostsim.run(hb)
+    assert res["status"][0] == 0 and res["ttl_messages"][0] == meta["ttl_messages"]
+
+
+def _abi_mod():
+    from abides_b200 import _abi
+    return _abi
+
+
+def test_lane_event_beyond_the_key_range_is_an_overflow():
+    """Event times are stored as 48-bit offsets from the kernel start (78 hours): a wakeup requested past that ends the
+    instance with ABIDES_EOVERFLOW instead of wrapping into the past."""
+    spec = build_case("rmsc03_s1234_1000")
+    spec.wakeup_time = spec.wakeup_time.copy()
+    noise = [i for i, t in enumerate(spec.agent_type) if spec.types[t]["klass"] == _abi_mod().NOISE]
+    spec.wakeup_time[noise[0]] = spec.cfg["start_time"] + 100 * 3600 * 10 ** 9
+    res, ares, _, _, _ = hostsim.run(lowering.HostBatch([spec]))
+    assert res["status"][0] == _abi_mod().EOVERFLOW
