@@ -155,7 +155,7 @@ LIB_PATH = os.environ.get("ABIDES_B200_LIB") or os.path.join(_PKG_DIR, "csrc", "
 EXPORTS = [
     "abides_create", "abides_destroy", "abides_last_error", "abides_version", "abides_load",
     "abides_reset", "abides_run", "abides_read_results", "abides_read_trace", "abides_last_run_ms", "abides_last_reset_ms", "abides_read_profile",
-    "abides_replay_book", "abides_set_engine", "abides_engine_info", "abides_launch_count",
+    "abides_replay_book", "abides_set_engine", "abides_engine_info", "abides_launch_count", "abides_dense_fundamental",
 ]
 ENGINE_AUTO, ENGINE_WARP, ENGINE_LANE = 0, 1, 2        # enum abides_engine
 LANE_AUTO_MIN_INSTANCES = 4096
@@ -211,5 +211,9 @@ def lib():
     L.abides_engine_info.restype = C.c_int
     L.abides_launch_count.argtypes = [H, C.POINTER(C.c_int64)]
     L.abides_launch_count.restype = C.c_int
+    L.abides_dense_fundamental.argtypes = [H, C.c_int32, C.POINTER(C.c_uint32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                           C.POINTER(C.c_double), C.c_double, C.c_double, C.c_double, C.c_int64,
+                                           C.POINTER(C.c_int64)]
+    L.abides_dense_fundamental.restype = C.c_int
     _lib = L
     return L

@@ -120,6 +120,30 @@ __global__ void __launch_bounds__(32 * SKIP_WARPS) rng_skip_kernel(const __grid_
   __syncwarp();
   if (lane == 0) p.pos[s] = (int)(k - (twists - 1) * ABIDES_MT_N);
 }
+// util/oracle/MeanRevertingOracle.py:49-81 -- the DENSE mean-reverting fundamental: one value per time step,
+//   r[0] = r_bar;  r[t] = max(0, kappa r_bar + (1 - kappa) r[t-1] + shock[t]),  shock = normal(scale = sqrt(sigma_s), size = T)
+// drawn from the stream whose state is handed in (the reference uses the process-global np.random).  The recurrence is
+// sequential in t, so the kernel vectorises ACROSS series: one thread per (seed, symbol) series, states in HBM.
+__global__ void dense_fundamental_kernel(int n_series, unsigned* mt, int* pos, int* has_gauss, double* gauss, double r_bar,
+                                         double kappa, double sigma_s, long long n_steps, long long* out) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_series) return;
+  SeqRng r;
+  r.mt = mt + (size_t)s * ABIDES_MT_N; r.pos = pos[s]; r.has_gauss = has_gauss[s]; r.gauss = gauss[s];
+  const double scale = sqrt(sigma_s);
+  long long* o = out + (size_t)s * n_steps;
+  double prev = r_bar;
+  for (long long t = 0; t < n_steps; t++) {
+    const double shock = 0.0 + scale * seq_gauss(r);         // np.random.normal(loc=0.0, scale): loc + scale * gauss
+    if (t > 0) {
+      double v = (kappa * r_bar) + ((1 - kappa) * prev);
+      v = v + shock;
+      prev = v < 0 ? 0.0 : v;                                // max(0, v)
+    }
+    o[t] = (long long)rint(prev);                            // np.round(r).astype(int)
+  }
+  pos[s] = r.pos; has_gauss[s] = r.has_gauss; gauss[s] = r.gauss;
+}
 }  // namespace rngsetup
 
 namespace {
@@ -919,6 +943,8 @@ int abides_load(abides_handle* h, const abides_batch* b) {
       if ((rc = dev_alloc(h, &lb.agents, (size_t)na))) return rc;
       if ((rc = dev_alloc(h, &lb.state, (size_t)ni))) return rc;
       if ((rc = dev_alloc(h, &lb.hkeys, (size_t)ni * lane::heap_stride(lcap.hcap)))) return rc;
+      lb.near_cap = lane::lane_near_cap(lane_variant);
+      if ((rc = dev_alloc(h, &lb.near, (size_t)ni * lb.near_cap))) return rc;
       if ((rc = dev_alloc(h, &lb.hpay, (size_t)ni * lcap.scap))) return rc;
       if ((rc = dev_alloc(h, &lb.hfree, (size_t)ni * lcap.scap))) return rc;
       if ((rc = dev_alloc(h, &lb.top, (size_t)ni * 2 * lcap.top_k))) return rc;
@@ -1143,6 +1169,46 @@ int abides_read_profile(abides_handle* h, uint64_t* out, int32_t n) {
   unsigned long long tmp[N_PROF];
   CK(cudaMemcpy(tmp, h->db.prof, sizeof tmp, cudaMemcpyDeviceToHost));
   for (int i = 0; i < n; i++) out[i] = i < N_PROF ? tmp[i] : 0;
+  return 0;
+}
+
+int abides_dense_fundamental(abides_handle* h, int32_t n_series, uint32_t* mt_key, int32_t* mt_pos, int32_t* mt_has_gauss,
+                             double* mt_gauss, double r_bar, double kappa, double sigma_s, int64_t n_steps, int64_t* out) {
+  if (!h || n_series <= 0 || !mt_key || !mt_pos || !mt_has_gauss || !mt_gauss || !out || n_steps <= 0)
+    return fail(ABIDES_EINVAL, "abides_dense_fundamental: bad argument");
+  if (!(sigma_s >= 0)) return fail(ABIDES_EINVAL, "abides_dense_fundamental: sigma_s must be a variance >= 0");
+  for (int i = 0; i < n_series; i++)
+    if (mt_pos[i] < 0 || mt_pos[i] > ABIDES_MT_N) return fail(ABIDES_EINVAL, "abides_dense_fundamental: bad mt_pos");
+  CK(cudaSetDevice(h->device));
+  unsigned* d_mt = nullptr; int *d_pos = nullptr, *d_hg = nullptr; double* d_g = nullptr; long long* d_out = nullptr;
+  auto cleanup = [&]() { cudaFree(d_mt); cudaFree(d_pos); cudaFree(d_hg); cudaFree(d_g); cudaFree(d_out); };
+#define RCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return fail(ABIDES_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
+  const size_t n = (size_t)n_series;
+  RCK(cudaMalloc(&d_mt, n * ABIDES_MT_N * sizeof(unsigned)));
+  RCK(cudaMalloc(&d_pos, n * sizeof(int)));
+  RCK(cudaMalloc(&d_hg, n * sizeof(int)));
+  RCK(cudaMalloc(&d_g, n * sizeof(double)));
+  RCK(cudaMalloc(&d_out, n * (size_t)n_steps * sizeof(long long)));
+  RCK(cudaMemcpyAsync(d_mt, mt_key, n * ABIDES_MT_N * sizeof(unsigned), cudaMemcpyHostToDevice, h->stream));
+  RCK(cudaMemcpyAsync(d_pos, mt_pos, n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  RCK(cudaMemcpyAsync(d_hg, mt_has_gauss, n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  RCK(cudaMemcpyAsync(d_g, mt_gauss, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  RCK(cudaEventRecord(h->ev0, h->stream));
+  rngsetup::dense_fundamental_kernel<<<(n_series + 63) / 64, 64, 0, h->stream>>>(n_series, d_mt, d_pos, d_hg, d_g, r_bar, kappa,
+                                                                                  sigma_s, (long long)n_steps, d_out);
+  RCK(cudaGetLastError());
+  RCK(cudaEventRecord(h->ev1, h->stream));
+  RCK(cudaMemcpyAsync(out, d_out, n * (size_t)n_steps * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+  RCK(cudaMemcpyAsync(mt_key, d_mt, n * ABIDES_MT_N * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
+  RCK(cudaMemcpyAsync(mt_pos, d_pos, n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  RCK(cudaMemcpyAsync(mt_has_gauss, d_hg, n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  RCK(cudaMemcpyAsync(mt_gauss, d_g, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  RCK(cudaStreamSynchronize(h->stream));
+  RCK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+#undef RCK
+  h->last_launches = 1;
+  h->launches_since_load += 1;
+  cleanup();
   return 0;
 }
 

@@ -21,6 +21,7 @@
 #else
 #define LN_HOT __device__ __forceinline__
 #endif
+#define LN_PREFETCH(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
 #define LN_KERNEL __global__
 #define LN_GRID_CONSTANT __grid_constant__
 #define LN_THREAD_INDEX() ((int)(blockIdx.x * blockDim.x + threadIdx.x))

@@ -60,6 +60,28 @@ class Engine:
         self._ck(self._L.abides_engine_info(self._h, C.byref(e), C.byref(v)), "abides_engine_info")
         return e.value, v.value
 
+    def dense_fundamental(self, states, r_bar, kappa, sigma_s, n_steps):
+        """MeanRevertingOracle.generate_fundamental_value_series (util/oracle/MeanRevertingOracle.py:49-81) for many
+        series at once.  `states` is a list of numpy legacy state tuples (np.random.get_state()) or of integer seeds;
+        returns (int64[n_series, n_steps], advanced states)."""
+        from .vecrng import init_genrand
+        n = len(states)
+        key = np.zeros((n, _abi.MT_N), np.uint32)
+        pos = np.full(n, _abi.MT_N, np.int32)
+        hg = np.zeros(n, np.int32)
+        gs = np.zeros(n, np.float64)
+        for i, st in enumerate(states):
+            if isinstance(st, (int, np.integer)):
+                key[i] = init_genrand([int(st)])[0]
+            else:
+                key[i], pos[i], hg[i], gs[i] = np.asarray(st[1], np.uint32), int(st[2]), int(st[3]), float(st[4])
+        out = np.zeros((n, int(n_steps)), np.int64)
+        p = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+        self._ck(self._L.abides_dense_fundamental(self._h, n, p(key, C.c_uint32), p(pos, C.c_int32), p(hg, C.c_int32),
+                                                  p(gs, C.c_double), float(r_bar), float(kappa), float(sigma_s),
+                                                  int(n_steps), p(out, C.c_int64)), "abides_dense_fundamental")
+        return out, [("MT19937", key[i].copy(), int(pos[i]), int(hg[i]), float(gs[i])) for i in range(n)]
+
     def launch_count(self):
         """Kernels launched through this handle so far."""
         n = C.c_int64(0)

@@ -306,6 +306,18 @@ int  abides_replay_book(abides_handle* h, int32_t n_books, const int64_t* op_off
                         abides_book_event* events_out, int32_t* event_count_out,
                         abides_book_state* states_out);
 
+/* util/oracle/MeanRevertingOracle.py:49-81 -- the dense mean-reverting fundamental (one value per time step):
+ *   r[0] = r_bar,  r[t] = max(0, kappa r_bar + (1 - kappa) r[t-1] + shock[t]),  out[s][t] = int(round(r[t])),
+ * shock = normal(scale = sqrt(sigma_s), size = n_steps) drawn from series s's MT19937 stream (the reference draws from
+ * the process-global np.random), whose state is given in and handed back advanced -- n_series independent series
+ * (seeds x symbols) in one launch, one thread each.  Floats follow the north star's 1e-9 relative tolerance: the
+ * normal deviates use the engine's table-driven log (include/abides_dd_math.h), correctly rounded except ~1e-4 of
+ * arguments. */
+int  abides_dense_fundamental(abides_handle* h, int32_t n_series, uint32_t* mt_key /*[n][624] in/out*/,
+                              int32_t* mt_pos /*in/out*/, int32_t* mt_has_gauss /*in/out*/, double* mt_gauss /*in/out*/,
+                              double r_bar, double kappa, double sigma_s, int64_t n_steps,
+                              int64_t* out /*[n_series][n_steps]*/);
+
 #ifdef __cplusplus
 }
 #endif

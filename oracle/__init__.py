@@ -3,4 +3,4 @@
 Imported by tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs; never by the
 product package abides_b200.
 """
-from .pyoracle import build, lib, run_instance, run_batch, replay_book, math_probe  # noqa: F401
+from .pyoracle import build, lib, run_instance, run_batch, replay_book, math_probe, dense_fundamental  # noqa: F401

@@ -48,6 +48,10 @@ def lib():
         L.oracle_rng_probe.argtypes = [C.POINTER(C.c_uint32), C.c_int, C.c_int, C.c_double, C.c_int, C.c_int,
                                        C.c_double, C.c_double, C.POINTER(C.c_double)]
         L.oracle_rng_probe.restype = None
+        L.oracle_dense_fundamental.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                               C.POINTER(C.c_double), C.c_double, C.c_double, C.c_double, C.c_int64,
+                                               C.POINTER(C.c_int64)]
+        L.oracle_dense_fundamental.restype = None
         L.oracle_math_probe.argtypes = [C.c_int, C.c_double, C.c_double]
         L.oracle_math_probe.restype = C.c_double
         L.oracle_math_probe_n.argtypes = [C.c_int, C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_double),
@@ -155,3 +159,14 @@ def replay_book(op_offset, ops, stream_history, max_events_per_op=64):
     if rc != 0:
         raise RuntimeError("oracle_replay_book failed")
     return ev, cnt, st
+
+
+def dense_fundamental(state, r_bar, kappa, sigma_s, n_steps):
+    """MeanRevertingOracle series from a numpy legacy state tuple; returns (int64[n_steps], advanced state)."""
+    key = np.ascontiguousarray(state[1], np.uint32).copy()
+    pos, hg, gs = C.c_int32(int(state[2])), C.c_int32(int(state[3])), C.c_double(float(state[4]))
+    out = np.zeros(int(n_steps), np.int64)
+    lib().oracle_dense_fundamental(key.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(pos), C.byref(hg), C.byref(gs),
+                                   float(r_bar), float(kappa), float(sigma_s), int(n_steps),
+                                   out.ctypes.data_as(C.POINTER(C.c_int64)))
+    return out, ("MT19937", key, pos.value, hg.value, gs.value)

@@ -117,3 +117,33 @@ def test_device_deep_book_fuzz_matches_oracle():
     # market-order children take fresh ids from 1 << 30 in both restatements
     assert np.array_equal(events, events_o)
     assert states[:, 5].max() > 100 and states[:, 6].max() > 100      # books really were deep (levels per side; 64 orders per side fit in shared memory)
+
+
+ORDERS_FILE = os.path.join(GOLDEN, "sample_orders_file.csv")     # the reference's data/sample_orders_file.csv (10 rows)
+
+
+def test_order_file_parser_reproduces_the_market_replay_tape():
+    """abides_b200.orderfile.parse_orders_file turns the order file into the messages MarketReplayAgent.placeOrder
+    (:47-62) sends: tape 0 of the book-replay golden was built from the same file by the generator."""
+    from abides_b200 import orderfile
+    g, _ = golden()
+    lo, hi = int(g["op_offset"][0]), int(g["op_offset"][1])
+    tape = orderfile.parse_orders_file(ORDERS_FILE)
+    assert np.array_equal(tape[:, :7], g["ops"][lo:hi, :7])
+    # the generator read the timestamps through pandas' float64 column (sub-millisecond digits lost); the parser keeps them
+    assert np.abs(tape[:, 7] - g["ops"][lo:hi, 7]).max() < 4 * 10 ** 6 and tape[0, 7] == 1559554200028558000
+    assert {int(k) for k in tape[:, 0]} == {7, 9, 10}           # limit orders, a cancel and a modify
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("engine", ["warp", "lane"])
+def test_order_file_replay_on_device_matches_reference_orderbook(engine):
+    from abides_b200 import orderfile
+    g, sh = golden()
+    lo, hi = int(g["op_offset"][0]), int(g["op_offset"][1])
+    e = eng_mod.Engine(0)
+    e.set_engine(engine)
+    tape, events, counts, states = orderfile.replay(e, ORDERS_FILE, stream_history=sh)
+    assert np.array_equal(counts, g["counts"][lo:hi]) and np.array_equal(states, g["states"][lo:hi])
+    ge = g["events"][(g["events"][:, 0] >= lo) & (g["events"][:, 0] < hi)]
+    assert np.array_equal(events, ge)
