@@ -158,7 +158,7 @@ EXPORTS = [
     "abides_replay_book", "abides_set_engine", "abides_engine_info", "abides_launch_count", "abides_dense_fundamental",
 ]
 ENGINE_AUTO, ENGINE_WARP, ENGINE_LANE = 0, 1, 2        # enum abides_engine
-LANE_AUTO_MIN_INSTANCES = 4096
+LANE_AUTO_MIN_INSTANCES_ZI, LANE_AUTO_MIN_INSTANCES = 8192, 24576
 VARIANT_NAMES = {0: "warp/full", 1: "warp/zi_legacy", 2: "warp/zi_cubic", 3: "warp/rmsc", 4: "warp/rmsc01",
                  5: "warp/rmsc02", 6: "warp/exec", 16: "lane/zi_legacy", 17: "lane/zi_cubic", 18: "lane/rmsc",
                  19: "lane/full"}

@@ -856,7 +856,9 @@ int abides_load(abides_handle* h, const abides_batch* b) {
     if (pref == ABIDES_ENGINE_LANE && lane_variant == lane::LV_NONE)
       return fail(ABIDES_EINVAL, "abides_load: the lane engine was requested but does not carry this batch (HBL agents, "
                                  "market-data subscriptions and Philox streams run on the warp engine)");
-    if (pref == ABIDES_ENGINE_WARP || (pref == ABIDES_ENGINE_AUTO && ni < ABIDES_LANE_AUTO_MIN_INSTANCES)) lane_variant = lane::LV_NONE;
+    const bool zi_only = lane_variant == lane::LV_ZI_LEGACY || lane_variant == lane::LV_ZI_CUBIC;
+    const int auto_min = zi_only ? ABIDES_LANE_AUTO_MIN_INSTANCES_ZI : ABIDES_LANE_AUTO_MIN_INSTANCES;
+    if (pref == ABIDES_ENGINE_WARP || (pref == ABIDES_ENGINE_AUTO && ni < auto_min)) lane_variant = lane::LV_NONE;
   }
   sig.lane_variant = lane_variant;
   const bool use_lane = lane_variant != lane::LV_NONE;
@@ -943,8 +945,6 @@ int abides_load(abides_handle* h, const abides_batch* b) {
       if ((rc = dev_alloc(h, &lb.agents, (size_t)na))) return rc;
       if ((rc = dev_alloc(h, &lb.state, (size_t)ni))) return rc;
       if ((rc = dev_alloc(h, &lb.hkeys, (size_t)ni * lane::heap_stride(lcap.hcap)))) return rc;
-      lb.near_cap = lane::lane_near_cap(lane_variant);
-      if ((rc = dev_alloc(h, &lb.near, (size_t)ni * lb.near_cap))) return rc;
       if ((rc = dev_alloc(h, &lb.hpay, (size_t)ni * lcap.scap))) return rc;
       if ((rc = dev_alloc(h, &lb.hfree, (size_t)ni * lcap.scap))) return rc;
       if ((rc = dev_alloc(h, &lb.top, (size_t)ni * 2 * lcap.top_k))) return rc;

@@ -12,7 +12,6 @@ enum { LV_NONE = -1, LV_ZI_LEGACY = 0, LV_ZI_CUBIC = 1, LV_RMSC = 2, LV_FULL = 3
 constexpr int LANE_VARIANT_BASE = 16;
 
 inline int lane_top_k(int variant) { return variant == LV_RMSC ? 128 : variant == LV_FULL ? 64 : 32; }
-inline int lane_near_cap(int variant) { return variant == LV_RMSC || variant == LV_FULL ? 32 : 16; }   // LN_NEAR of the variant
 
 // the leanest lane variant whose feature set covers the batch, or LV_NONE (HBL agents and market-data subscriptions
 // run on the warp-per-instance engine)

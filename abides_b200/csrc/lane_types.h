@@ -112,9 +112,6 @@ struct LN_ALIGN(16) LHot {              // per-instance scalars, in HBM; staged 
   int hn;                               // events in the heap
   int n_hfree, slot_bump, spare_slot;   // payload slots: free stack, never-used frontier, one cached free slot
   int status, done, n_trace, queue_peak;
-  LKey hroot;                           // copy of the heap's root key (all ones: heap empty)
-  int nn;                               // events in the near buffer
-  int pad0_[3];
   // the rest: only the handle half (and kernelStopping)
   long long n_fills, volume;
   long long exch_cd, exch_cur_time, additional_delay;
@@ -134,7 +131,7 @@ struct LN_ALIGN(16) LHot {              // per-instance scalars, in HBM; staged 
   int pad_[3];
   RngState rs[ABIDES_EXTRA_STREAMS];
 };
-constexpr int LHOT_POP_BYTES = 96;
+constexpr int LHOT_POP_BYTES = 64;
 static_assert(sizeof(LHot) % 16 == 0 && offsetof(LHot, n_fills) == LHOT_POP_BYTES, "LHot layout");
 
 // everything a launch needs; passed BY VALUE as a __grid_constant__ kernel parameter (no __constant__ symbol shared
@@ -165,8 +162,6 @@ struct LaneBatch {
   LAgent* agents;
   LHot* state;
   LKey* hkeys;                          // [ni][hcap + HEAP_ROOT + 1]
-  LKey* near;                           // [ni][near_cap]: the imminent events, unsorted, one contiguous block per instance
-  int near_cap;
   LPay* hpay;                           // [ni][scap]
   int* hfree;                           // [ni][scap]
   LOrd* top;                            // [ni][2][top_k]

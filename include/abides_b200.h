@@ -269,16 +269,19 @@ void abides_destroy(abides_handle* h);
 const char* abides_last_error(void);
 const char* abides_version(void);
 
-/* Two device engines run the same path: the WARP engine gives every instance a warp (best below a few
- * thousand instances, carries every agent class, Philox streams and market-data subscriptions), the LANE engine gives
- * every instance a thread, so that a warp advances 32 instances and each fetched instruction serves all lanes that
- * take the same handler (best for large sweeps).  abides_load picks one (AUTO: lane from
- * ABIDES_LANE_AUTO_MIN_INSTANCES instances up when it carries the batch; the environment variable ABIDES_ENGINE=warp|lane
+/* Two device engines run the same path.  The WARP engine gives every instance a warp: a step of a few
+ * thousand instances takes seconds, it carries every agent class and market-data subscriptions.  The LANE engine gives
+ * every instance a thread and regroups the popped events of a CTA by handler, so that a warp runs one handler for 32
+ * instances: it needs tens of thousands of resident instances and then sustains 2-3x the warp engine's messages/s on the
+ * sparse_zi populations (a step is the 10-20 s a single instance's event chain takes).  abides_load picks one (AUTO:
+ * the lane engine when it carries the batch and the batch has at least ABIDES_LANE_AUTO_MIN_INSTANCES_ZI instances of a
+ * ZI-only population, or ABIDES_LANE_AUTO_MIN_INSTANCES of any other; the environment variable ABIDES_ENGINE=warp|lane
  * overrides AUTO); abides_set_engine forces the choice for the following loads and abides_engine_info reports what the
  * loaded batch runs on: engine, and the kernel variant (warp engine: 0 full, 1 zi_legacy, 2 zi_cubic, 3 rmsc,
  * 4 rmsc01, 5 rmsc02, 6 exec; lane engine: 16 zi_legacy, 17 zi_cubic, 18 rmsc, 19 full). */
 enum abides_engine { ABIDES_ENGINE_AUTO = 0, ABIDES_ENGINE_WARP = 1, ABIDES_ENGINE_LANE = 2 };
-#define ABIDES_LANE_AUTO_MIN_INSTANCES 4096
+#define ABIDES_LANE_AUTO_MIN_INSTANCES_ZI 8192
+#define ABIDES_LANE_AUTO_MIN_INSTANCES 24576
 int  abides_set_engine(abides_handle* h, int32_t engine);
 int  abides_engine_info(abides_handle* h, int32_t* engine, int32_t* variant);
 

@@ -138,8 +138,6 @@ int hostsim_run(const abides_batch* b, int force_variant, abides_instance_result
   lb.agents = own.keep((LAgent*)aligned_alloc(128, sizeof(LAgent) * (size_t)(na ? na : 1)));
   lb.state = own.keep(zalloc<LHot>(ni));
   lb.hkeys = own.keep(zalloc<LKey>((size_t)ni * heap_stride(cap.hcap)));
-  lb.near_cap = lane_near_cap(variant);
-  lb.near = own.keep((LKey*)aligned_alloc(128, sizeof(LKey) * (size_t)ni * lb.near_cap));
   lb.hpay = own.keep(zalloc<LPay>((size_t)ni * cap.scap));
   lb.hfree = own.keep(zalloc<int>((size_t)ni * cap.scap));
   lb.top = own.keep(zalloc<LOrd>((size_t)ni * 2 * cap.top_k));
