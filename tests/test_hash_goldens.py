@@ -26,8 +26,11 @@ def finals_digest(cash, holdings, mtm):
 
 
 def seeds_of(name, limit=None):
+    """All hashed seeds, or the `limit` smallest plus every seed on which the reference itself raised."""
     s = sorted(HASHES[name]["seeds"], key=int)
-    return [int(x) for x in (s[:limit] if limit else s)]
+    if limit:
+        s = s[:limit] + [x for x in s[limit:] if "reference_raises" in HASHES[name]["seeds"][x]]
+    return [int(x) for x in s]
 
 
 def check(name, seeds, res, ares, n_agents):
