@@ -44,6 +44,7 @@
 #include <string.h>
 #include <limits.h>
 #include <math.h>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -574,6 +575,15 @@ enum { VAR_FULL = 0, VAR_ZI_LEGACY, VAR_ZI_CUBIC, VAR_RMSC, VAR_RMSC01, VAR_RMSC
 // host side
 // ----------------------------------------------------------------------------------------------
 thread_local std::string g_err;
+// The warp engine's kernels read their batch descriptor from ONE __constant__ symbol per device (c_db), uploaded
+// in-stream before each launch: two handles on the same device must not overlap a warp-engine load / reset / run.
+// (The lane engine passes its descriptor by value as a __grid_constant__ parameter and needs no lock.)
+std::mutex g_cdb_mutex[64];
+struct CdbLock {
+  std::mutex* m;
+  CdbLock(const abides_handle* h, bool warp);
+  ~CdbLock() { if (m) m->unlock(); }
+};
 int fail(int code, const std::string& msg) { g_err = msg; return code; }
 #define CK(call)                                                                                  \
   do {                                                                                            \
@@ -629,6 +639,9 @@ struct abides_handle {
 };
 
 namespace {
+CdbLock::CdbLock(const abides_handle* h, bool warp) : m(nullptr) {
+  if (warp && h->device >= 0 && h->device < 64) { m = &g_cdb_mutex[h->device]; m->lock(); }
+}
 
 template <typename T>
 int dev_alloc(abides_handle* h, T** out, size_t count) {
@@ -792,6 +805,7 @@ int abides_load(abides_handle* h, const abides_batch* b) {
   long long na = b->n_agents_total;
   int max_agents = 0;
   long long off = 0;
+  if (na <= 0 || b->n_types <= 0 || b->n_theta_total < 0) return fail(ABIDES_EINVAL, "abides_load: n_agents_total / n_types / n_theta_total out of range");
   std::vector<int> mom_index((size_t)na, -1);
   int n_mom = 0, n_hbl = 0;
   unsigned class_mask = 0, lat_mask = 0;
@@ -801,6 +815,8 @@ int abides_load(abides_handle* h, const abides_batch* b) {
     if (ic.latency_kind < ABIDES_LAT_DETERMINISTIC || ic.latency_kind > ABIDES_LAT_LEGACY_NOISE)
       return fail(ABIDES_EINVAL, "abides_load: bad latency_kind");
     lat_mask |= 1u << ic.latency_kind;
+    if (ic.latency_kind == ABIDES_LAT_LEGACY_NOISE && ic.n_latency_noise < 1) return fail(ABIDES_EINVAL, "abides_load: the legacy latency model needs n_latency_noise >= 1");
+    if (ic.theta_offset < 0 || ic.theta_offset > b->n_theta_total) return fail(ABIDES_EINVAL, "abides_load: bad theta_offset");
     if (ic.agent_offset != off || ic.n_agents <= 0) return fail(ABIDES_EINVAL, "abides_load: agent_offset must be the prefix sum of n_agents");
     if (ic.type_base < 0 || ic.type_base >= b->n_types) return fail(ABIDES_EINVAL, "abides_load: bad type_base");
     if (ic.r_bar < 0 || ic.r_bar > 2.0e9) return fail(ABIDES_EINVAL, "abides_load: r_bar out of the int32 price range");
@@ -822,6 +838,9 @@ int abides_load(abides_handle* h, const abides_batch* b) {
       } else if (k == ABIDES_SUBSCRIPTION) return fail(ABIDES_EINVAL, "abides_load: SubscriptionAgent without subscribe");
       if (k == ABIDES_MOMENTUM) mom_index[off + a] = n_mom++;
       if ((k == ABIDES_ZI || k == ABIDES_HBL) && (b->agent_theta[off + a] < 0 || (!b->theta && !draw_theta))) return fail(ABIDES_EINVAL, "abides_load: ZI / HBL agent without theta");
+      if ((k == ABIDES_ZI || k == ABIDES_HBL) && !draw_theta && b->agent_theta[off + a] >= 0 &&
+          ic.theta_offset + b->agent_theta[off + a] + 2ll * b->types[t].q_max > b->n_theta_total)
+        return fail(ABIDES_EINVAL, "abides_load: a ZI / HBL agent's theta rows run past n_theta_total");
       if ((k == ABIDES_ZI || k == ABIDES_HBL) && draw_theta && (!(b->types[t].sigma_pv >= 0) || b->types[t].q_max < 1 ||
           ic.theta_offset + b->agent_theta[off + a] + 2ll * b->types[t].q_max > b->n_theta_total))
         return fail(ABIDES_EINVAL, "abides_load: ABIDES_DRAW_ZI_THETA needs sigma_pv, q_max and room for 2 q_max values per agent");
@@ -867,7 +886,12 @@ int abides_load(abides_handle* h, const abides_batch* b) {
   const size_t ns_all = (size_t)na + (size_t)ABIDES_EXTRA_STREAMS * ni;
   std::vector<int> dev_row;
   size_t n_dev_rows = ns_all;
+  if (b->rng_mode == ABIDES_RNG_MT19937 && !seeded)
+    for (size_t s2 = 0; s2 < ns_all; s2++)
+      if (b->mt_pos[s2] < 0 || b->mt_pos[s2] > ABIDES_MT_N) return fail(ABIDES_EINVAL, "abides_load: mt_pos outside 0..624");
   if (seeded) {
+    for (size_t s2 = 0; s2 < ns_all; s2++)
+      if (b->mt_key_row[s2] >= 0 && (b->mt_pos[s2] < 0 || b->mt_pos[s2] > ABIDES_MT_N)) return fail(ABIDES_EINVAL, "abides_load: mt_pos outside 0..624");
     for (size_t s2 = 0; s2 < ns_all; s2++)
       if (b->mt_key_row[s2] >= b->n_mt_rows || b->mt_key_row[s2] < -1 || (b->mt_key_row[s2] < 0 && b->mt_pos[s2] < 0))
         return fail(ABIDES_EINVAL, "abides_load: bad mt_key_row / mt_pos");
@@ -1097,8 +1121,11 @@ int abides_load(abides_handle* h, const abides_batch* b) {
   }
   h->launches_total += h->launches_since_load;
   h->launches_since_load = 0;
-  if ((rc = launch_init(h))) return rc;
-  CK(cudaStreamSynchronize(h->stream));      // mom_index (a local vector) must outlive the copy
+  {
+    CdbLock lock(h, h->lane_variant == lane::LV_NONE);
+    if ((rc = launch_init(h))) return rc;
+    CK(cudaStreamSynchronize(h->stream));      // mom_index (a local vector) must outlive the copy
+  }
   h->n_instances = ni; h->n_agents_total = na; h->loaded = true;
   return 0;
 }
@@ -1108,6 +1135,7 @@ int abides_load(abides_handle* h, const abides_batch* b) {
 int abides_reset(abides_handle* h) {
   if (!h || !h->loaded) return fail(ABIDES_ESTATE, "abides_reset: no batch loaded");
   CK(cudaSetDevice(h->device));
+  CdbLock lock(h, h->lane_variant == lane::LV_NONE);
   CK(cudaEventRecord(h->ev0, h->stream));
   int rc = launch_init(h);
   if (rc) return rc;
@@ -1126,6 +1154,7 @@ int abides_last_reset_ms(abides_handle* h, float* ms) {
 int abides_run(abides_handle* h, int64_t until_time) {
   if (!h || !h->loaded) return fail(ABIDES_ESTATE, "abides_run: no batch loaded");
   CK(cudaSetDevice(h->device));
+  CdbLock lock(h, h->lane_variant == lane::LV_NONE);
   CK(cudaEventRecord(h->ev0, h->stream));
   if (h->lane_variant != lane::LV_NONE) {
     CK(lane::launch_sim(h->lane_variant, h->lb, (long long)until_time, h->stream));

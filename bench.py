@@ -399,6 +399,10 @@ def main():
                              "ncu DRAM bytes per message of the committed capture x messages per launch. The kernel is "
                              "latency bound, not HBM bound: see DESIGN.md and profiles/" % ALGO_BYTES_PER_MESSAGE},
         "reference_note": REFERENCE_NOTE,
+        "scaling_note": ("weak scaling: every rank runs its own %d instances, so the job at N GPUs is N times the N=1 job; "
+                         "the reference arm always times one bounded CPU sample on one host, whatever N is"
+                         % per_rank) if args.scaling == "weak" else
+                        "strong scaling: %d instances in total, split evenly over the ranks" % total,
     }
     if also:
         line["also"] = also

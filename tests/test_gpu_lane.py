@@ -158,3 +158,21 @@ def test_philox_throughput_mode_on_device_matches_oracle(engine):
         assert sb.h2d_bytes() < 100 * sb.n_agents_total
         eng2, res2, ares2 = device_run(sb, engine="lane")
         _same_results(res2, ares2, res, ares)
+
+
+def test_chunked_sweep_driver_on_device_equals_one_batch():
+    """runtime.run_sweep cuts the sweep into chunks handed to the device worker(s) by a ticket counter; per-instance
+    results equal those of the same seeds run as ONE batch (and, with two GPUs visible, of the two-device run)."""
+    import torch
+    seeds = runtime.parallel_seeds(77, 150)
+    one = runtime.run_sweep("sparse_zi_100", seeds, devices=(0,))
+    chunked = runtime.run_sweep("sparse_zi_100", seeds, devices=(0,), chunk_instances=40)
+    assert len(chunked.placement) == 4
+    for f in ("ttl_messages", "delivered", "last_trade", "n_fills", "final_time"):
+        assert np.array_equal(one.res[f], chunked.res[f]), f
+    assert np.array_equal(one.ares["cash"], chunked.ares["cash"])
+    assert np.array_equal(one.agents(123)["holdings"], chunked.agents(123)["holdings"])
+    if torch.cuda.device_count() >= 2:
+        two = runtime.run_sweep("sparse_zi_100", seeds, devices=(0, 1), chunk_instances=25)
+        assert {p[0] for p in two.placement} == {0, 1}
+        assert np.array_equal(one.res["ttl_messages"], two.res["ttl_messages"]) and np.array_equal(one.ares["cash"], two.ares["cash"])
