@@ -53,10 +53,11 @@ GRID = {"--num-noise": [2500, 5000], "--num-value": [50, 100], "--mm-pov": [0.02
 HOURS = {"rmsc03": "09:30-11:30, kernel 00:00-11:31", "rmsc03_2h": "09:30-11:30, kernel 00:00-11:31",
          "rmsc03_grid": "09:30-11:30, kernel 00:00-11:31", "execution": "09:30-11:30, kernel 00:00-11:31",
          "sparse_zi_100": "09:30-16:00, kernel 00:00-17:00", "sparse_zi_1000": "09:30-16:00, kernel 00:00-17:00"}
-# instances per GPU: the headline runs on the warp engine (a step of a few seconds, so the driver's 25 steps fit), the
+# instances per GPU: the headline runs on the warp engine -- 2368 = 148 SMs x 16 resident warps, one full wave, a step of
+# 6.7 s so that the driver's 25 steps fit -- and the
 # `also` workload on the lane engine, whose throughput needs tens of thousands of resident instances and whose step is
 # the ~15 s one instance's event chain takes
-DEFAULT_INSTANCES = {"rmsc03": 2048, "rmsc03_2h": 2048, "rmsc03_grid": 2048, "sparse_zi_1000": 40960,
+DEFAULT_INSTANCES = {"rmsc03": 2368, "rmsc03_2h": 2368, "rmsc03_grid": 2048, "sparse_zi_1000": 45056,
                      "sparse_zi_100": 65536}
 
 

@@ -265,6 +265,32 @@ def test_load_rejects_malformed_batches():
         eng.load(hb)
     with pytest.raises(EngineError, match="no batch loaded"):
         Engine(0).run()
+    # inputs the device would dereference are range-checked before anything is allocated or launched
+    hb = lowering.HostBatch([spec])
+    hb.c.n_agents_total = -5
+    with pytest.raises(EngineError, match="out of range"):
+        eng.load(hb)
+    hb = lowering.HostBatch([spec])
+    hb.mt_pos[3] = 700
+    with pytest.raises(EngineError, match="mt_pos"):
+        eng.load(hb)
+    hb = lowering.HostBatch([spec])
+    hb.mt_pos[3] = -1
+    with pytest.raises(EngineError, match="mt_pos"):
+        eng.load(hb)
+    z1000 = build_case("zi1000_s123456789")                 # legacy latency matrix + noise
+    hb = lowering.HostBatch([z1000])
+    hb.instances[0].n_latency_noise = 0
+    with pytest.raises(EngineError, match="n_latency_noise"):
+        eng.load(hb)
+    hb = lowering.HostBatch([spec])
+    hb.c.n_theta_total = 10                                 # the agents' theta rows would run past the table
+    with pytest.raises(EngineError, match="theta"):
+        eng.load(hb)
+    hb = lowering.HostBatch([spec])
+    eng.load(hb)                                            # and a well-formed batch still loads afterwards
+    eng.run()
+    assert eng.results_arrays()[0]["ttl_messages"][0] == 21799
 
 
 def test_philox_throughput_mode_matches_oracle():
