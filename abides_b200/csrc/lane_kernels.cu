@@ -47,7 +47,7 @@ cudaError_t launch_init(int variant, const LaneBatch& lb, cudaStream_t stream) {
 
 cudaError_t launch_sim(int variant, const LaneBatch& lb, long long until_time, cudaStream_t stream) {
   const int grid = (lb.n_instances + LANE_CTA - 1) / LANE_CTA;
-  LANE_DISPATCH(variant, (lane_sim_kernel<<<grid, LANE_CTA, 0, stream>>>(lb, until_time)));
+  LANE_DISPATCH(variant, (lane_sim_kernel<<<grid, LANE_CTA + LANE_HEAVY, 0, stream>>>(lb, until_time)));
   return cudaGetLastError();
 }
 

@@ -52,7 +52,11 @@ namespace lane {
 #ifndef LANE_CTA_THREADS
 #define LANE_CTA_THREADS 128
 #endif
-constexpr int LANE_CTA = LANE_CTA_THREADS;   // instances (threads) per CTA of the event loop
+#ifndef LANE_HEAVY_WARPS
+#define LANE_HEAVY_WARPS 1
+#endif
+constexpr int LANE_CTA = LANE_CTA_THREADS;   // instances per CTA of the event loop (one owner thread each)
+constexpr int LANE_HEAVY = 32 * LANE_HEAVY_WARPS;   // extra threads of a CTA that only run the heavy handler classes
 constexpr int LANE_KINDS = 128;              // handler classes the CTA regroups popped events by
 constexpr int LANE_PROF_SLOTS = 8;            // rounds, pop cycles, sort cycles, handle cycles, events, ...
 constexpr int HEAP_ROOT = 3;                 // children of node i: 4 * (i - 2) .. + 3; parent of j: j / 4 + 2

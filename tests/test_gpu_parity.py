@@ -308,3 +308,30 @@ def test_philox_throughput_mode_matches_oracle():
     _, res_mt, _ = device_run(mt)
     assert not np.array_equal(res["ttl_messages"], res_mt["ttl_messages"])          # different streams ...
     assert abs(res["ttl_messages"].mean() / res_mt["ttl_messages"].mean() - 1) < 0.05   # ... same market
+
+
+def test_full_size_rmsc03_full_day_matches_oracle_on_the_lean_variant():
+    """config/rmsc03.py at full size (5129 agents) over the whole day 09:30-16:00, 32 seeds, untraced -- i.e. on the
+    lean rmsc kernel variant the bench runs -- against the oracle, instance by instance (3.6 M messages each)."""
+    from abides_b200 import _abi
+    seeds = runtime.parallel_seeds(31, 32)
+    extra = ["-t", "ABM", "-d", "20200603", "--end-time", "16:00:00"]
+    specs = runtime.build_specs_parallel("rmsc03", [extra + ["-s", s] for s in seeds])
+    assert specs[0].n_agents == 5129
+    hb = lowering.HostBatch(specs)
+    eng, res, ares = device_run(hb, engine="warp")
+    assert eng.engine_info() == (_abi.ENGINE_WARP, 3)
+    ores, oares = oracle.run_batch(hb)
+    o = np.frombuffer(oares, dtype=ares.dtype)
+    n_ok = 0
+    for i in range(hb.n_instances):
+        assert res["status"][i] == ores[i].status, i
+        for f in ("ttl_messages", "delivered", "final_time", "last_trade", "n_orders", "n_fills", "traded_volume",
+                  "slowest_agent_finish_time", "final_fundamental"):
+            assert res[f][i] == getattr(ores[i], f), (i, f)
+        if res["status"][i] == 0:
+            n_ok += 1
+            sl = agent_slices(hb, i)
+            for f in ("cash", "holdings", "marked_to_market"):
+                assert np.array_equal(ares[f][sl], o[f][sl]), (i, f)
+    assert n_ok >= 28 and int(res["ttl_messages"].min()) > 3000000
