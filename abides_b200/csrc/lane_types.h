@@ -52,8 +52,10 @@ namespace lane {
 #ifndef LANE_CTA_THREADS
 #define LANE_CTA_THREADS 128
 #endif
+// warps of a CTA that only run the heavy handler classes (-DLANE_HEAVY_WARPS=1: measured, no gain -- the order-placement
+// handler alone is the critical path of a round, whichever warp runs it)
 #ifndef LANE_HEAVY_WARPS
-#define LANE_HEAVY_WARPS 1
+#define LANE_HEAVY_WARPS 0
 #endif
 constexpr int LANE_CTA = LANE_CTA_THREADS;   // instances per CTA of the event loop (one owner thread each)
 constexpr int LANE_HEAVY = 32 * LANE_HEAVY_WARPS;   // extra threads of a CTA that only run the heavy handler classes
