@@ -27,7 +27,9 @@ MSG_NAMES = {
 }
 MD_MAX_LEVELS = 8
 MSG_CODES = {v: k for k, v in MSG_NAMES.items()}
-TRACE_FUNDAMENTAL = 64          # trace code of an oracle step (include/abides_b200.h: abides_trace_rec)
+TRACE_FUNDAMENTAL = 64          # trace code of an oracle step (include/abides_b200.h: enum abides_trace_code)
+TRACE_ORDER_PLACED, TRACE_BOOK_TOP, TRACE_LAST_TRADE, TRACE_EXCH_SENT = 65, 66, 67, 128
+TRACE_EXCHANGE_LOG = 1          # enum abides_trace_flags
 MSG_REPLY = 32
 
 
@@ -94,7 +96,7 @@ class Batch(C.Structure):
         ("mt_key_row", C.POINTER(C.c_int32)),
         ("mt_seed", C.POINTER(C.c_uint32)),
         ("n_mt_rows", C.c_int64),
-        ("draw_flags", C.c_int32), ("reserved0", C.c_int32),
+        ("draw_flags", C.c_int32), ("trace_flags", C.c_int32),
     ]
 
 

@@ -266,6 +266,7 @@ struct __align__(128) InstShared {      // persisted per instance between launch
 
 struct DevBatch {
   int n_instances, rng_mode, trace_cap, b_cap, arena_cap, n_types, deep_cap;
+  int trace_flags;                      // enum abides_trace_flags
   const abides_instance_cfg* cfg;
   const abides_agent_type* types;
   abm_dd* type_log1mk;                  // log(1 - kappa) per type, double-double
@@ -795,6 +796,7 @@ int abides_load(abides_handle* h, const abides_batch* b) {
   if (seeded && (b->rng_mode != ABIDES_RNG_MT19937 || !b->mt_seed || b->n_mt_rows < 0 || (b->n_mt_rows > 0 && !b->mt_key)))
     return fail(ABIDES_EINVAL, "abides_load: mt_key_row needs MT19937 mode, mt_seed and n_mt_rows rows of mt_key");
   if (b->draw_flags & ~(ABIDES_DRAW_ZI_THETA | ABIDES_DRAW_MOMENTUM_SIZE)) return fail(ABIDES_EINVAL, "abides_load: unknown draw_flags");
+  if (b->trace_flags & ~ABIDES_TRACE_EXCHANGE_LOG) return fail(ABIDES_EINVAL, "abides_load: unknown trace_flags");
   if (b->draw_flags && (!b->mt_seed && b->mt_key_row)) return fail(ABIDES_EINVAL, "abides_load: draw_flags with mt_key_row need mt_seed");
   if (b->draw_flags && b->rng_mode == ABIDES_RNG_PHILOX && (!b->mt_key_row || !b->mt_seed || !b->mt_pos || !b->mt_has_gauss || !b->mt_gauss))
     return fail(ABIDES_EINVAL, "abides_load: in Philox mode the constructor draws need every agent stream described by its seed");
@@ -877,7 +879,24 @@ int abides_load(abides_handle* h, const abides_batch* b) {
                                  "market-data subscriptions and Philox streams run on the warp engine)");
     const bool zi_only = lane_variant == lane::LV_ZI_LEGACY || lane_variant == lane::LV_ZI_CUBIC;
     const int auto_min = zi_only ? ABIDES_LANE_AUTO_MIN_INSTANCES_ZI : ABIDES_LANE_AUTO_MIN_INSTANCES;
-    if (pref == ABIDES_ENGINE_WARP || (pref == ABIDES_ENGINE_AUTO && ni < auto_min)) lane_variant = lane::LV_NONE;
+    bool to_warp = pref == ABIDES_ENGINE_WARP || (pref == ABIDES_ENGINE_AUTO && ni < auto_min);
+    if (to_warp && pref == ABIDES_ENGINE_AUTO && lane_variant != lane::LV_NONE) {
+      // AUTO never picks an engine whose tables cannot fit: the warp engine keeps a 2.5 KB MT19937 state per stream
+      // (twice for batches uploaded with their states) and the larger per-instance capacities below -- ~20 MB for an
+      // rmsc03 instance, i.e. ~8 000 of them in 180 GB -- where the lane engine holds 33 000
+      const double streams = (double)na + (double)ABIDES_EXTRA_STREAMS * ni;
+      double need = b->rng_mode == ABIDES_RNG_MT19937 ? streams * ABIDES_MT_N * 4.0 * (seeded && b->n_mt_rows == 0 ? 1.0 : 2.0) : 0.0;
+      need += (double)na * (sizeof(AgentRec) + 64.0);
+      need += (double)ni * ((double)sizeof(InstShared) + (double)A_CAP * (sizeof(EvKey) + sizeof(EvPay)) +
+                            (4.0 * max_agents + 4096) * (sizeof(EvKey) + sizeof(EvPay)) +
+                            (8.0 * max_agents + 4096) * sizeof(OpenOrd) +
+                            2.0 * (4.0 * max_agents + 1024) * (sizeof(EvKey) + sizeof(EvPay) + 4.0) +
+                            (needs_tv ? (double)(TXN_CAP + UNR_CAP) * sizeof(TxnRow) : 0.0) +
+                            (double)(b->trace_capacity > 0 ? b->trace_capacity : 0) * sizeof(abides_trace_rec));
+      size_t free_b = 0, total_b = 0;
+      if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && need > 0.92 * (double)total_b) to_warp = false;
+    }
+    if (to_warp) lane_variant = lane::LV_NONE;
   }
   sig.lane_variant = lane_variant;
   const bool use_lane = lane_variant != lane::LV_NONE;
@@ -1019,6 +1038,8 @@ int abides_load(abides_handle* h, const abides_batch* b) {
     }
     h->sig = sig;
   }
+  d.trace_flags = b->trace_flags;
+  if (use_lane) h->lb.trace_flags = b->trace_flags;
   h->lane_variant = lane_variant;
   h->n_streams = ns; h->n_mom = n_mom; h->n_dev_rows = n_dev_rows;
   h->rematerialize = rematerialize; h->max_agents = max_agents; h->n_skip = (int)skip_list.size();

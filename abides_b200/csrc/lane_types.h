@@ -147,6 +147,7 @@ struct LaneBatch {
   int hcap, scap, arena_cap, deep_cap, txn_cap, unr_cap;
   int rng_mode;                         // enum abides_rng_mode
   int run_ahead;                        // light events an instance may run past its sorted one per round
+  int trace_flags;                      // enum abides_trace_flags
   const abides_instance_cfg* cfg;
   const abides_agent_type* types;
   abm_dd* type_log1mk;

@@ -1,0 +1,294 @@
+"""The reference's per-agent log archives, rebuilt from the device trace.
+
+What the reference writes at kernelTerminating (agent/Agent.py:87-98 -> Kernel.writeLog, Kernel.py:487-510), one
+bz2-pickled DataFrame each, index `EventTime`, columns `EventType`, `Event`:
+
+* the exchange's log `<exchange name>.bz2` (EXCHANGE_AGENT.bz2 in the rmsc configs): every message it received before the
+  close (order messages as `order.to_dict()` when `log_orders`, the others as the sender id; agent/ExchangeAgent.py:
+  126-150), every ORDER_ACCEPTED / _EXECUTED / _CANCELLED it sent (:404-408) and, after each handleLimitOrder, BEST_BID /
+  BEST_ASK / LAST_TRADE (util/OrderBook.py:108-132);
+* `ORDERBOOK_<symbol>_FULL.bz2` when `book_freq == 0` and `wide_book`: the full depth after every handleLimitOrder
+  (OrderBook.py:138-156, :492-520; ExchangeAgent.py:319-396), a sparse frame times x quotes, bids negative;
+* one log per trading agent with `log_to_file` (agent/TradingAgent.py:106-168, :390-500, :575-603).
+
+Everything here is derived from the device's trace of one instance: the dispatched events plus the exchange-log records
+(`ABIDES_TRACE_EXCHANGE_LOG`, include/abides_b200.h).  The book depth is an ACCOUNT of the device's own notifications
+(accepted - executed - cancelled per price), not a second matching engine; the device's top-of-book record cross-checks
+it at every snapshot.
+
+Not reproduced: MODIFY_ORDER in the archives, `book_freq` sampling other than 0 (every update), the long-format
+(`wide_book=False`) archive (the reference itself fails there: pd.SparseDataFrame, ExchangeAgent.py:384), agents with
+`log_orders=True` that place orders, and the logs of agents whose spread queries ask for more than the best level (market makers,
+execution agents that trade): their BID_DEPTH / ASK_DEPTH rows would need levels the trace does not carry -- those
+agents are skipped and reported."""
+import os
+
+import numpy as np
+
+from abides_b200 import _abi
+
+M = _abi.MSG_CODES
+ORDER_MSGS = (M["LIMIT_ORDER"], M["MARKET_ORDER"], M["CANCEL_ORDER"], M["MODIFY_ORDER"])
+QUERY_MSGS = (M["QUERY_LAST_TRADE"], M["QUERY_SPREAD"], M["QUERY_ORDER_STREAM"], M["QUERY_TRANSACTED_VOLUME"])
+SENT = _abi.TRACE_EXCH_SENT
+NAT = np.iinfo(np.int64).min
+DEEP_QUERY_CLASSES = ("MarketMakerAgent", "AdaptiveMarketMakerAgent", "AdaptivePOVMarketMakerAgent", "ExecutionAgent",
+                      "POVExecutionAgent", "TWAPExecutionAgent", "VWAPExecutionAgent", "SubscriptionAgent",
+                      "HeuristicBeliefLearningAgent")
+
+
+def _iso(ns):
+    import pandas as pd
+    return pd.Timestamp(int(ns)).isoformat()
+
+
+def _order_dict(agent, placed_ns, symbol, qty, is_buy, oid, fill, limit):
+    """Order.to_dict() (util/order/Order.py:52-55) of a LimitOrder (limit is not None) or a MarketOrder."""
+    d = {'agent_id': int(agent), 'time_placed': _iso(placed_ns), 'symbol': symbol, 'quantity': int(qty),
+         'is_buy_order': bool(is_buy), 'order_id': int(oid), 'fill_price': None if fill is None or fill < 0 else int(fill),
+         'tag': None}
+    if limit is not None:
+        d['limit_price'] = int(limit)
+    return d
+
+
+class ExchangeArchive:
+    """Walks one instance's trace once; afterwards `exchange_rows`, `book_rows` and `agent_rows` hold the archives."""
+
+    def __init__(self, kernel, trace):
+        self.kernel = kernel
+        self.exch = kernel.agents[0]
+        self.symbol = next(iter(self.exch.order_books))
+        self.mkt_close = _ns(self.exch.mkt_close)
+        self.log_orders = bool(self.exch.log_orders)
+        self.snapshots = self.exch.book_freq is not None
+        self.exchange_rows = [(NAT, 'AGENT_TYPE', self.exch.type)]
+        self.book_rows = []                     # (time, {quote: signed volume})
+        self.quotes_seen = set()
+        self.agent_rows = {}
+        self.skipped_agents = []
+        self._walk(np.asarray(trace, np.int64))
+
+    # ---- agents -------------------------------------------------------------------------------------------------
+    def _agent_logged(self, a):
+        if not getattr(a, "log_to_file", False) or a.id == 0:
+            return False
+        names = [k.__name__ for k in type(a).__mro__]
+        deep = any(n in DEEP_QUERY_CLASSES for n in names) and getattr(a, "trade", True)
+        if deep:
+            self.skipped_agents.append(a.name)
+            return False
+        return True
+
+    def _walk(self, tr):
+        k = self.kernel
+        sym = self.symbol
+        logged = {a.id: a for a in k.agents if self._agent_logged(a)}
+        rows = {i: [(NAT, 'AGENT_TYPE', a.type), (NAT, 'STARTING_CASH', a.starting_cash)] for i, a in logged.items()}
+        hold = {i: {'CASH': a.starting_cash} for i, a in logged.items()}
+        woke, last_time = set(), {}
+        placed = {}            # order id in the agent's message -> (time_placed, agent, price, signed qty, is_market)
+        copy_qty = {}          # id of the agent's own copy of an order -> [quantity the copy shows, message id]
+        book_time = {}         # order id in the book -> time_placed
+        resting = {}           # order id in the book -> [price, side (+1 bid / -1 ask), quantity]
+        depth = {}             # price -> signed resting volume (bids negative, as the archive stores them)
+        cur = None             # the order message the exchange is handling: [time_placed, message id, row to patch]
+        ex = self.exchange_rows
+        for time, agent, code, p0, p1, p2, p3 in tr.tolist():
+            if code == _abi.TRACE_FUNDAMENTAL:
+                continue
+            if code == _abi.TRACE_ORDER_PLACED:
+                placed[p0] = (time, agent, p1, p2, p3)
+                if agent in logged and getattr(logged[agent], "log_orders", False):
+                    self.skipped_agents.append(logged.pop(agent).name)     # ORDER_SUBMITTED / CANCEL_SUBMITTED rows: not derivable
+                # the agent keeps a deepcopy; the copy of order id 0 takes a fresh id (Order.py:29): the next one
+                copy_qty[p0 if p0 != 0 else 1] = [abs(p2), p0]
+                continue
+            if code >= SENT:
+                msg = code - SENT
+                if cur is not None and cur[2] is not None:        # the logged copy of order id 0 took the id before the book's
+                    r = ex[cur[2]]
+                    r[2]['order_id'] = p0 - 1
+                    cur[2] = None
+                tp = book_time.get(p0, cur[0] if cur is not None else time)
+                if self.log_orders:
+                    ex.append([time, _abi.MSG_NAMES[msg], _order_dict(agent, tp, sym, abs(p2), p2 > 0, p0, p3, p1)])
+                if msg == M["ORDER_ACCEPTED"]:
+                    book_time[p0] = tp
+                    side = 1 if p2 > 0 else -1
+                    resting[p0] = [p1, side, abs(p2)]
+                    depth[p1] = depth.get(p1, 0) - side * abs(p2)
+                elif msg in (M["ORDER_EXECUTED"], M["ORDER_CANCELLED"]) and p0 in resting:
+                    r = resting[p0]
+                    q = abs(p2)
+                    depth[r[0]] += r[1] * q
+                    if depth[r[0]] == 0:
+                        del depth[r[0]]
+                    r[2] -= q
+                    if r[2] <= 0:
+                        del resting[p0]
+                elif msg == M["ORDER_MODIFIED"] and self.snapshots:
+                    raise NotImplementedError("MODIFY_ORDER in the order-book archive")
+                continue
+            if code == _abi.TRACE_BOOK_TOP:
+                if p0 >= 0:
+                    ex.append([time, 'BEST_BID', "{},{},{}".format(sym, p0, p1)])
+                if p2 >= 0:
+                    ex.append([time, 'BEST_ASK', "{},{},{}".format(sym, p2, p3)])
+                if self.snapshots:
+                    bids = [q for q, v in depth.items() if v < 0]
+                    asks = [q for q, v in depth.items() if v > 0]
+                    best_bid, best_ask = (max(bids) if bids else -1), (min(asks) if asks else -1)
+                    if (best_bid, best_ask) != (p0, p2) or (bids and -depth[best_bid] != p1) or (asks and depth[best_ask] != p3):
+                        raise RuntimeError("order-book account disagrees with the device's top of book at %d" % time)
+                    self.quotes_seen.update(depth)
+                    self.book_rows.append((time, dict(depth)))
+                continue
+            if code == _abi.TRACE_LAST_TRADE:
+                ex.append([time, 'LAST_TRADE', "{},${:0.4f}".format(p0, p1)])
+                continue
+            # ---- a dispatched event ----
+            base = code & ~_abi.MSG_REPLY
+            if agent == 0:
+                cur = None
+                if code == 0:
+                    continue
+                closed = time > self.mkt_close
+                if closed and base not in QUERY_MSGS:
+                    continue                                       # answered MKT_CLOSED before any logging (:126-144)
+                if base in ORDER_MSGS:
+                    if base == M["CANCEL_ORDER"]:
+                        c = copy_qty.get(p1)
+                        pl = placed.get(c[1]) if c else None
+                        if self.log_orders:
+                            if pl is None:
+                                raise RuntimeError("CANCEL_ORDER for an order the trace never saw placed (id %d)" % p1)
+                            ex.append([time, 'CANCEL_ORDER', _order_dict(p0, pl[0], sym, c[0], p3 > 0, p1, None, p2)])
+                        continue
+                    if base == M["MODIFY_ORDER"]:
+                        if self.log_orders:
+                            raise NotImplementedError("MODIFY_ORDER in the exchange log")
+                        continue
+                    pl = placed.get(p1)
+                    tp = pl[0] if pl else time
+                    cur = [tp, p1, None]
+                    if self.log_orders:
+                        lim = p2 if base == M["LIMIT_ORDER"] else None
+                        ex.append([time, _abi.MSG_NAMES[base], _order_dict(p0, tp, sym, abs(p3), p3 > 0, p1, None, lim)])
+                        if p1 == 0:
+                            cur[2] = len(ex) - 1
+                else:
+                    ex.append([time, _abi.MSG_NAMES[base], int(p0)])
+                continue
+            # delivered to a trading agent
+            last_time[agent] = time
+            if base == M["ORDER_EXECUTED"]:
+                c = copy_qty.get(p0)
+                if c is not None and abs(p2) < c[0]:               # orderExecuted (:416-421): a full fill only drops the copy
+                    c[0] -= abs(p2)
+            if agent not in logged:
+                continue
+            r = rows[agent]
+            if code == 0:
+                if agent not in woke:
+                    woke.add(agent)
+                    r.append((time, 'HOLDINGS_UPDATED', dict(hold[agent])))
+            elif base == M["QUERY_SPREAD"]:
+                bids = [(int(p0), int(p1))] if p0 >= 0 else []
+                asks = [(int(p2), int(p3))] if p2 >= 0 else []
+                r.append((time, 'BID_DEPTH', bids))
+                r.append((time, 'ASK_DEPTH', asks))
+                r.append((time, 'IMBALANCE', [sum(x[1] for x in bids), sum(x[1] for x in asks)]))
+            elif base == M["ORDER_EXECUTED"]:
+                h = hold[agent]
+                h[sym] = h.get(sym, 0) + p2
+                if h[sym] == 0:
+                    del h[sym]
+                h['CASH'] -= p2 * p3
+                r.append((time, 'HOLDINGS_UPDATED', dict(h)))
+            elif base == M["MKT_CLOSED"]:
+                r.append((time, 'MKT_CLOSED', ''))
+        for i, a in logged.items():                                # kernelStopping (TradingAgent.py:122-133, subclasses)
+            t = last_time.get(i, NAT)
+            r = rows[i]
+            h = dict(a.holdings)
+            r.append((t, 'FINAL_HOLDINGS', a.fmtHoldings(h)))
+            r.append((t, 'FINAL_CASH_POSITION', h['CASH']))
+            for s, shares in h.items():
+                if s == 'CASH':
+                    continue
+                lt = (a.marked_to_market - h['CASH']) // shares   # one symbol: marked_to_market = CASH + last_trade * shares
+                r.append((t, 'MARK_TO_MARKET', "{} {} @ {} == {}".format(shares, s, lt, lt * shares)))
+            r.append((t, 'MARKED_TO_MARKET', a.marked_to_market))
+            r.append((t, 'ENDING_CASH', a.marked_to_market))
+            for row in _summary_tail(a):
+                r.append((t,) + row)
+        self.agent_rows = {logged[i].name: r for i, r in rows.items() if i in logged}
+
+    # ---- frames -------------------------------------------------------------------------------------------------
+    def exchange_frame(self):
+        return _event_frame(self.exchange_rows)
+
+    def agent_frames(self):
+        return {name: _event_frame(r) for name, r in self.agent_rows.items()}
+
+    def book_frame(self):
+        """OrderBook.book_log_to_df + ExchangeAgent.logOrderBookSnapshots, book_freq == 0, wide_book."""
+        import pandas as pd
+        from scipy.sparse import dok_matrix
+        if not self.book_rows:
+            return None
+        quotes = sorted(self.quotes_seen)
+        col = {q: j for j, q in enumerate(quotes)}
+        S = dok_matrix((len(self.book_rows), len(quotes)), dtype=int)
+        for i, (_, row) in enumerate(self.book_rows):
+            for q, v in row.items():
+                S[i, col[q]] = v
+        df = pd.DataFrame.sparse.from_spmatrix(S.tocsc(), columns=quotes)
+        df.insert(0, 'QuoteTime', pd.to_datetime(np.array([t for t, _ in self.book_rows], np.int64)), allow_duplicates=True)
+        df.set_index('QuoteTime', inplace=True)
+        df = df[~df.index.duplicated(keep='last')]
+        df.sort_index(inplace=True)
+        return df.reindex(sorted(df.columns), axis=1)
+
+
+def _summary_tail(a):
+    """The rows an agent appends after ENDING_CASH (the same values runtime.summary_log_rows reports)."""
+    out = []
+    if a.final_valuation is not None:
+        zi = any(k.__name__ == "ZeroIntelligenceAgent" for k in type(a).__mro__)
+        out.append(('FINAL_VALUATION', int(a.final_valuation) if zi else a.final_valuation))
+    return out
+
+
+def _event_frame(rows):
+    import pandas as pd
+    t = np.array([r[0] for r in rows], np.int64)
+    df = pd.DataFrame({'EventTime': pd.to_datetime(t).where(t != NAT, pd.NaT), 'EventType': [r[1] for r in rows],
+                       'Event': pd.Series([r[2] for r in rows], dtype=object)})
+    return df.set_index('EventTime')
+
+
+def _ns(t):
+    import pandas as pd
+    return int(pd.Timestamp(t).value)
+
+
+def write_archives(kernel, trace, path):
+    """Write the exchange's log, the order-book archive and the agents' logs under `path` with the reference's file
+    names (Kernel.writeLog: the agent's name without blanks).  Returns the ExchangeArchive."""
+    ar = ExchangeArchive(kernel, trace)
+    os.makedirs(path, exist_ok=True)
+
+    def put(df, name):
+        df.to_pickle(os.path.join(path, "{}.bz2".format(name.replace(" ", ""))), compression='bz2')
+
+    if getattr(ar.exch, "log_to_file", True):
+        put(ar.exchange_frame(), ar.exch.name)
+    if ar.snapshots and str(ar.exch.book_freq).isdigit() and int(ar.exch.book_freq) == 0 and ar.exch.wide_book:
+        bf = ar.book_frame()
+        if bf is not None:
+            put(bf, "ORDERBOOK_{}_FULL".format(ar.symbol))
+    for name, df in ar.agent_frames().items():
+        put(df, name)
+    return ar

@@ -353,7 +353,7 @@ def lower_instance(agents, startTime, stopTime, defaultComputationDelay=1, defau
 class HostBatch:
     """Concatenated host tables of a list of InstanceSpec plus the ctypes `abides_batch` view."""
 
-    def __init__(self, specs, rng_mode=_abi.RNG_MT19937, trace_capacity=0):
+    def __init__(self, specs, rng_mode=_abi.RNG_MT19937, trace_capacity=0, trace_flags=0):
         self.specs = specs
         ni = len(specs)
         self.instances = (_abi.InstanceCfg * ni)()
@@ -392,7 +392,7 @@ class HostBatch:
         b = _abi.Batch()
         b.n_instances, b.n_types = ni, len(type_rows)
         b.n_agents_total, b.n_theta_total = a_off, t_off
-        b.rng_mode, b.trace_capacity = rng_mode, trace_capacity
+        b.rng_mode, b.trace_capacity, b.trace_flags = rng_mode, trace_capacity, trace_flags
         b.instances = C.cast(self.instances, C.POINTER(_abi.InstanceCfg))
         b.types = C.cast(self.types, C.POINTER(_abi.AgentType))
         p = lambda arr, ct: None if arr is None else arr.ctypes.data_as(C.POINTER(ct))

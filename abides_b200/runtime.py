@@ -68,7 +68,7 @@ def _check_status(res, allow_status):
 
 
 def run_specs(specs, device=0, rng_mode=_abi.RNG_MT19937, trace_capacity=0, allow_status=(), devices=None,
-              chunk_instances=None, engine_name=None):
+              chunk_instances=None, engine_name=None, trace_flags=0):
     """Kernel.runner for a list of lowered instances: H2D, run to completion, D2H.  An instance that ends with a
     status outside `allow_status` raises (ABIDES_ESTATE marks a run in which the reference itself raises).
     `devices` (a list of CUDA device indices) spreads the instances over several GPUs: see run_chunks."""
@@ -80,7 +80,7 @@ def run_specs(specs, device=0, rng_mode=_abi.RNG_MT19937, trace_capacity=0, allo
                           [hi - lo for lo, hi in bounds], devices, allow_status=allow_status, engine_name=engine_name)
     if devices:
         device = devices[0]
-    hb = lowering.HostBatch(specs, rng_mode=rng_mode, trace_capacity=trace_capacity)
+    hb = lowering.HostBatch(specs, rng_mode=rng_mode, trace_capacity=trace_capacity, trace_flags=trace_flags)
     eng = engine(device)
     if engine_name is not None:
         eng.set_engine(engine_name)
@@ -248,9 +248,11 @@ def fundamental_frame(kernel, trace):
 
 
 def write_logs(kernel, trace=None, root="."):
-    """Kernel.writeSummaryLog (Kernel.py:523-532) and, when a trace was taken, the exchange's fundamental archive --
-    bz2-pickled DataFrames under ./log/<log_dir>/ with the reference's file names, columns and dtypes.  The
-    per-agent event logs and the order-book snapshots are not emitted (out of scope)."""
+    """Kernel.writeSummaryLog (Kernel.py:523-532) and, when a trace was taken, what the agents archive at
+    kernelTerminating: the exchange's fundamental series (ExchangeAgent.py:91-101) and -- when the trace carries the
+    exchange-log records (run_spec_logged) -- the exchange's event log, its ORDERBOOK_<symbol>_FULL depth archive and
+    the trading agents' logs (abides_b200/exchange_log.py).  bz2-pickled DataFrames under ./log/<log_dir>/ with the
+    reference's file names, columns and dtypes."""
     import pandas as pd
     path = os.path.join(root, "log", kernel.log_dir)
     os.makedirs(path, exist_ok=True)
@@ -259,15 +261,21 @@ def write_logs(kernel, trace=None, root="."):
     if trace is not None and getattr(kernel.oracle, "symbols", None):
         sym, df = fundamental_frame(kernel, trace)
         df.to_pickle(os.path.join(path, "fundamental_{}.bz2".format(sym)), compression='bz2')
+    if trace is not None and len(trace) and (trace[:, 2] == _abi.TRACE_BOOK_TOP).any():
+        from abides_b200 import exchange_log
+        kernel.log_archive = exchange_log.write_archives(kernel, trace, path)
     return path
 
 
-def run_spec_logged(spec, device=0):
+def run_spec_logged(spec, device=0, engine_name=None, trace_flags=_abi.TRACE_EXCHANGE_LOG):
     """One instance with its full device trace: a first run sizes the trace (every dispatched event plus at most
-    one oracle step per event), the second records it."""
-    out = run_specs([spec], device=device)
+    one oracle step per event; with the exchange-log records at most five per order -- placed, accepted, cancelled,
+    book top, last trade -- and two per fill), the second records it."""
+    out = run_specs([spec], device=device, engine_name=engine_name)
     cap = 2 * int(out.res["delivered"][0]) + 2 * spec.n_agents + 64
-    out = run_specs([spec], device=device, trace_capacity=cap)
+    if trace_flags & _abi.TRACE_EXCHANGE_LOG:
+        cap += 5 * int(out.res["n_orders"][0]) + 2 * int(out.res["n_fills"][0])
+    out = run_specs([spec], device=device, trace_capacity=cap, engine_name=engine_name, trace_flags=trace_flags)
     tr, n = engine(device).trace(0)
     if n > cap:
         raise RuntimeError("trace overflow: %d records, capacity %d" % (n, cap))

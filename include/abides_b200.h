@@ -163,8 +163,28 @@ typedef struct abides_batch {
   int64_t n_mt_rows;                      /* rows of mt_key when mt_key_row is given */
   /* constructor-time draws the device performs from the agents' own (seeded) streams, enum abides_draw_flags */
   int32_t draw_flags;
-  int32_t reserved0;
+  int32_t trace_flags;                    /* enum abides_trace_flags: extra trace records (only with trace_capacity > 0) */
 } abides_batch;
+
+enum abides_trace_flags {
+  /* Everything the reference's EXCHANGE_AGENT.bz2 and ORDERBOOK_<symbol>_FULL.bz2 archives hold beyond the dispatched
+   * events (agent/ExchangeAgent.py:147-150,:404-408, util/OrderBook.py:108-156), as extra trace records in program order:
+   *   ABIDES_TRACE_ORDER_PLACED  agent = the placing agent, time = its currentTime (Order.time_placed):
+   *                              p0 = order id in the message, p1 = limit price, p2 = signed quantity, p3 = 1 for a
+   *                              market order (TradingAgent.placeLimitOrder / placeMarketOrder :295-365)
+   *   ABIDES_TRACE_EXCH_SENT | ORDER_ACCEPTED / _EXECUTED / _CANCELLED / _MODIFIED   agent = recipient, time = the
+   *                              exchange's currentTime: p0 = order id, p1 = limit price, p2 = signed quantity,
+   *                              p3 = fill price (-1 none) -- one per notification, in the order the book sends them
+   *   ABIDES_TRACE_BOOK_TOP      after every handleLimitOrder: p0 / p1 = best bid and its volume, p2 / p3 = best ask and
+   *                              its volume (price -1 = empty side): the BEST_BID / BEST_ASK rows and the snapshot marker
+   *   ABIDES_TRACE_LAST_TRADE    after a handleLimitOrder that traded: p0 = traded quantity, p1 = average price */
+  ABIDES_TRACE_EXCHANGE_LOG = 1
+};
+enum abides_trace_code {
+  ABIDES_TRACE_FUNDAMENTAL = 64,          /* an oracle step: time = its timestamp, agent = -1, p0 = the new value */
+  ABIDES_TRACE_ORDER_PLACED = 65, ABIDES_TRACE_BOOK_TOP = 66, ABIDES_TRACE_LAST_TRADE = 67,
+  ABIDES_TRACE_EXCH_SENT = 128
+};
 
 enum abides_draw_flags {
   /* `theta` is not given (agent_theta holds the layout only): every ZI / HBL agent draws

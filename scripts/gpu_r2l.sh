@@ -1,8 +1,8 @@
 #!/bin/bash
-# round 2, GPU trip: a warp of the lane CTA dedicated to the heavy handler classes
+# round 2, GPU trip: the whole -m gpu suite on the restored tree, then BASELINE configs[4] -- the rmsc03 parameter grid,
+# 16 points x 1024 seeds = 16 384 instances in one batch on one GPU
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_lane.py -x -q -k "golden or sweep or philox or pause" 2>&1 | tail -2
-timeout 600 python scripts/gpu_lane_prof.py sparse_zi_1000 8192 2>&1 | grep -v Warning | tail -1
-timeout 900 python scripts/gpu_lane_perf.py sparse_zi_1000 45056 lane 2>&1 | grep -v Warning | tail -1 | cut -c1-330
-timeout 600 python scripts/gpu_lane_perf.py sparse_zi_100 65536 lane 2>&1 | grep -v Warning | tail -1 | cut -c1-330
-timeout 900 python scripts/gpu_lane_perf.py rmsc03_2h 16384 lane 2>&1 | grep -v Warning | tail -1 | cut -c1-330
+nvidia-smi --query-gpu=index,name --format=csv,noheader
+( time timeout 840 python -m pytest tests -m gpu -x -q ) > gpurun_out/r2l_gpu_tests.log 2>&1; tail -4 gpurun_out/r2l_gpu_tests.log
+timeout 540 python bench.py --workload rmsc03_grid --instances 16384 --steps 2 --warmup 1 --e2e-steps 1 --also '' \
+    > gpurun_out/r2l_bench_grid_x16384.json 2> gpurun_out/r2l_bench_grid_x16384.err; tail -c 1500 gpurun_out/r2l_bench_grid_x16384.json; tail -3 gpurun_out/r2l_bench_grid_x16384.err

@@ -95,6 +95,7 @@ int hostsim_run(const abides_batch* b, int force_variant, abides_instance_result
   lb.n_instances = ni; lb.trace_cap = (int)trace_capacity; lb.n_types = b->n_types; lb.top_k = cap.top_k;
   lb.rng_mode = b->rng_mode;
   lb.run_ahead = getenv("ABIDES_LANE_RUN_AHEAD") ? atoi(getenv("ABIDES_LANE_RUN_AHEAD")) : 0;
+  lb.trace_flags = b->trace_flags;
   lb.hcap = cap.hcap; lb.scap = cap.scap; lb.arena_cap = cap.arena_cap; lb.deep_cap = cap.deep_cap;
   lb.txn_cap = cap.txn_cap; lb.unr_cap = cap.unr_cap;
   lb.cfg = b->instances; lb.types = b->types;
