@@ -11,7 +11,7 @@ EXTRA_STREAMS = 4
 STREAM_ORACLE, STREAM_KERNEL, STREAM_LATENCY, STREAM_GLOBAL = 0, 1, 2, 3
 
 # enum abides_agent_class
-EXCHANGE, ZI, VALUE, NOISE, MOMENTUM, ADAPTIVE_MM, POV_EXEC, MARKET_MAKER, HBL, SCHEDULE_EXEC, SUBSCRIPTION = range(11)
+EXCHANGE, ZI, VALUE, NOISE, MOMENTUM, ADAPTIVE_MM, POV_EXEC, MARKET_MAKER, HBL, SCHEDULE_EXEC, SUBSCRIPTION, MARKET_REPLAY = range(12)
 # enum abides_latency_kind
 LAT_DETERMINISTIC, LAT_CUBIC, LAT_LEGACY_NOISE = range(3)
 # enum abides_rng_mode
@@ -30,6 +30,7 @@ MSG_CODES = {v: k for k, v in MSG_NAMES.items()}
 TRACE_FUNDAMENTAL = 64          # trace code of an oracle step (include/abides_b200.h: enum abides_trace_code)
 TRACE_ORDER_PLACED, TRACE_BOOK_TOP, TRACE_LAST_TRADE, TRACE_EXCH_SENT = 65, 66, 67, 128
 TRACE_EXCHANGE_LOG = 1          # enum abides_trace_flags
+INST_NO_ORACLE = 1              # enum abides_instance_flags
 MSG_REPLY = 32
 
 
@@ -71,7 +72,7 @@ class InstanceCfg(C.Structure):
         ("n_agents", C.c_int32), ("type_base", C.c_int32),
         ("theta_offset", C.c_int64),
         ("seed", C.c_uint64),
-        ("reserved", C.c_int64 * 2),
+        ("flags", C.c_int64), ("reserved", C.c_int64),
     ]
 
 

@@ -822,13 +822,20 @@ int abides_load(abides_handle* h, const abides_batch* b) {
     if (ic.agent_offset != off || ic.n_agents <= 0) return fail(ABIDES_EINVAL, "abides_load: agent_offset must be the prefix sum of n_agents");
     if (ic.type_base < 0 || ic.type_base >= b->n_types) return fail(ABIDES_EINVAL, "abides_load: bad type_base");
     if (ic.r_bar < 0 || ic.r_bar > 2.0e9) return fail(ABIDES_EINVAL, "abides_load: r_bar out of the int32 price range");
+    if (ic.flags & ~(int64_t)ABIDES_INST_NO_ORACLE) return fail(ABIDES_EINVAL, "abides_load: unknown instance flags");
     if (off + ic.n_agents > na) return fail(ABIDES_EINVAL, "abides_load: n_agents_total mismatch");
     for (int a = 0; a < ic.n_agents; a++) {
       int t = ic.type_base + b->agent_type[off + a];
       if (t < 0 || t >= b->n_types) return fail(ABIDES_EINVAL, "abides_load: agent_type out of range");
       int k = b->types[t].klass;
       if ((a == 0) != (k == ABIDES_EXCHANGE)) return fail(ABIDES_EINVAL, "abides_load: agent 0 (and only agent 0) must be the exchange");
-      if (k < 0 || k > ABIDES_SUBSCRIPTION) return fail(ABIDES_EINVAL, "abides_load: unknown agent class");
+      if (k < 0 || k > ABIDES_MARKET_REPLAY) return fail(ABIDES_EINVAL, "abides_load: unknown agent class");
+      if (k == ABIDES_MARKET_REPLAY) {                    // the tape: six ints per row in the agent's theta slice
+        const long long rows = b->agent_size ? b->agent_size[off + a] : 0;
+        if (rows < 1 || b->agent_theta[off + a] < 0 || !b->theta || draw_theta ||
+            ic.theta_offset + b->agent_theta[off + a] + 6 * rows > b->n_theta_total)
+          return fail(ABIDES_EINVAL, "abides_load: MarketReplayAgent without a tape (theta rows, agent_size = row count)");
+      }
       if (k == ABIDES_HBL) { n_hbl++; if (b->types[t].hbl_L < 1) return fail(ABIDES_EINVAL, "abides_load: HBL agent with L < 1"); }
       if (a > 0) class_mask |= 1u << k;
       if (b->types[t].subscribe) {
@@ -880,6 +887,11 @@ int abides_load(abides_handle* h, const abides_batch* b) {
     const bool zi_only = lane_variant == lane::LV_ZI_LEGACY || lane_variant == lane::LV_ZI_CUBIC;
     const int auto_min = zi_only ? ABIDES_LANE_AUTO_MIN_INSTANCES_ZI : ABIDES_LANE_AUTO_MIN_INSTANCES;
     bool to_warp = pref == ABIDES_ENGINE_WARP || (pref == ABIDES_ENGINE_AUTO && ni < auto_min);
+    if (class_mask & (1u << ABIDES_MARKET_REPLAY)) {      // order-tape replay agents run on the lane engine only
+      if (pref == ABIDES_ENGINE_WARP || lane_variant == lane::LV_NONE)
+        return fail(ABIDES_EINVAL, "abides_load: MarketReplayAgent runs on the lane engine (not with HBL agents / subscriptions)");
+      to_warp = false;
+    }
     if (to_warp && pref == ABIDES_ENGINE_AUTO && lane_variant != lane::LV_NONE) {
       // AUTO never picks an engine whose tables cannot fit: the warp engine keeps a 2.5 KB MT19937 state per stream
       // (twice for batches uploaded with their states) and the larger per-instance capacities below -- ~20 MB for an

@@ -21,7 +21,7 @@ inline int lane_pick_variant(unsigned class_mask, unsigned lat_mask, int rng_mod
   const unsigned zi = 1u << ABIDES_ZI;
   const unsigned rmsc = (1u << ABIDES_NOISE) | (1u << ABIDES_VALUE) | (1u << ABIDES_MOMENTUM) | (1u << ABIDES_ADAPTIVE_MM) |
                         (1u << ABIDES_POV_EXEC);
-  const unsigned full = zi | rmsc | (1u << ABIDES_MARKET_MAKER) | (1u << ABIDES_SCHEDULE_EXEC);
+  const unsigned full = zi | rmsc | (1u << ABIDES_MARKET_MAKER) | (1u << ABIDES_SCHEDULE_EXEC) | (1u << ABIDES_MARKET_REPLAY);
   if ((class_mask & ~zi) == 0 && lat_mask == (1u << ABIDES_LAT_LEGACY_NOISE)) return LV_ZI_LEGACY;
   if ((class_mask & ~zi) == 0 && lat_mask == (1u << ABIDES_LAT_CUBIC)) return LV_ZI_CUBIC;
   if ((class_mask & ~rmsc) == 0 && lat_mask == (1u << ABIDES_LAT_DETERMINISTIC)) return LV_RMSC;

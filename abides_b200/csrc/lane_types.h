@@ -41,10 +41,12 @@
 #define LN_CLS_MARKET_MAKER 7
 #define LN_CLS_HBL 8
 #define LN_CLS_SCHEDULE_EXEC 9
+#define LN_CLS_MARKET_REPLAY 11
 static_assert(LN_CLS_ZI == ABIDES_ZI && LN_CLS_VALUE == ABIDES_VALUE && LN_CLS_NOISE == ABIDES_NOISE &&
               LN_CLS_MOMENTUM == ABIDES_MOMENTUM && LN_CLS_ADAPTIVE_MM == ABIDES_ADAPTIVE_MM &&
               LN_CLS_POV_EXEC == ABIDES_POV_EXEC && LN_CLS_MARKET_MAKER == ABIDES_MARKET_MAKER &&
-              LN_CLS_HBL == ABIDES_HBL && LN_CLS_SCHEDULE_EXEC == ABIDES_SCHEDULE_EXEC, "class constants");
+              LN_CLS_HBL == ABIDES_HBL && LN_CLS_SCHEDULE_EXEC == ABIDES_SCHEDULE_EXEC &&
+              LN_CLS_MARKET_REPLAY == ABIDES_MARKET_REPLAY, "class constants");
 #define LN_CLS(k) (1 << (k))
 
 namespace lane {
@@ -56,6 +58,14 @@ namespace lane {
 // handler alone is the critical path of a round, whichever warp runs it)
 #ifndef LANE_HEAVY_WARPS
 #define LANE_HEAVY_WARPS 0
+#endif
+// LANE_STAGE: copy the instance's hot scalars and the recipient's record to thread-local memory around each half of a
+// round (1) or work on them in place (0).  LANE_ONE_CTX: one LCtx per thread, re-pointed per half, instead of two.
+#ifndef LANE_STAGE
+#define LANE_STAGE 1
+#endif
+#ifndef LANE_ONE_CTX
+#define LANE_ONE_CTX 0
 #endif
 constexpr int LANE_CTA = LANE_CTA_THREADS;   // instances per CTA of the event loop (one owner thread each)
 constexpr int LANE_HEAVY = 32 * LANE_HEAVY_WARPS;   // extra threads of a CTA that only run the heavy handler classes
@@ -108,6 +118,7 @@ struct LN_ALIGN(128) LAgent {           // 128 bytes = four 32-byte sectors; sec
              int buy_size, sell_size, tick_size, last_mid; } mm;
     struct { long long executed, transacted_volume; } pov;
     struct { long long executed; double arrival; } sx;
+    struct { int row0, started; } rp;   // MarketReplayAgent: first tape row of the group the next wake places
   } u;
 };
 static_assert(sizeof(LAgent) == 128, "LAgent must be 128 bytes");

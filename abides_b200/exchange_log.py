@@ -16,7 +16,7 @@ Everything here is derived from the device's trace of one instance: the dispatch
 (accepted - executed - cancelled per price), not a second matching engine; the device's top-of-book record cross-checks
 it at every snapshot.
 
-Not reproduced: MODIFY_ORDER in the archives, `book_freq` sampling other than 0 (every update), the long-format
+Not reproduced: `book_freq` sampling other than 0 (every update), the long-format
 (`wide_book=False`) archive (the reference itself fails there: pd.SparseDataFrame, ExchangeAgent.py:384), agents with
 `log_orders=True` that place orders, and the logs of agents whose spread queries ask for more than the best level (market makers,
 execution agents that trade): their BID_DEPTH / ASK_DEPTH rows would need levels the trace does not carry -- those
@@ -90,14 +90,19 @@ class ExchangeArchive:
         placed = {}            # order id in the agent's message -> (time_placed, agent, price, signed qty, is_market)
         copy_qty = {}          # id of the agent's own copy of an order -> [quantity the copy shows, message id]
         book_time = {}         # order id in the book -> time_placed
-        resting = {}           # order id in the book -> [price, side (+1 bid / -1 ask), quantity]
+        modified_at = {}       # order id -> time_placed of the new order of its latest MODIFY_ORDER
+        levels = {}            # price -> [side (+1 bid / -1 ask), [[order id, quantity], ...] oldest first]
         depth = {}             # price -> signed resting volume (bids negative, as the archive stores them)
         cur = None             # the order message the exchange is handling: [time_placed, message id, row to patch]
+        n_exec = 0             # ORDER_EXECUTED notifications of the current exchange event: aggressor, resting, aggressor, ...
         ex = self.exchange_rows
         for time, agent, code, p0, p1, p2, p3 in tr.tolist():
             if code == _abi.TRACE_FUNDAMENTAL:
                 continue
             if code == _abi.TRACE_ORDER_PLACED:
+                if p3 == 2:                                        # the new order of a modification: only its time matters
+                    modified_at[p0] = time
+                    continue
                 placed[p0] = (time, agent, p1, p2, p3)
                 if agent in logged and getattr(logged[agent], "log_orders", False):
                     self.skipped_agents.append(logged.pop(agent).name)     # ORDER_SUBMITTED / CANCEL_SUBMITTED rows: not derivable
@@ -111,24 +116,41 @@ class ExchangeArchive:
                     r[2]['order_id'] = p0 - 1
                     cur[2] = None
                 tp = book_time.get(p0, cur[0] if cur is not None else time)
-                if self.log_orders:
+                if self.log_orders and msg != M["ORDER_MODIFIED"]:   # ORDER_MODIFIED is sent but not logged (ExchangeAgent.py:404-411)
                     ex.append([time, _abi.MSG_NAMES[msg], _order_dict(agent, tp, sym, abs(p2), p2 > 0, p0, p3, p1)])
+                # the depth account: price levels as the FIFO lists the book keeps (OrderBook.py:272-298)
+                lv = levels.get(p1)
                 if msg == M["ORDER_ACCEPTED"]:
                     book_time[p0] = tp
-                    side = 1 if p2 > 0 else -1
-                    resting[p0] = [p1, side, abs(p2)]
-                    depth[p1] = depth.get(p1, 0) - side * abs(p2)
-                elif msg in (M["ORDER_EXECUTED"], M["ORDER_CANCELLED"]) and p0 in resting:
-                    r = resting[p0]
-                    q = abs(p2)
-                    depth[r[0]] += r[1] * q
-                    if depth[r[0]] == 0:
-                        del depth[r[0]]
-                    r[2] -= q
-                    if r[2] <= 0:
-                        del resting[p0]
-                elif msg == M["ORDER_MODIFIED"] and self.snapshots:
-                    raise NotImplementedError("MODIFY_ORDER in the order-book archive")
+                    if lv is None:
+                        lv = levels[p1] = [1 if p2 > 0 else -1, []]
+                    lv[1].append([p0, abs(p2)])
+                elif msg == M["ORDER_EXECUTED"]:
+                    n_exec += 1
+                    if n_exec % 2 == 0:                            # the resting side: always the oldest order of its level
+                        if lv is None or lv[1][0][0] != p0:
+                            raise RuntimeError("order-book account: execution of %d is not at the front of level %d" % (p0, p1))
+                        lv[1][0][1] -= abs(p2)
+                        if lv[1][0][1] <= 0:
+                            lv[1].pop(0)
+                elif msg == M["ORDER_CANCELLED"]:                  # the first order of that id at the level (:319-346)
+                    k = next((i for i, e in enumerate(lv[1]) if e[0] == p0), None) if lv else None
+                    if k is None:
+                        raise RuntimeError("order-book account: cancellation of an unknown order %d" % p0)
+                    lv[1].pop(k)
+                elif msg == M["ORDER_MODIFIED"]:                   # book[i][0] = new_order (:359): the level's FIRST order
+                    if lv is None or not lv[1]:
+                        raise RuntimeError("order-book account: modification at an empty level %d" % p1)
+                    lv[1][0] = [p0, abs(p2)]
+                    book_time[p0] = modified_at.get(p0, time)
+                if lv is not None:
+                    v = sum(e[1] for e in lv[1])
+                    if v:
+                        depth[p1] = -lv[0] * v
+                    else:
+                        depth.pop(p1, None)
+                        if not lv[1]:
+                            del levels[p1]
                 continue
             if code == _abi.TRACE_BOOK_TOP:
                 if p0 >= 0:
@@ -151,6 +173,7 @@ class ExchangeArchive:
             base = code & ~_abi.MSG_REPLY
             if agent == 0:
                 cur = None
+                n_exec = 0
                 if code == 0:
                     continue
                 closed = time > self.mkt_close
@@ -165,9 +188,14 @@ class ExchangeArchive:
                                 raise RuntimeError("CANCEL_ORDER for an order the trace never saw placed (id %d)" % p1)
                             ex.append([time, 'CANCEL_ORDER', _order_dict(p0, pl[0], sym, c[0], p3 > 0, p1, None, p2)])
                         continue
-                    if base == M["MODIFY_ORDER"]:
+                    if base == M["MODIFY_ORDER"]:                  # logs the sender's own copy of the order (:148)
+                        c = copy_qty.get(p1)
+                        pl = placed.get(c[1]) if c else None
                         if self.log_orders:
-                            raise NotImplementedError("MODIFY_ORDER in the exchange log")
+                            if pl is None:
+                                raise RuntimeError("MODIFY_ORDER for an order the trace never saw placed (id %d)" % p1)
+                            ex.append([time, 'MODIFY_ORDER', _order_dict(p0, pl[0], sym, c[0], p3 > 0, p1, None, p2)])
+                        cur = [pl[0] if pl else time, p1, None]
                         continue
                     pl = placed.get(p1)
                     tp = pl[0] if pl else time

@@ -24,6 +24,7 @@ _CLASS_BY_NAME = {
     "TWAPExecutionAgent": _abi.SCHEDULE_EXEC,
     "VWAPExecutionAgent": _abi.SCHEDULE_EXEC,
     "SubscriptionAgent": _abi.SUBSCRIPTION,
+    "MarketReplayAgent": _abi.MARKET_REPLAY,
 }
 
 
@@ -90,6 +91,30 @@ def _schedule_rows(agent):
             raise NotImplementedError("schedule quantity %r" % (q,))
         out.append(int(q))
     return out
+
+
+def _replay_rows(agent, mkt_open_ns):
+    """The tape of a MarketReplayAgent as the device reads it: six int32 per row in time order -- time lo, time hi (ns),
+    ORDER_ID, PRICE, SIZE, BUY -- from `historical_orders.orders_dict` ({timestamp: [row dicts]}, MarketReplayAgent.py:
+    121); returns (rows, first wake-up time).  A row that re-prices or flips an order the agent still holds open ends
+    the instance on the device with ABIDES_EINVAL: the reference's modifyOrder then leaves a book whose level prices are
+    inconsistent (util/OrderBook.py:359 overwrites the first order of the OLD price level with the new order), which no
+    sorted book can mirror."""
+    od = agent.historical_orders.orders_dict
+    out = []
+    times = [_ns(t) for t in od]
+    if not times or any(b <= a for a, b in zip(times, times[1:])):
+        raise NotImplementedError("MarketReplayAgent: order timestamps must be non-empty and ascending")
+    if times[0] < mkt_open_ns:
+        raise NotImplementedError("MarketReplayAgent: first order before the market opens")
+    for t, group in zip(times, od.values()):
+        for r in group:
+            oid, price, size = int(r['ORDER_ID']), int(r['PRICE']), int(r['SIZE'])
+            buy = 1 if r['BUY_SELL_FLAG'] == 'BUY' else 0
+            if not (0 < oid < 2 ** 31 and 0 <= price < 2 ** 31 and 0 <= size < 2 ** 31):
+                raise NotImplementedError("MarketReplayAgent: order row out of range: %r" % (r,))
+            out.extend([np.int32(np.uint32(t & 0xFFFFFFFF)), np.int32(t >> 32), oid, price, size, buy])
+    return [int(x) for x in out], times[0]
 
 
 _MM_LEVELS_QUOTE_DICT = {1: [1, 0, 0, 0, 0], 2: [.5, .5, 0, 0, 0], 3: [.34, .33, .33, 0, 0], 4: [.25, .25, .25, .25, 0],
@@ -229,6 +254,9 @@ def lower_instance(agents, startTime, stopTime, defaultComputationDelay=1, defau
         if k != _abi.EXCHANGE and getattr(a, "symbol", symbol) != symbol:
             raise NotImplementedError("agent %d trades %r, the exchange lists %r" % (i, a.symbol, symbol))
         row = _type_row(a, k)
+        if k == _abi.MARKET_REPLAY:
+            replay_rows, first = _replay_rows(a, _ns(ex.mkt_open))
+            row["wake_up_freq"] = first - _ns(ex.mkt_open)                       # getWakeFrequency (:64-66)
         key = tuple(sorted(row.items()))
         if key not in type_index:
             type_index[key] = len(types)
@@ -252,6 +280,10 @@ def lower_instance(agents, startTime, stopTime, defaultComputationDelay=1, defau
         if k == _abi.SCHEDULE_EXEC:
             agent_theta[i] = len(theta)
             theta.extend(_schedule_rows(a))
+        if k == _abi.MARKET_REPLAY:
+            agent_theta[i] = len(theta)
+            theta.extend(replay_rows)
+            size[i] = len(replay_rows) // 6
         mt_key[i], mt_pos[i], mt_hg[i], mt_g[i] = _mt_state(a.random_state)
         spec.agent_names.append(getattr(a, "name", str(i)))
         spec.agent_type_names.append(getattr(a, "type", ""))
@@ -307,7 +339,11 @@ def lower_instance(agents, startTime, stopTime, defaultComputationDelay=1, defau
             lat_from[:] = np.asarray(agentLatency[0], dtype=np.float64)
             lat_to[:] = np.asarray([agentLatency[i][0] for i in range(n)], dtype=np.float64)
 
-    # oracle (util/oracle/SparseMeanRevertingOracle.py)
+    # oracle (util/oracle/SparseMeanRevertingOracle.py); none at all for a pure replay (config/marketreplay.py:138)
+    if oracle is None and all(agent_class(a) == _abi.MARKET_REPLAY for a in agents[1:]):
+        return _finish_without_oracle(spec, cfg, ex, startTime, stopTime, defaultComputationDelay, seed, types, agent_type,
+                                      lat_to, lat_from, size, wake, agent_theta, theta, mt_key, mt_pos, mt_hg, mt_g,
+                                      kernel_random_state, lat_rs, global_state, n)
     if oracle is None or type(oracle).__name__ != "SparseMeanRevertingOracle":
         raise NotImplementedError("oracle must be a SparseMeanRevertingOracle")
     if list(oracle.symbols) != [symbol]:
@@ -335,6 +371,33 @@ def lower_instance(agents, startTime, stopTime, defaultComputationDelay=1, defau
     mt_key[n + 3], mt_pos[n + 3], mt_hg[n + 3], mt_g[n + 3] = _mt_state(global_state)
     assert e == 4
 
+    cfg.update(start_time=_ns(startTime), stop_time=_ns(stopTime), mkt_open=_ns(ex.mkt_open),
+               mkt_close=_ns(ex.mkt_close), default_computation_delay=int(defaultComputationDelay),
+               exch_pipeline_delay=int(ex.pipeline_delay), exch_computation_delay=int(ex.computation_delay),
+               stream_history=int(ex.stream_history), exch_log_orders=1 if ex.log_orders else 0,
+               seed=int(seed) & 0xFFFFFFFFFFFFFFFF)
+    spec.types = types
+    spec.agent_type = agent_type
+    spec.lat_to, spec.lat_from = lat_to, lat_from
+    spec.size, spec.wakeup_time = size, wake
+    spec.agent_theta = agent_theta
+    spec.theta = np.asarray(theta, np.int32)
+    spec.mt_key, spec.mt_pos, spec.mt_has_gauss, spec.mt_gauss = mt_key, mt_pos, mt_hg, mt_g
+    return spec
+
+
+def _finish_without_oracle(spec, cfg, ex, startTime, stopTime, defaultComputationDelay, seed, types, agent_type, lat_to,
+                           lat_from, size, wake, agent_theta, theta, mt_key, mt_pos, mt_hg, mt_g, kernel_random_state,
+                           lat_rs, global_state, n):
+    """Kernel.runner(oracle=None): the exchange opens without a price (ExchangeAgent.py:84-88)."""
+    cfg.update(r_bar=0.0, kappa=0.0, fund_vol=0.0, megashock_lambda_a=1.0, megashock_mean=0.0, megashock_var=0.0,
+               megashock_time0=2 ** 62, megashock_value0=0.0, flags=_abi.INST_NO_ORACLE)
+    if kernel_random_state is not None:
+        mt_key[n + 1], mt_pos[n + 1], mt_hg[n + 1], mt_g[n + 1] = _mt_state(kernel_random_state)
+    if lat_rs is not None:
+        mt_key[n + 2], mt_pos[n + 2], mt_hg[n + 2], mt_g[n + 2] = _mt_state(lat_rs)
+    mt_key[n + 3], mt_pos[n + 3], mt_hg[n + 3], mt_g[n + 3] = _mt_state(
+        global_state if global_state is not None else np.random.get_state())
     cfg.update(start_time=_ns(startTime), stop_time=_ns(stopTime), mkt_open=_ns(ex.mkt_open),
                mkt_close=_ns(ex.mkt_close), default_computation_delay=int(defaultComputationDelay),
                exch_pipeline_delay=int(ex.pipeline_delay), exch_computation_delay=int(ex.computation_delay),

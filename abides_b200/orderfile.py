@@ -25,26 +25,34 @@ def _timestamp_ns(text):
     return int((t - _EPOCH).total_seconds()) * 10 ** 9 + ns
 
 
-def parse_orders_file(path, agent=1, price_scale=1, start_ns=None, end_ns=None):
-    """Rows TIMESTAMP, ORDER_ID, PRICE, SIZE, BUY_SELL_FLAG (',' or '|' separated; flag BUY / SELL or 0 / 1) ->
-    int64[n, 8] tape rows (kind, agent, order_id, price, qty, is_buy, new_qty, time_ns) for engine.replay_book."""
+def read_rows(path, price_scale=1, start_ns=None, end_ns=None):
+    """Rows TIMESTAMP, ORDER_ID, PRICE, SIZE, BUY_SELL_FLAG (',' or '|' separated; flag BUY / SELL or 0 / 1) of an order
+    file inside [start_ns, end_ns) -> list of (time_ns, order_id, price, size, is_buy)."""
     with open(path, newline="") as f:
         head = f.readline()
         sep = "|" if "|" in head else ","
         cols = [c.strip() for c in head.strip().split(sep)]
         rows = list(csv.reader(f, delimiter=sep))
     ix = {c: cols.index(c) for c in ("TIMESTAMP", "ORDER_ID", "PRICE", "SIZE", "BUY_SELL_FLAG")}
-    tape, live = [], {}
+    out = []
     for r in rows:
         if len(r) < len(cols):
             continue
         t = _timestamp_ns(r[ix["TIMESTAMP"]])
         if (start_ns is not None and t < start_ns) or (end_ns is not None and t >= end_ns):
             continue
-        oid, size = int(r[ix["ORDER_ID"]]), int(r[ix["SIZE"]])
-        price = int(float(r[ix["PRICE"]]) * price_scale)
         flag = r[ix["BUY_SELL_FLAG"]].strip().upper()
-        buy = 1 if flag in ("BUY", "0") else 0
+        # PRICE: float * scale, truncated (MarketReplayAgent.py:113-114: .astype(float) * 100, .astype(int))
+        out.append((t, int(r[ix["ORDER_ID"]]), int(float(r[ix["PRICE"]]) * price_scale), int(r[ix["SIZE"]]),
+                    1 if flag in ("BUY", "0") else 0))
+    return out
+
+
+def parse_orders_file(path, agent=1, price_scale=1, start_ns=None, end_ns=None):
+    """An order file -> int64[n, 8] tape rows (kind, agent, order_id, price, qty, is_buy, new_qty, time_ns) for
+    engine.replay_book: the message MarketReplayAgent.placeOrder (:47-62) sends for every row."""
+    tape, live = [], {}
+    for t, oid, price, size, buy in read_rows(path, price_scale, start_ns, end_ns):
         ex = live.get(oid)
         if ex is None and size > 0:
             tape.append((LIMIT, agent, oid, price, size, buy, 0, t))

@@ -49,7 +49,11 @@ enum abides_agent_class {
   ABIDES_MARKET_MAKER = 7,  /* agent/market_makers/MarketMakerAgent.py (polling mode, subscribe=False) */
   ABIDES_HBL = 8,           /* agent/HeuristicBeliefLearningAgent.py (a ZeroIntelligenceAgent subclass) */
   ABIDES_SCHEDULE_EXEC = 9, /* agent/execution/ExecutionAgent.py with a schedule: TWAPExecutionAgent.py, VWAPExecutionAgent.py */
-  ABIDES_SUBSCRIPTION = 10  /* agent/examples/SubscriptionAgent.py: subscribes to market data, never trades */
+  ABIDES_SUBSCRIPTION = 10, /* agent/examples/SubscriptionAgent.py: subscribes to market data, never trades */
+  /* agent/examples/MarketReplayAgent.py: replays an order tape (lane engine only).  The agent's `theta` rows hold the
+   * tape, six ints per row in time order -- time lo, time hi (ns), ORDER_ID, PRICE, SIZE, BUY (1 / 0) --, agent_size the
+   * number of rows, the type row's wake_up_freq = first tape time - mkt_open (getWakeFrequency :64-66) */
+  ABIDES_MARKET_REPLAY = 11
 };
 
 enum abides_latency_kind {
@@ -124,8 +128,13 @@ typedef struct abides_instance_cfg {
   int32_t type_base;                      /* first row of this instance's types in `types` */
   int64_t theta_offset;                   /* first int of this instance in `theta` */
   uint64_t seed;                          /* Philox mode: instance key */
-  int64_t reserved[2];
+  int64_t flags;                          /* enum abides_instance_flags */
+  int64_t reserved;
 } abides_instance_cfg;
+enum abides_instance_flags {
+  ABIDES_INST_NO_ORACLE = 1               /* Kernel.runner(oracle=None) (config/marketreplay.py): the exchange has no opening
+                                             price (ExchangeAgent.py:84-88), no agent may ask the oracle */
+};
 
 /* A batch of instances: tables are concatenated over instances in instance order. */
 typedef struct abides_batch {
@@ -171,7 +180,8 @@ enum abides_trace_flags {
    * events (agent/ExchangeAgent.py:147-150,:404-408, util/OrderBook.py:108-156), as extra trace records in program order:
    *   ABIDES_TRACE_ORDER_PLACED  agent = the placing agent, time = its currentTime (Order.time_placed):
    *                              p0 = order id in the message, p1 = limit price, p2 = signed quantity, p3 = 1 for a
-   *                              market order (TradingAgent.placeLimitOrder / placeMarketOrder :295-365)
+   *                              market order (TradingAgent.placeLimitOrder / placeMarketOrder :295-365), 2 for the
+   *                              new order of a modification (MarketReplayAgent.py:56-59)
    *   ABIDES_TRACE_EXCH_SENT | ORDER_ACCEPTED / _EXECUTED / _CANCELLED / _MODIFIED   agent = recipient, time = the
    *                              exchange's currentTime: p0 = order id, p1 = limit price, p2 = signed quantity,
    *                              p3 = fill price (-1 none) -- one per notification, in the order the book sends them

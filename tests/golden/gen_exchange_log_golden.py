@@ -50,6 +50,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--name", required=True)
     ap.add_argument("--out", default=os.path.join(REPO, "tests", "golden"))
+    ap.add_argument("--config-path", default=None,
+                    help="run this config FILE (written against the reference API) instead of config.<name>")
     ap.add_argument("ref_args", nargs=argparse.REMAINDER)
     args = ap.parse_args()
     ref_args = [a for a in args.ref_args if a != "--"]
@@ -66,7 +68,12 @@ def main():
     sys.argv = ["abides.py"] + ref_args + ["-l", "golden"]
     cfg = ref_args[ref_args.index("-c") + 1]
     with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
-        importlib.import_module("config." + cfg)
+        if args.config_path:
+            import runpy
+            runpy.run_path(args.config_path if os.path.isabs(args.config_path) else os.path.join(REPO, args.config_path),
+                           run_name="__abides_config__")
+        else:
+            importlib.import_module("config." + cfg)
     d = os.path.join(work, "log", "golden")
     files = sorted(os.listdir(d))
     nat = np.iinfo(np.int64).min

@@ -172,7 +172,7 @@ def main():
                 fval[a.id] = float(ev["Event"])
             if ev["EventType"] == "ARRIVAL_MID":        # TWAP / VWAP agents: abides_agent_result.final_valuation
                 fval[a.id] = float(ev["Event"])         # carries their arrival mid price (include/abides_b200.h)
-    f_log = oracle.f_log[sym]
+    f_log = oracle.f_log[sym] if oracle is not None else []       # config/marketreplay.py runs without an oracle
     f_t = np.array([x["FundamentalTime"].value for x in f_log], np.int64)
     f_v = np.array([x["FundamentalValue"] for x in f_log], np.float64)
     tr = np.array(trace, dtype=np.int64).reshape(-1, 7)
@@ -181,7 +181,7 @@ def main():
     book = agents[0].order_books[sym]
     meta = dict(config=cfg, ref_args=ref_args, ttl_messages=ttl, delivered=int(len(tr)), means=means,
                 trace_sha256=tr_sha, spec_sha256=spec_sha, n_agents=n,
-                last_trade=int(book.last_trade), final_time=int(kernel.currentTime.value),
+                last_trade=-1 if book.last_trade is None else int(book.last_trade), final_time=int(kernel.currentTime.value),
                 slowest_agent_finish_time=int(max(kernel.agentCurrentTimes).value),
                 numpy=np.__version__, pandas=pd.__version__)
     os.makedirs(args.out, exist_ok=True)

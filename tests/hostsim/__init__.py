@@ -12,7 +12,9 @@ from abides_b200.engine import INSTANCE_RESULT_DTYPE, AGENT_RESULT_DTYPE, TRACE_
 _DIR = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(_DIR))
 CSRC = os.path.join(ROOT, "abides_b200", "csrc")
-LIB_PATH = os.path.join(_DIR, "_build", "liblane_host.so")
+# ABIDES_HOSTSIM_DEFINES="LANE_STAGE=0 LANE_ONE_CTX=1": build options of the lane engine under test (csrc/lane_types.h)
+DEFINES = os.environ.get("ABIDES_HOSTSIM_DEFINES", "").split()
+LIB_PATH = os.path.join(_DIR, "_build", "liblane_host%s.so" % "".join("_" + d.replace("=", "") for d in DEFINES))
 LV_ZI_LEGACY, LV_ZI_CUBIC, LV_RMSC, LV_FULL = range(4)
 _lib = None
 
@@ -24,8 +26,9 @@ def build(force=False):
     deps += [os.path.join(ROOT, "include", h) for h in ("abides_b200.h", "abides_dd_math.h", "abides_math_tables.h")]
     if force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(d) > os.path.getmtime(LIB_PATH) for d in deps):
         os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
-        subprocess.check_call(["g++", "-std=c++17", "-O2", "-g", "-ffp-contract=off", "-fPIC", "-shared",
-                               "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", LIB_PATH, src])
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-g", "-ffp-contract=off", "-fPIC", "-shared"] +
+                              ["-D" + d for d in DEFINES] +
+                              ["-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", LIB_PATH, src])
     return LIB_PATH
 
 

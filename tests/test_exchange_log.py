@@ -21,6 +21,11 @@ RMSC03 = ["-t", "ABM", "-d", "20200603"]
 CASES = {
     "zi100_s123456789": ("sparse_zi_100", ["-s", "123456789"]),
     "rmsc03_s1234_0940": ("rmsc03", RMSC03 + ["-s", "1234", "--end-time", "09:40:00"]),
+    # config/marketreplay.py: exchange log with order dicts incl. MODIFY_ORDER rows, order-book archive through
+    # modifications and an order id that is used twice (reference side: tests/golden/refcfg/marketreplay_flags.py)
+    "marketreplay_s5": ("marketreplay", ["-t", "XYZ", "-d", "20190603", "-s", "5", "--orders-file",
+                                         os.path.join(GOLDEN, "replay_orders_file.csv"),
+                                         "--processed-orders-folder", os.path.join(GOLDEN, "no_such_cache") + os.sep]),
 }
 NAT = np.iinfo(np.int64).min
 TRACE_CAP = 1 << 20
@@ -83,7 +88,7 @@ def test_archives_from_host_traces_reproduce_reference_files(tmp_path, name, sou
     else:
         d = oracle.run_instance(hb, 0, trace_cap=TRACE_CAP, flog_cap=TRACE_CAP)
         n = d["n_trace"]
-        fund = np.zeros((len(d["f_time"]) - 1, 7), np.int64)
+        fund = np.zeros((max(0, len(d["f_time"]) - 1), 7), np.int64)          # no oracle, no series (marketreplay)
         fund[:, 0], fund[:, 1], fund[:, 2], fund[:, 3] = d["f_time"][1:], -1, _abi.TRACE_FUNDAMENTAL, d["f_value"][1:]
         trace = np.concatenate([d["trace"], fund])
         res = np.zeros(1, eng_mod.INSTANCE_RESULT_DTYPE)
@@ -111,6 +116,8 @@ def test_exchange_log_records_leave_the_dispatch_trace_alone():
 @pytest.mark.parametrize("engine", ["warp", "lane"])
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_archives_from_device_traces_reproduce_reference_files(tmp_path, name, engine):
+    if engine == "warp" and name.startswith("marketreplay"):
+        pytest.skip("MarketReplayAgent runs on the lane engine only")
     spec, kernel = build(name)
     out, trace = runtime.run_spec_logged(spec, engine_name=engine)
     runtime.write_back(kernel, out, 0)
@@ -162,3 +169,34 @@ def test_reference_consumers_read_the_archives(tmp_path):
     r = subprocess.run([sys.executable, "-W", "ignore", os.path.join(REFERENCE, "cli", "stats.py"), path], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     assert "Agent Mean" in r.stdout and "Read summary files in 1 log directories." in r.stdout
+
+
+@pytest.mark.parametrize("name", ["rmsc03e_s1234_1100", "rmsc01_s33_1100", "rmsc02fast_s23_1100", "exec_twap_s6"])
+def test_order_book_account_agrees_with_top_of_book_on_other_populations(name):
+    """Market orders (POV / TWAP execution), the polling and the subscribing MarketMakerAgent's ladders, HBL agents: the
+    depth account kept from the exchange's notifications must show the device's own best bid / ask and their volumes
+    after every handleLimitOrder (ExchangeArchive raises otherwise); the traded volume of the LAST_TRADE rows is the
+    run's volume."""
+    from abides_b200 import exchange_log
+    from test_oracle_golden import CASES as GOLDEN_CASES
+    cfg, args = GOLDEN_CASES[name]
+    ((spec, kernel),) = runtime.build_instances(cfg, [list(args) + ["-l", "x"]])
+    hb = lowering.HostBatch([spec], trace_capacity=4 * TRACE_CAP, trace_flags=_abi.TRACE_EXCHANGE_LOG)
+    d = oracle.run_instance(hb, 0, trace_cap=4 * TRACE_CAP)
+    assert d["n_trace"] <= 4 * TRACE_CAP and d["status"] == 0
+    kernel.agents[0].book_freq, kernel.agents[0].wide_book, kernel.agents[0].log_orders = 0, True, True
+    ares = np.zeros(hb.n_agents_total, eng_mod.AGENT_RESULT_DTYPE)
+    ares["cash"], ares["holdings"], ares["marked_to_market"] = d["cash"], d["holdings"], d["mtm"]
+    ares["final_valuation"] = d["final_valuation"]
+    res = np.zeros(1, eng_mod.INSTANCE_RESULT_DTYPE)
+    for f in ("ttl_messages", "last_trade", "slowest_agent_finish_time"):
+        res[f][0] = d[f]
+    runtime.write_back(kernel, runtime.RunOutput(hb, res, ares, 0.0, 1.0), 0)
+    ar = exchange_log.ExchangeArchive(kernel, d["trace"])
+    assert len(ar.book_rows) == int((d["trace"][:, 2] == _abi.TRACE_BOOK_TOP).sum()) > 0
+    traded = sum(int(r[2].split(",")[0]) for r in ar.exchange_rows if r[1] == "LAST_TRADE")
+    assert traded == d["traded_volume"]
+    executed = [r[2] for r in ar.exchange_rows if r[1] == "ORDER_EXECUTED"]
+    assert len(executed) == 2 * d["n_fills"] and sum(e["quantity"] for e in executed) == 2 * d["traded_volume"]
+    bf = ar.book_frame()
+    assert bf.index.is_monotonic_increasing and bf.index.is_unique

@@ -53,7 +53,7 @@ WARP_VARIANT = {"zi100_s123456789": 2, "zi1000_s123456789": 1, "rmsc03_s1234_100
                 "value_noise_s7": 0, "random_fund_value_s7": 3, "random_fund_diverse_s7": 0}
 LANE_VARIANT = {"zi100_s123456789": 17, "zi1000_s123456789": 16, "rmsc03_s1234_1000": 18, "rmsc03e_s1234_1100": 18,
                 "rmsc01s_s77": 18, "rmsc01mm_s33": 19, "exec_twap_s6": 19, "exec_vwap_s5": 19, "execution_s8_e": 19,
-                "value_noise_s7": 19, "random_fund_value_s7": 18, "random_fund_diverse_s7": 19}
+                "value_noise_s7": 19, "random_fund_value_s7": 18, "random_fund_diverse_s7": 19, "marketreplay_s5": 19}
 
 
 @pytest.mark.parametrize("engine", ["warp", "lane"])
@@ -64,6 +64,8 @@ def test_untraced_lean_variant_matches_reference_golden(name, engine):
     portfolio and the last trade must equal what the unmodified reference produced (Kernel.py:204,:318-322)."""
     if engine == "lane" and name not in LANE_VARIANT:
         pytest.skip("population runs on the warp engine only (HBL agents / market-data subscriptions)")
+    if engine == "warp" and name not in WARP_VARIANT:
+        pytest.skip("population runs on the lane engine only (MarketReplayAgent)")
     g, meta = load_golden(name)
     spec = build_case(name)
     hb = lowering.HostBatch([spec, spec, spec])             # a small homogeneous batch

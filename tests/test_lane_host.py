@@ -17,7 +17,7 @@ from test_book_replay import golden as book_golden, check as book_check
 # goldens whose population the lane engine carries (HBL agents and market-data subscriptions stay on the warp engine)
 LANE_CASES = ["zi100_s123456789", "zi1000_s123456789", "rmsc03_s1234_1000", "rmsc03e_s1234_1100", "rmsc01s_s77",
               "rmsc01mm_s33", "exec_twap_s6", "exec_vwap_s5", "execution_s8_e", "value_noise_s7",
-              "random_fund_value_s7", "random_fund_diverse_s7"]
+              "random_fund_value_s7", "random_fund_diverse_s7", "marketreplay_s5"]
 LEAN = {"zi100_s123456789": hostsim.LV_ZI_CUBIC, "zi1000_s123456789": hostsim.LV_ZI_LEGACY,
         "rmsc03_s1234_1000": hostsim.LV_RMSC, "rmsc03e_s1234_1100": hostsim.LV_RMSC, "rmsc01s_s77": hostsim.LV_RMSC,
         "random_fund_value_s7": hostsim.LV_RMSC}

@@ -74,6 +74,9 @@ def test_cli_run_writes_reference_logs(tmp_path):
     assert r.returncode == 0, r.stderr[-2000:]
     assert "Simulation ending!" in r.stdout
     _check_files(os.path.join(str(tmp_path), "log", "run"))
+    # ... and the exchange's log and the 100 agents' logs (tests/test_exchange_log.py)
+    from test_exchange_log import check_directory
+    check_directory(os.path.join(str(tmp_path), "log", "run"), NAME)
 
 
 def _load_parallel():

@@ -54,6 +54,12 @@ CASES = {
                                        "--mm-subscribe-freq", "1e8"]),
     # the reference's config/execution.py itself, full size (5129 agents, TWAP agent trading)
     "execution_s8_e": ("execution", ["-t", "ABM", "-d", "20200603", "-s", "8", "-e"]),
+    # config/marketreplay.py -- the reference's MarketReplayAgent replaying an order file inside a running
+    # simulation (no oracle, zero latency): limit orders, cancels, quantity modifies, crossing orders, an id that is
+    # submitted again after it filled; reference side: tests/golden/refcfg/marketreplay_flags.py
+    "marketreplay_s5": ("marketreplay", ["-t", "XYZ", "-d", "20190603", "-s", "5", "--orders-file",
+                                         os.path.join(GOLDEN, "replay_orders_file.csv"),
+                                         "--processed-orders-folder", os.path.join(GOLDEN, "no_such_cache") + os.sep]),
     "value_noise_s7": ("value_noise", ["-s", "7"]),
     "random_fund_value_s7": ("random_fund_value", ["-s", "7", "-t", "ABM", "-d", "20200603"]),
     "random_fund_diverse_s7": ("random_fund_diverse", ["-s", "7", "-t", "ABM", "-d", "20200603"]),
