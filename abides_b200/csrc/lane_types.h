@@ -61,8 +61,11 @@ namespace lane {
 #endif
 // LANE_STAGE: copy the instance's hot scalars and the recipient's record to thread-local memory around each half of a
 // round (1) or work on them in place (0).  LANE_ONE_CTX: one LCtx per thread, re-pointed per half, instead of two.
+// Measured at the bench size (sparse_zi_1000 x 45 056, profiles/r2_lane_staging_ab.json): staging 579 M msg/s and 3.0 KB of
+// DRAM traffic per message, in place 659 M msg/s and 1.65 KB, in place with one context 620 M msg/s -- the staged copies
+// live in local memory, which no longer fits the L2 at that many resident threads.
 #ifndef LANE_STAGE
-#define LANE_STAGE 1
+#define LANE_STAGE 0
 #endif
 #ifndef LANE_ONE_CTX
 #define LANE_ONE_CTX 0

@@ -222,3 +222,18 @@ def test_lane_event_beyond_the_key_range_is_an_overflow():
     spec.wakeup_time[noise[0]] = spec.cfg["start_time"] + 100 * 3600 * 10 ** 9
     res, ares, _, _, _ = hostsim.run(lowering.HostBatch([spec]))
     assert res["status"][0] == _abi_mod().EOVERFLOW
+
+
+@pytest.mark.parametrize("defines", ["LANE_STAGE=1", "LANE_STAGE=0 LANE_ONE_CTX=1"])
+def test_lane_build_options_do_not_change_results(defines):
+    """The lane engine's build options (csrc/lane_types.h: thread-local staging of the hot state, one context per
+    thread) are performance choices only: the host build of each setting reproduces the reference goldens event for
+    event (a subprocess, because the harness loads one build per process)."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, ABIDES_HOSTSIM_DEFINES=defines)
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-p", "no:cacheprovider", os.path.abspath(__file__), "-k",
+                        "test_lane_logic_matches_reference_golden and (zi100 or rmsc03_s1234 or marketreplay or exec_twap)"],
+                       env=env, capture_output=True, text=True, timeout=1200, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0 and "5 passed" in r.stdout and "failed" not in r.stdout, r.stdout[-1500:] + r.stderr[-500:]
