@@ -8,6 +8,7 @@
 #include <limits.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "lane_kernels.h"
@@ -47,6 +48,12 @@ cudaError_t launch_init(int variant, const LaneBatch& lb, cudaStream_t stream) {
 
 cudaError_t launch_sim(int variant, const LaneBatch& lb, long long until_time, cudaStream_t stream) {
   const int grid = (lb.n_instances + LANE_CTA - 1) / LANE_CTA;
+  // shared memory / L1 split of the SM: the kernel needs 6.5 KB of shared memory per CTA and lives on its L1 hit rate
+  // (thread-local memory); ABIDES_LANE_SMEM_CARVEOUT = preferred shared-memory share in percent (0 = as much L1 as
+  // possible), unset = the driver's default choice
+  static const int carve = [] { const char* e = getenv("ABIDES_LANE_SMEM_CARVEOUT"); return e && *e ? atoi(e) : -1; }();
+  if (carve >= 0 && carve <= 100)
+    LANE_DISPATCH(variant, cudaFuncSetAttribute(lane_sim_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
   LANE_DISPATCH(variant, (lane_sim_kernel<<<grid, LANE_CTA + LANE_HEAVY, 0, stream>>>(lb, until_time)));
   return cudaGetLastError();
 }

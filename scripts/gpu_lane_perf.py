@@ -51,10 +51,11 @@ def main():
         eng.load(hb)
         load_s = time.time() - t1
         eng.run()
-        ms = eng.last_run_ms()[0]
-        eng.reset()
-        eng.run()
-        ms2 = eng.last_run_ms()[0]
+        ms = ms2 = eng.last_run_ms()[0]
+        if os.environ.get("ABIDES_PERF_RUNS", "2") != "1":
+            eng.reset()
+            eng.run()
+            ms2 = eng.last_run_ms()[0]
         res, ares = eng.results_arrays()
         msgs = int(res["ttl_messages"].sum())
         bad = int((res["status"] != 0).sum())
