@@ -16,11 +16,14 @@ Everything here is derived from the device's trace of one instance: the dispatch
 (accepted - executed - cancelled per price), not a second matching engine; the device's top-of-book record cross-checks
 it at every snapshot.
 
-Not reproduced: `book_freq` sampling other than 0 (every update), the long-format
-(`wide_book=False`) archive (the reference itself fails there: pd.SparseDataFrame, ExchangeAgent.py:384), agents with
-`log_orders=True` that place orders, and the logs of agents whose spread queries ask for more than the best level (market makers,
-execution agents that trade): their BID_DEPTH / ASK_DEPTH rows would need levels the trace does not carry -- those
-agents are skipped and reported."""
+The BID_DEPTH / ASK_DEPTH rows of agents that ask for more than the best level (market makers: five levels, execution
+agents: the whole book) come from the same account: the levels it shows when the exchange handles the QUERY_SPREAD are
+what the reply carries; the reply's top of book, which the trace does carry, cross-checks it.
+
+Not reproduced: `book_freq` sampling other than 0 (every update), the long-format (`wide_book=False`) archive (the
+reference itself fails there: pd.SparseDataFrame, ExchangeAgent.py:384), and the logs of agents with `log_orders=True`
+that place orders (their ORDER_SUBMITTED / CANCEL_SUBMITTED rows carry send times the trace does not) -- those agents
+are skipped and reported."""
 import os
 
 import numpy as np
@@ -32,9 +35,6 @@ ORDER_MSGS = (M["LIMIT_ORDER"], M["MARKET_ORDER"], M["CANCEL_ORDER"], M["MODIFY_
 QUERY_MSGS = (M["QUERY_LAST_TRADE"], M["QUERY_SPREAD"], M["QUERY_ORDER_STREAM"], M["QUERY_TRANSACTED_VOLUME"])
 SENT = _abi.TRACE_EXCH_SENT
 NAT = np.iinfo(np.int64).min
-DEEP_QUERY_CLASSES = ("MarketMakerAgent", "AdaptiveMarketMakerAgent", "AdaptivePOVMarketMakerAgent", "ExecutionAgent",
-                      "POVExecutionAgent", "TWAPExecutionAgent", "VWAPExecutionAgent", "SubscriptionAgent",
-                      "HeuristicBeliefLearningAgent")
 
 
 def _iso(ns):
@@ -71,14 +71,7 @@ class ExchangeArchive:
 
     # ---- agents -------------------------------------------------------------------------------------------------
     def _agent_logged(self, a):
-        if not getattr(a, "log_to_file", False) or a.id == 0:
-            return False
-        names = [k.__name__ for k in type(a).__mro__]
-        deep = any(n in DEEP_QUERY_CLASSES for n in names) and getattr(a, "trade", True)
-        if deep:
-            self.skipped_agents.append(a.name)
-            return False
-        return True
+        return bool(getattr(a, "log_to_file", False)) and a.id != 0
 
     def _walk(self, tr):
         k = self.kernel
@@ -95,6 +88,9 @@ class ExchangeArchive:
         depth = {}             # price -> signed resting volume (bids negative, as the archive stores them)
         cur = None             # the order message the exchange is handling: [time_placed, message id, row to patch]
         n_exec = 0             # ORDER_EXECUTED notifications of the current exchange event: aggressor, resting, aggressor, ...
+        spread_replies = {}    # agent -> the (bids, asks, traded) of its QUERY_SPREAD replies still in flight
+        traded = False         # a trade has happened: the book's last_trade is an int (before: the oracle's opening price)
+        open_price_last = {}   # agent -> its known last trade is still that opening price (a float in most configs)
         ex = self.exchange_rows
         for time, agent, code, p0, p1, p2, p3 in tr.tolist():
             if code == _abi.TRACE_FUNDAMENTAL:
@@ -168,6 +164,7 @@ class ExchangeArchive:
                 continue
             if code == _abi.TRACE_LAST_TRADE:
                 ex.append([time, 'LAST_TRADE', "{},${:0.4f}".format(p0, p1)])
+                traded = True
                 continue
             # ---- a dispatched event ----
             base = code & ~_abi.MSG_REPLY
@@ -207,6 +204,10 @@ class ExchangeArchive:
                             cur[2] = len(ex) - 1
                 else:
                     ex.append([time, _abi.MSG_NAMES[base], int(p0)])
+                    if base == M["QUERY_SPREAD"] and p0 in logged:   # getInsideBids / getInsideAsks(depth) right now (:189-204)
+                        bids = sorted(((q, -v) for q, v in depth.items() if v < 0), reverse=True)[:max(0, p1)]
+                        asks = sorted((q, v) for q, v in depth.items() if v > 0)[:max(0, p1)]
+                        spread_replies.setdefault(p0, []).append((bids, asks, traded))
                 continue
             # delivered to a trading agent
             last_time[agent] = time
@@ -222,8 +223,13 @@ class ExchangeArchive:
                     woke.add(agent)
                     r.append((time, 'HOLDINGS_UPDATED', dict(hold[agent])))
             elif base == M["QUERY_SPREAD"]:
-                bids = [(int(p0), int(p1))] if p0 >= 0 else []
-                asks = [(int(p2), int(p3))] if p2 >= 0 else []
+                top = ((int(p0), int(p1)) if p0 >= 0 else None, (int(p2), int(p3)) if p2 >= 0 else None)
+                q = spread_replies.get(agent, [])
+                k = next((i for i, (b, a, _) in enumerate(q) if ((b[0] if b else None), (a[0] if a else None)) == top), None)
+                if k is None:
+                    raise RuntimeError("order-book account disagrees with the QUERY_SPREAD reply to agent %d at %d" % (agent, time))
+                bids, asks, had_trade = q.pop(k)
+                open_price_last[agent] = not had_trade
                 r.append((time, 'BID_DEPTH', bids))
                 r.append((time, 'ASK_DEPTH', asks))
                 r.append((time, 'IMBALANCE', [sum(x[1] for x in bids), sum(x[1] for x in asks)]))
@@ -246,6 +252,10 @@ class ExchangeArchive:
                 if s == 'CASH':
                     continue
                 lt = (a.marked_to_market - h['CASH']) // shares   # one symbol: marked_to_market = CASH + last_trade * shares
+                if open_price_last.get(i) and getattr(self.kernel.oracle, "symbols", None):
+                    # the agent only ever saw the opening price, which the exchange took from the oracle as it is
+                    # configured -- 1e5, a float, in the stock configs (ExchangeAgent.py:84-86, TradingAgent.py:590-601)
+                    lt = type(self.kernel.oracle.symbols[s]['r_bar'])(lt)
                 r.append((t, 'MARK_TO_MARKET', "{} {} @ {} == {}".format(shares, s, lt, lt * shares)))
             r.append((t, 'MARKED_TO_MARKET', a.marked_to_market))
             r.append((t, 'ENDING_CASH', a.marked_to_market))

@@ -247,12 +247,14 @@ def fundamental_frame(kernel, trace):
     return sym, df.set_index('FundamentalTime')
 
 
-def write_logs(kernel, trace=None, root="."):
+def write_logs(kernel, trace=None, root=".", exchange_log=None):
     """Kernel.writeSummaryLog (Kernel.py:523-532) and, when a trace was taken, what the agents archive at
     kernelTerminating: the exchange's fundamental series (ExchangeAgent.py:91-101) and -- when the trace carries the
     exchange-log records (run_spec_logged) -- the exchange's event log, its ORDERBOOK_<symbol>_FULL depth archive and
     the trading agents' logs (abides_b200/exchange_log.py).  bz2-pickled DataFrames under ./log/<log_dir>/ with the
-    reference's file names, columns and dtypes."""
+    reference's file names, columns and dtypes.  `exchange_log`: None = write those archives iff the trace holds
+    exchange-log records, True = the trace was taken with ABIDES_TRACE_EXCHANGE_LOG (a run without a single order
+    has none and still gets its archives), False = never."""
     import pandas as pd
     path = os.path.join(root, "log", kernel.log_dir)
     os.makedirs(path, exist_ok=True)
@@ -261,7 +263,9 @@ def write_logs(kernel, trace=None, root="."):
     if trace is not None and getattr(kernel.oracle, "symbols", None):
         sym, df = fundamental_frame(kernel, trace)
         df.to_pickle(os.path.join(path, "fundamental_{}.bz2".format(sym)), compression='bz2')
-    if trace is not None and len(trace) and (trace[:, 2] == _abi.TRACE_BOOK_TOP).any():
+    if exchange_log is None:
+        exchange_log = trace is not None and len(trace) > 0 and bool((trace[:, 2] >= _abi.TRACE_ORDER_PLACED).any())
+    if exchange_log and trace is not None:
         from abides_b200 import exchange_log
         try:
             kernel.log_archive = exchange_log.write_archives(kernel, trace, path)

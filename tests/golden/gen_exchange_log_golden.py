@@ -52,6 +52,9 @@ def main():
     ap.add_argument("--out", default=os.path.join(REPO, "tests", "golden"))
     ap.add_argument("--config-path", default=None,
                     help="run this config FILE (written against the reference API) instead of config.<name>")
+    ap.add_argument("--no-book-archive", action="store_true",
+                    help="compat shim: skip ExchangeAgent.logOrderBookSnapshots (a long-format archive, wide_book=False, "
+                         "fails in the reference itself under current pandas: pd.SparseDataFrame, ExchangeAgent.py:384)")
     ap.add_argument("ref_args", nargs=argparse.REMAINDER)
     args = ap.parse_args()
     ref_args = [a for a in args.ref_args if a != "--"]
@@ -63,6 +66,9 @@ def main():
     pandas.io.json.json_normalize = pd.json_normalize
     pd.Timedelta.delta = property(lambda self: self.value)     # removed in pandas 2 (ExchangeAgent.py:309)
 
+    if args.no_book_archive:
+        import agent.ExchangeAgent as EA
+        EA.ExchangeAgent.logOrderBookSnapshots = lambda self, symbol: None
     work = tempfile.mkdtemp(prefix="abides_exlog_")
     os.chdir(work)
     sys.argv = ["abides.py"] + ref_args + ["-l", "golden"]
@@ -75,6 +81,9 @@ def main():
         else:
             importlib.import_module("config." + cfg)
     d = os.path.join(work, "log", "golden")
+    if not os.path.isdir(d):                                   # a config without a log-dir flag: the run's only directory
+        (only,) = os.listdir(os.path.join(work, "log"))
+        d = os.path.join(work, "log", only)
     files = sorted(os.listdir(d))
     nat = np.iinfo(np.int64).min
     log_files, log_start, times, types, events = [], [0], [], [], []

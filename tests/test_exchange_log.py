@@ -27,6 +27,12 @@ CASES = {
                                          os.path.join(GOLDEN, "replay_orders_file.csv"),
                                          "--processed-orders-folder", os.path.join(GOLDEN, "no_such_cache") + os.sep]),
 }
+# CPU-only cases (the device runs of the same populations are covered by the parity tests): the literal rmsc01 population
+# -- the MarketMakerAgent's five-level BID_DEPTH / ASK_DEPTH rows, HBL, ZI and momentum agents' logs, exchange log without
+# order dicts; reference side: tests/golden/refcfg/rmsc01_flags.py with the long-format book archive skipped
+HOST_ONLY_CASES = {
+    "rmsc01_s33_0935": ("rmsc01", ["-s", "33", "--end-time", "09:35:00"]),
+}
 NAT = np.iinfo(np.int64).min
 TRACE_CAP = 1 << 20
 
@@ -66,7 +72,7 @@ def check_directory(path, name):
 
 
 def build(name):
-    cfg, args = CASES[name]
+    cfg, args = (CASES.get(name) or HOST_ONLY_CASES[name])
     ((spec, kernel),) = runtime.build_instances(cfg, [list(args) + ["-l", "x"]])
     return spec, kernel
 
@@ -79,8 +85,10 @@ def finish(kernel, hb, res, ares, trace, tmp_path, name):
 
 
 @pytest.mark.parametrize("source", ["oracle", "lane"])
-@pytest.mark.parametrize("name", sorted(CASES))
+@pytest.mark.parametrize("name", sorted(CASES) + sorted(HOST_ONLY_CASES))
 def test_archives_from_host_traces_reproduce_reference_files(tmp_path, name, source):
+    if source == "lane" and name.startswith("rmsc01_"):
+        pytest.skip("HBL agents run on the warp engine only")
     spec, kernel = build(name)
     hb = lowering.HostBatch([spec], trace_capacity=TRACE_CAP, trace_flags=_abi.TRACE_EXCHANGE_LOG)
     if source == "lane":
