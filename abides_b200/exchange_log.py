@@ -25,6 +25,7 @@ reference itself fails there: pd.SparseDataFrame, ExchangeAgent.py:384), and the
 that place orders (their ORDER_SUBMITTED / CANCEL_SUBMITTED rows carry send times the trace does not) -- those agents
 are skipped and reported."""
 import os
+from array import array
 
 import numpy as np
 
@@ -63,7 +64,9 @@ class ExchangeArchive:
         self.log_orders = bool(self.exch.log_orders)
         self.snapshots = self.exch.book_freq is not None
         self.exchange_rows = [(NAT, 'AGENT_TYPE', self.exch.type)]
-        self.book_rows = []                     # (time, {quote: signed volume})
+        # book snapshots as compact columns: one time per snapshot, its non-zero cells as (snapshot, quote, signed volume)
+        self.book_times = array('q')
+        self.book_cells = (array('l'), array('q'), array('q'))
         self.quotes_seen = set()
         self.agent_rows = {}
         self.skipped_agents = []
@@ -74,9 +77,8 @@ class ExchangeArchive:
         return bool(getattr(a, "log_to_file", False)) and a.id != 0
 
     def _walk(self, tr):
-        k = self.kernel
         sym = self.symbol
-        logged = {a.id: a for a in k.agents if self._agent_logged(a)}
+        logged = {a.id: a for a in self.kernel.agents if self._agent_logged(a)}
         rows = {i: [(NAT, 'AGENT_TYPE', a.type), (NAT, 'STARTING_CASH', a.starting_cash)] for i, a in logged.items()}
         hold = {i: {'CASH': a.starting_cash} for i, a in logged.items()}
         woke, last_time = set(), {}
@@ -160,7 +162,12 @@ class ExchangeArchive:
                     if (best_bid, best_ask) != (p0, p2) or (bids and -depth[best_bid] != p1) or (asks and depth[best_ask] != p3):
                         raise RuntimeError("order-book account disagrees with the device's top of book at %d" % time)
                     self.quotes_seen.update(depth)
-                    self.book_rows.append((time, dict(depth)))
+                    row = len(self.book_times)
+                    self.book_times.append(time)
+                    for q, v in depth.items():
+                        self.book_cells[0].append(row)
+                        self.book_cells[1].append(q)
+                        self.book_cells[2].append(v)
                 continue
             if code == _abi.TRACE_LAST_TRADE:
                 ex.append([time, 'LAST_TRADE', "{},${:0.4f}".format(p0, p1)])
@@ -270,24 +277,31 @@ class ExchangeArchive:
     def agent_frames(self):
         return {name: _event_frame(r) for name, r in self.agent_rows.items()}
 
+    @property
+    def n_snapshots(self):
+        return len(self.book_times)
+
     def book_frame(self):
-        """OrderBook.book_log_to_df + ExchangeAgent.logOrderBookSnapshots, book_freq == 0, wide_book."""
+        """OrderBook.book_log_to_df + ExchangeAgent.logOrderBookSnapshots for book_freq == 0, wide_book: a sparse frame
+        snapshot times x every quote seen, of several snapshots in one nanosecond the last, times ascending."""
         import pandas as pd
-        from scipy.sparse import dok_matrix
-        if not self.book_rows:
+        from scipy.sparse import coo_matrix
+        if not len(self.book_times):
             return None
-        quotes = sorted(self.quotes_seen)
-        col = {q: j for j, q in enumerate(quotes)}
-        S = dok_matrix((len(self.book_rows), len(quotes)), dtype=int)
-        for i, (_, row) in enumerate(self.book_rows):
-            for q, v in row.items():
-                S[i, col[q]] = v
-        df = pd.DataFrame.sparse.from_spmatrix(S.tocsc(), columns=quotes)
-        df.insert(0, 'QuoteTime', pd.to_datetime(np.array([t for t, _ in self.book_rows], np.int64)), allow_duplicates=True)
-        df.set_index('QuoteTime', inplace=True)
-        df = df[~df.index.duplicated(keep='last')]
-        df.sort_index(inplace=True)
-        return df.reindex(sorted(df.columns), axis=1)
+        t = np.frombuffer(self.book_times, np.int64)
+        keep = np.ones(len(t), bool)
+        keep[:-1] = t[1:] != t[:-1]                     # snapshots are taken in time order: duplicates are adjacent
+        new_row = np.cumsum(keep) - 1
+        r = np.frombuffer(self.book_cells[0], np.int64) if len(self.book_cells[0]) else np.zeros(0, np.int64)
+        q = np.frombuffer(self.book_cells[1], np.int64) if len(self.book_cells[1]) else np.zeros(0, np.int64)
+        v = np.frombuffer(self.book_cells[2], np.int64) if len(self.book_cells[2]) else np.zeros(0, np.int64)
+        quotes = np.array(sorted(self.quotes_seen), np.int64)
+        sel = keep[r]
+        S = coo_matrix((v[sel], (new_row[r[sel]], np.searchsorted(quotes, q[sel]))), shape=(int(keep.sum()), len(quotes)),
+                       dtype=np.int64).tocsc()
+        df = pd.DataFrame.sparse.from_spmatrix(S, columns=[int(x) for x in quotes])
+        df.index = pd.DatetimeIndex(pd.to_datetime(t[keep]), name='QuoteTime')
+        return df
 
 
 def _summary_tail(a):

@@ -46,6 +46,24 @@ def canon(x):
     return repr(x)
 
 
+def digest(log_time, log_type, log_event, book=None):
+    """SHA-256 of one event log (times, types, canonical events) and of the order-book archive's cells: what a hash-only
+    fixture (exlog_hashes.json) keeps of a run whose archives are too big to commit."""
+    import hashlib
+    import numpy as np
+    h = hashlib.sha256()
+    h.update(np.ascontiguousarray(log_time, np.int64).tobytes())
+    h.update("\n".join(str(x) for x in log_type).encode())
+    h.update("\n".join(str(x) for x in log_event).encode())
+    out = {"rows": int(len(log_time)), "sha256": h.hexdigest()}
+    if book is not None:
+        hb = hashlib.sha256()
+        for k in ("book_time", "book_quotes", "book_row", "book_col", "book_val"):
+            hb.update(np.ascontiguousarray(book[k], np.int64).tobytes())
+        out.update(book_shape=[int(len(book["book_time"])), int(len(book["book_quotes"]))], book_sha256=hb.hexdigest())
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--name", required=True)
@@ -55,6 +73,8 @@ def main():
     ap.add_argument("--no-book-archive", action="store_true",
                     help="compat shim: skip ExchangeAgent.logOrderBookSnapshots (a long-format archive, wide_book=False, "
                          "fails in the reference itself under current pandas: pd.SparseDataFrame, ExchangeAgent.py:384)")
+    ap.add_argument("--hash-only", default=None, metavar="LOG_FILE",
+                    help="keep only the digest of this log file (and of the order-book archive) in exlog_hashes.json")
     ap.add_argument("ref_args", nargs=argparse.REMAINDER)
     args = ap.parse_args()
     ref_args = [a for a in args.ref_args if a != "--"]
@@ -109,6 +129,17 @@ def main():
         types += list(df.EventType)
         events += [canon(x) for x in df.Event]
         log_start.append(log_start[-1] + len(df))
+    if args.hash_only:
+        import json
+        k = log_files.index(args.hash_only)
+        lo, hi = log_start[k], log_start[k + 1]
+        path = os.path.join(args.out, "exlog_hashes.json")
+        table = json.load(open(path)) if os.path.exists(path) else {}
+        table[args.name] = dict(digest(np.concatenate(times)[lo:hi], types[lo:hi], events[lo:hi], book or None),
+                                log_file=args.hash_only, files=files, ref_args=ref_args)
+        json.dump(table, open(path, "w"), indent=1, sort_keys=True)
+        print(args.name, "->", path, table[args.name]["rows"], "rows")
+        return
     np.savez_compressed(
         os.path.join(args.out, args.name + ".exlog.npz"), files=np.array(files, dtype=str),
         log_files=np.array(log_files, dtype=str), log_start=np.array(log_start, np.int64),

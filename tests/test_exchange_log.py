@@ -201,10 +201,50 @@ def test_order_book_account_agrees_with_top_of_book_on_other_populations(name):
         res[f][0] = d[f]
     runtime.write_back(kernel, runtime.RunOutput(hb, res, ares, 0.0, 1.0), 0)
     ar = exchange_log.ExchangeArchive(kernel, d["trace"])
-    assert len(ar.book_rows) == int((d["trace"][:, 2] == _abi.TRACE_BOOK_TOP).sum()) > 0
+    assert ar.n_snapshots == int((d["trace"][:, 2] == _abi.TRACE_BOOK_TOP).sum()) > 0
     traded = sum(int(r[2].split(",")[0]) for r in ar.exchange_rows if r[1] == "LAST_TRADE")
     assert traded == d["traded_volume"]
     executed = [r[2] for r in ar.exchange_rows if r[1] == "ORDER_EXECUTED"]
     assert len(executed) == 2 * d["n_fills"] and sum(e["quantity"] for e in executed) == 2 * d["traded_volume"]
     bf = ar.book_frame()
     assert bf.index.is_monotonic_increasing and bf.index.is_unique
+
+
+def test_exchange_log_and_book_archive_of_the_execution_config_match_reference_hashes():
+    """config/execution.py `-e` at 1/10 scale (TWAP agent: limit orders every minute, a MARKET order at the end; adaptive
+    market makers, momentum, value and noise agents), whole 09:30-11:30 session: the exchange's 381 019 log rows --
+    MARKET_ORDER rows and the notifications of their child limit orders included -- and the 30 214 x 1 322 order-book
+    archive hash to what the reference wrote (tests/golden/exlog_hashes.json, gen_exchange_log_golden.py --hash-only).
+    Every trading agent of that config logs its own orders, so no agent log is written."""
+    import json
+    from abides_b200 import exchange_log
+    from gen_exchange_log_golden import digest
+    from test_oracle_golden import CASES as GOLDEN_CASES
+    want = json.load(open(os.path.join(GOLDEN, "exlog_hashes.json")))["exec_twap_s6"]
+    cfg, args = GOLDEN_CASES["exec_twap_s6"]
+    ((spec, kernel),) = runtime.build_instances(cfg, [list(args) + ["-l", "x"]])
+    cap = 8 * TRACE_CAP
+    hb = lowering.HostBatch([spec], trace_capacity=cap, trace_flags=_abi.TRACE_EXCHANGE_LOG)
+    d = oracle.run_instance(hb, 0, trace_cap=cap)
+    assert d["n_trace"] <= cap
+    ares = np.zeros(hb.n_agents_total, eng_mod.AGENT_RESULT_DTYPE)
+    ares["cash"], ares["holdings"], ares["marked_to_market"] = d["cash"], d["holdings"], d["mtm"]
+    ares["final_valuation"] = d["final_valuation"]
+    res = np.zeros(1, eng_mod.INSTANCE_RESULT_DTYPE)
+    for f in ("ttl_messages", "last_trade", "slowest_agent_finish_time"):
+        res[f][0] = d[f]
+    runtime.write_back(kernel, runtime.RunOutput(hb, res, ares, 0.0, 1.0), 0)
+    ar = exchange_log.ExchangeArchive(kernel, d["trace"])
+    df = ar.exchange_frame()
+    t = df.index.to_numpy("datetime64[ns]")
+    ti = t.astype(np.int64)
+    ti[np.isnat(t)] = NAT
+    b = ar.book_frame()
+    dense = b.sparse.to_coo().tocsr()
+    dense.sort_indices()
+    r, c = dense.nonzero()
+    book = dict(book_time=b.index.to_numpy("datetime64[ns]").astype(np.int64), book_quotes=[int(q) for q in b.columns],
+                book_row=r, book_col=c, book_val=np.asarray(dense[r, c]).ravel())
+    got = digest(ti, list(df.EventType), [canon(x) for x in df.Event], book)
+    assert got == {k: want[k] for k in got}
+    assert not ar.agent_rows and len(ar.skipped_agents) == 13
