@@ -277,12 +277,13 @@ def write_logs(kernel, trace=None, root=".", exchange_log=None):
 
 def run_spec_logged(spec, device=0, engine_name=None, trace_flags=_abi.TRACE_EXCHANGE_LOG):
     """One instance with its full device trace: a first run sizes the trace (every dispatched event plus at most
-    one oracle step per event; with the exchange-log records at most five per order -- placed, accepted, cancelled,
-    book top, last trade -- and two per fill), the second records it."""
+    one oracle step per event, plus the exchange-log records), the second records it."""
     out = run_specs([spec], device=device, engine_name=engine_name)
     cap = 2 * int(out.res["delivered"][0]) + 2 * spec.n_agents + 64
     if trace_flags & _abi.TRACE_EXCHANGE_LOG:
-        cap += 5 * int(out.res["n_orders"][0]) + 2 * int(out.res["n_fills"][0])
+        # every exchange-log record belongs to a dispatched event: a placed order or a modification to the message the
+        # exchange receives, a notification to its delivery, top of book / last trade to the order message handled
+        cap += 3 * int(out.res["delivered"][0]) + 5 * int(out.res["n_orders"][0]) + 2 * int(out.res["n_fills"][0])
     out = run_specs([spec], device=device, trace_capacity=cap, engine_name=engine_name, trace_flags=trace_flags)
     tr, n = engine(device).trace(0)
     if n > cap:
