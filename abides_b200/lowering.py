@@ -339,29 +339,29 @@ def lower_instance(agents, startTime, stopTime, defaultComputationDelay=1, defau
             lat_from[:] = np.asarray(agentLatency[0], dtype=np.float64)
             lat_to[:] = np.asarray([agentLatency[i][0] for i in range(n)], dtype=np.float64)
 
-    # oracle (util/oracle/SparseMeanRevertingOracle.py); none at all for a pure replay (config/marketreplay.py:138)
-    if oracle is None and all(agent_class(a) == _abi.MARKET_REPLAY for a in agents[1:]):
-        return _finish_without_oracle(spec, cfg, ex, startTime, stopTime, defaultComputationDelay, seed, types, agent_type,
-                                      lat_to, lat_from, size, wake, agent_theta, theta, mt_key, mt_pos, mt_hg, mt_g,
-                                      kernel_random_state, lat_rs, global_state, n)
-    if oracle is None or type(oracle).__name__ != "SparseMeanRevertingOracle":
-        raise NotImplementedError("oracle must be a SparseMeanRevertingOracle")
-    if list(oracle.symbols) != [symbol]:
-        raise NotImplementedError("oracle symbols must match the exchange's single symbol")
-    s = oracle.symbols[symbol]
-    ms = oracle.megashocks[symbol][-1]
-    if len(oracle.megashocks[symbol]) != 1 or _ns(oracle.r[symbol][0]) != _ns(oracle.mkt_open):
-        raise ValueError("oracle has already been advanced")
-    cfg.update(r_bar=float(s["r_bar"]), kappa=float(s["kappa"]), fund_vol=float(s["fund_vol"]),
-               megashock_lambda_a=float(s["megashock_lambda_a"]),
-               megashock_mean=float(s["megashock_mean"]), megashock_var=float(s["megashock_var"]),
-               megashock_time0=_ns(ms["MegashockTime"]), megashock_value0=float(ms["MegashockValue"]))
-    if _ns(oracle.mkt_open) != _ns(ex.mkt_open) or _ns(oracle.mkt_close) != _ns(ex.mkt_close):
-        raise NotImplementedError("oracle and exchange market hours differ")
-
+    # oracle (util/oracle/SparseMeanRevertingOracle.py); none at all for a pure replay (config/marketreplay.py:138):
+    # the exchange then opens without a price (ExchangeAgent.py:84-88)
     e = _abi.EXTRA_STREAMS
-    mt_key[n + _abi.STREAM_ORACLE], mt_pos[n + _abi.STREAM_ORACLE], mt_hg[n + _abi.STREAM_ORACLE], \
-        mt_g[n + _abi.STREAM_ORACLE] = _mt_state(s["random_state"])
+    if oracle is None and all(agent_class(a) == _abi.MARKET_REPLAY for a in agents[1:]):
+        cfg.update(r_bar=0.0, kappa=0.0, fund_vol=0.0, megashock_lambda_a=1.0, megashock_mean=0.0, megashock_var=0.0,
+                   megashock_time0=2 ** 62, megashock_value0=0.0, flags=_abi.INST_NO_ORACLE)
+    else:
+        if oracle is None or type(oracle).__name__ != "SparseMeanRevertingOracle":
+            raise NotImplementedError("oracle must be a SparseMeanRevertingOracle")
+        if list(oracle.symbols) != [symbol]:
+            raise NotImplementedError("oracle symbols must match the exchange's single symbol")
+        s = oracle.symbols[symbol]
+        ms = oracle.megashocks[symbol][-1]
+        if len(oracle.megashocks[symbol]) != 1 or _ns(oracle.r[symbol][0]) != _ns(oracle.mkt_open):
+            raise ValueError("oracle has already been advanced")
+        cfg.update(r_bar=float(s["r_bar"]), kappa=float(s["kappa"]), fund_vol=float(s["fund_vol"]),
+                   megashock_lambda_a=float(s["megashock_lambda_a"]),
+                   megashock_mean=float(s["megashock_mean"]), megashock_var=float(s["megashock_var"]),
+                   megashock_time0=_ns(ms["MegashockTime"]), megashock_value0=float(ms["MegashockValue"]))
+        if _ns(oracle.mkt_open) != _ns(ex.mkt_open) or _ns(oracle.mkt_close) != _ns(ex.mkt_close):
+            raise NotImplementedError("oracle and exchange market hours differ")
+        mt_key[n + _abi.STREAM_ORACLE], mt_pos[n + _abi.STREAM_ORACLE], mt_hg[n + _abi.STREAM_ORACLE], \
+            mt_g[n + _abi.STREAM_ORACLE] = _mt_state(s["random_state"])
     if kernel_random_state is not None:
         mt_key[n + 1], mt_pos[n + 1], mt_hg[n + 1], mt_g[n + 1] = _mt_state(kernel_random_state)
     if lat_rs is not None:
@@ -371,33 +371,6 @@ def lower_instance(agents, startTime, stopTime, defaultComputationDelay=1, defau
     mt_key[n + 3], mt_pos[n + 3], mt_hg[n + 3], mt_g[n + 3] = _mt_state(global_state)
     assert e == 4
 
-    cfg.update(start_time=_ns(startTime), stop_time=_ns(stopTime), mkt_open=_ns(ex.mkt_open),
-               mkt_close=_ns(ex.mkt_close), default_computation_delay=int(defaultComputationDelay),
-               exch_pipeline_delay=int(ex.pipeline_delay), exch_computation_delay=int(ex.computation_delay),
-               stream_history=int(ex.stream_history), exch_log_orders=1 if ex.log_orders else 0,
-               seed=int(seed) & 0xFFFFFFFFFFFFFFFF)
-    spec.types = types
-    spec.agent_type = agent_type
-    spec.lat_to, spec.lat_from = lat_to, lat_from
-    spec.size, spec.wakeup_time = size, wake
-    spec.agent_theta = agent_theta
-    spec.theta = np.asarray(theta, np.int32)
-    spec.mt_key, spec.mt_pos, spec.mt_has_gauss, spec.mt_gauss = mt_key, mt_pos, mt_hg, mt_g
-    return spec
-
-
-def _finish_without_oracle(spec, cfg, ex, startTime, stopTime, defaultComputationDelay, seed, types, agent_type, lat_to,
-                           lat_from, size, wake, agent_theta, theta, mt_key, mt_pos, mt_hg, mt_g, kernel_random_state,
-                           lat_rs, global_state, n):
-    """Kernel.runner(oracle=None): the exchange opens without a price (ExchangeAgent.py:84-88)."""
-    cfg.update(r_bar=0.0, kappa=0.0, fund_vol=0.0, megashock_lambda_a=1.0, megashock_mean=0.0, megashock_var=0.0,
-               megashock_time0=2 ** 62, megashock_value0=0.0, flags=_abi.INST_NO_ORACLE)
-    if kernel_random_state is not None:
-        mt_key[n + 1], mt_pos[n + 1], mt_hg[n + 1], mt_g[n + 1] = _mt_state(kernel_random_state)
-    if lat_rs is not None:
-        mt_key[n + 2], mt_pos[n + 2], mt_hg[n + 2], mt_g[n + 2] = _mt_state(lat_rs)
-    mt_key[n + 3], mt_pos[n + 3], mt_hg[n + 3], mt_g[n + 3] = _mt_state(
-        global_state if global_state is not None else np.random.get_state())
     cfg.update(start_time=_ns(startTime), stop_time=_ns(stopTime), mkt_open=_ns(ex.mkt_open),
                mkt_close=_ns(ex.mkt_close), default_computation_delay=int(defaultComputationDelay),
                exch_pipeline_delay=int(ex.pipeline_delay), exch_computation_delay=int(ex.computation_delay),
