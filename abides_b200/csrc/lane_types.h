@@ -126,7 +126,7 @@ struct LN_ALIGN(128) LAgent {           // 128 bytes = four 32-byte sectors; sec
 };
 static_assert(sizeof(LAgent) == 128, "LAgent must be 128 bytes");
 
-struct LN_ALIGN(16) LHot {              // per-instance scalars, in HBM; staged in thread-local memory while a half runs
+struct LN_ALIGN(16) LHot {              // per-instance scalars, in HBM; worked on in place (LANE_STAGE=1: staged in thread-local memory while a half runs)
   // first 64 bytes: everything the pop half reads or writes (loaded / stored as four 16-byte vectors)
   long long now, ttl, delivered, exch_busy;
   int hn;                               // events in the heap
