@@ -51,7 +51,7 @@ class Kernel:
         else:
             out, trace = runtime.run_spec_logged(spec)
         runtime.write_back(self, out, 0)
-        runtime.write_logs(self, trace, exchange_log=trace is not None)
+        runtime.write_logs(self, trace, exchange_log=trace is not None, spec=spec)
         runtime.report(self, out, 0)
         return self.custom_state
 

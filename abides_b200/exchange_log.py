@@ -20,10 +20,13 @@ The BID_DEPTH / ASK_DEPTH rows of agents that ask for more than the best level (
 agents: the whole book) come from the same account: the levels it shows when the exchange handles the QUERY_SPREAD are
 what the reply carries; the reply's top of book, which the trace does carry, cross-checks it.
 
+Agents with `log_orders=True` also log what they send: ORDER_SUBMITTED from the placement records, CANCEL_SUBMITTED at the
+send time of each cancellation, which under the deterministic latency model is the exchange's receive time minus the
+computation delay and the agent's latency (needs the lowered instance, `spec`).
+
 Not reproduced: `book_freq` sampling other than 0 (every update), the long-format (`wide_book=False`) archive (the
 reference itself fails there: pd.SparseDataFrame, ExchangeAgent.py:384), and the logs of agents with `log_orders=True`
-that place orders (their ORDER_SUBMITTED / CANCEL_SUBMITTED rows carry send times the trace does not) -- those agents
-are skipped and reported."""
+that place orders under a random latency model or without `spec` -- those agents are skipped and reported."""
 import os
 from array import array
 
@@ -56,8 +59,12 @@ def _order_dict(agent, placed_ns, symbol, qty, is_buy, oid, fill, limit):
 class ExchangeArchive:
     """Walks one instance's trace once; afterwards `exchange_rows`, `book_rows` and `agent_rows` hold the archives."""
 
-    def __init__(self, kernel, trace):
+    def __init__(self, kernel, trace, spec=None):
         self.kernel = kernel
+        # agents with log_orders=True also log what they SEND; a cancellation's send time is not in the trace, but under
+        # the deterministic latency model it is the exchange's receive time minus computation delay and latency -- which
+        # needs the lowered instance (`spec`: lat_to, default_computation_delay)
+        self.spec = spec if spec is not None and spec.cfg.get("latency_kind") == _abi.LAT_DETERMINISTIC else None
         self.exch = kernel.agents[0]
         self.symbol = next(iter(self.exch.order_books))
         self.mkt_close = _ns(self.exch.mkt_close)
@@ -79,7 +86,13 @@ class ExchangeArchive:
     def _walk(self, tr):
         sym = self.symbol
         logged = {a.id: a for a in self.kernel.agents if self._agent_logged(a)}
-        rows = {i: [(NAT, 'AGENT_TYPE', a.type), (NAT, 'STARTING_CASH', a.starting_cash)] for i, a in logged.items()}
+        own_orders = {i for i, a in logged.items() if getattr(a, "log_orders", False)}     # these log what they send, too
+        # an agent's rows, one block per dispatched event: [time, trace index, rows logged on arrival, CANCEL_SUBMITTED
+        # rows, ORDER_SUBMITTED rows] -- every supported strategy cancels before it places inside one handler
+        blocks = {i: [[NAT, -1, [(NAT, 'AGENT_TYPE', a.type), (NAT, 'STARTING_CASH', a.starting_cash)], [], []]]
+                  for i, a in logged.items()}
+        copy_hist = {}         # id of an agent's own copy -> [(trace index, quantity shown from then on), ...]
+        sent_tp = {}           # order id in a notification -> time_placed it carries
         hold = {i: {'CASH': a.starting_cash} for i, a in logged.items()}
         woke, last_time = set(), {}
         placed = {}            # order id in the agent's message -> (time_placed, agent, price, signed qty, is_market)
@@ -94,7 +107,7 @@ class ExchangeArchive:
         traded = False         # a trade has happened: the book's last_trade is an int (before: the oracle's opening price)
         open_price_last = {}   # agent -> its known last trade is still that opening price (a float in most configs)
         ex = self.exchange_rows
-        for time, agent, code, p0, p1, p2, p3 in tr.tolist():
+        for ti, (time, agent, code, p0, p1, p2, p3) in enumerate(tr.tolist()):
             if code == _abi.TRACE_FUNDAMENTAL:
                 continue
             if code == _abi.TRACE_ORDER_PLACED:
@@ -102,10 +115,15 @@ class ExchangeArchive:
                     modified_at[p0] = time
                     continue
                 placed[p0] = (time, agent, p1, p2, p3)
-                if agent in logged and getattr(logged[agent], "log_orders", False):
-                    self.skipped_agents.append(logged.pop(agent).name)     # ORDER_SUBMITTED / CANCEL_SUBMITTED rows: not derivable
                 # the agent keeps a deepcopy; the copy of order id 0 takes a fresh id (Order.py:29): the next one
                 copy_qty[p0 if p0 != 0 else 1] = [abs(p2), p0]
+                copy_hist[p0 if p0 != 0 else 1] = [(ti, abs(p2))]
+                if agent in own_orders and agent in logged:
+                    if self.spec is None:                      # CANCEL_SUBMITTED times would be guesses: no log at all
+                        self.skipped_agents.append(logged.pop(agent).name)
+                    else:                                      # ORDER_SUBMITTED: order.to_dict(), whose copy of id 0 is id 2
+                        blocks[agent][-1][4].append((time, 'ORDER_SUBMITTED', _order_dict(
+                            agent, time, sym, abs(p2), p2 > 0, p0 if p0 != 0 else 2, None, None if p3 == 1 else p1)))
                 continue
             if code >= SENT:
                 msg = code - SENT
@@ -114,6 +132,7 @@ class ExchangeArchive:
                     r[2]['order_id'] = p0 - 1
                     cur[2] = None
                 tp = book_time.get(p0, cur[0] if cur is not None else time)
+                sent_tp[p0] = tp
                 if self.log_orders and msg != M["ORDER_MODIFIED"]:   # ORDER_MODIFIED is sent but not logged (ExchangeAgent.py:404-411)
                     ex.append([time, _abi.MSG_NAMES[msg], _order_dict(agent, tp, sym, abs(p2), p2 > 0, p0, p3, p1)])
                 # the depth account: price levels as the FIFO lists the book keeps (OrderBook.py:272-298)
@@ -180,6 +199,15 @@ class ExchangeArchive:
                 n_exec = 0
                 if code == 0:
                     continue
+                if base == M["CANCEL_ORDER"] and p0 in own_orders and p0 in logged and p1 in copy_qty:
+                    # CANCEL_SUBMITTED (TradingAgent.py:366-374): logged by the handler that sent this message, whenever
+                    # the exchange gets it (also after the close)
+                    sent = time - int(self.spec.cfg["default_computation_delay"]) - int(self.spec.lat_to[p0])
+                    blk = next((b for b in reversed(blocks[p0]) if b[0] == sent), None)
+                    if blk is None:
+                        raise RuntimeError("no handler of agent %d at %d sent the CANCEL_ORDER received at %d" % (p0, sent, time))
+                    q = [v for i, v in copy_hist[p1] if i <= blk[1]][-1]
+                    blk[3].append((sent, 'CANCEL_SUBMITTED', _order_dict(p0, placed[copy_qty[p1][1]][0], sym, q, p3 > 0, p1, None, p2)))
                 closed = time > self.mkt_close
                 if closed and base not in QUERY_MSGS:
                     continue                                       # answered MKT_CLOSED before any logging (:126-144)
@@ -222,9 +250,13 @@ class ExchangeArchive:
                 c = copy_qty.get(p0)
                 if c is not None and abs(p2) < c[0]:               # orderExecuted (:416-421): a full fill only drops the copy
                     c[0] -= abs(p2)
+                    copy_hist[p0].append((ti, c[0]))
             if agent not in logged:
                 continue
-            r = rows[agent]
+            blocks[agent].append([time, ti, [], [], []])
+            r = blocks[agent][-1][2]
+            if agent in own_orders and base in (M["ORDER_EXECUTED"], M["ORDER_ACCEPTED"], M["ORDER_CANCELLED"]):
+                r.append((time, _abi.MSG_NAMES[base], _order_dict(agent, sent_tp.get(p0, time), sym, abs(p2), p2 > 0, p0, p3, p1)))
             if code == 0:
                 if agent not in woke:
                     woke.add(agent)
@@ -249,6 +281,7 @@ class ExchangeArchive:
                 r.append((time, 'HOLDINGS_UPDATED', dict(h)))
             elif base == M["MKT_CLOSED"]:
                 r.append((time, 'MKT_CLOSED', ''))
+        rows = {i: [row for b in blocks[i] for part in b[2:] for row in part] for i in logged}
         for i, a in logged.items():                                # kernelStopping (TradingAgent.py:122-133, subclasses)
             t = last_time.get(i, NAT)
             r = rows[i]
@@ -266,7 +299,7 @@ class ExchangeArchive:
                 r.append((t, 'MARK_TO_MARKET', "{} {} @ {} == {}".format(shares, s, lt, lt * shares)))
             r.append((t, 'MARKED_TO_MARKET', a.marked_to_market))
             r.append((t, 'ENDING_CASH', a.marked_to_market))
-            for row in _summary_tail(a):
+            for row in summary_tail(a):
                 r.append((t,) + row)
         self.agent_rows = {logged[i].name: r for i, r in rows.items() if i in logged}
 
@@ -304,12 +337,21 @@ class ExchangeArchive:
         return df
 
 
-def _summary_tail(a):
-    """The rows an agent appends after ENDING_CASH (the same values runtime.summary_log_rows reports)."""
+def summary_tail(a):
+    """The (type, value) rows an agent logs after ENDING_CASH, all of them also summary-log rows: FINAL_VALUATION
+    (ZeroIntelligenceAgent.py:93, ValueAgent.py:75, NoiseAgent.py:68) and a trading ExecutionAgent's report
+    (agent/execution/ExecutionAgent.py:32-42).  Needs runtime.write_back() to have run."""
     out = []
     if a.final_valuation is not None:
+        # ZI / HBL report an integer surplus, Value / Noise agents a ratio to the starting cash
         zi = any(k.__name__ == "ZeroIntelligenceAgent" for k in type(a).__mro__)
         out.append(('FINAL_VALUATION', int(a.final_valuation) if zi else a.final_valuation))
+    if hasattr(a, "execution_time_horizon") and a.trade:
+        avg, mid = a.average_transaction_price, a.arrival_price
+        if avg is None or mid is None:
+            raise RuntimeError("the reference raises in ExecutionAgent.kernelStopping: no fill or no arrival price")
+        out += [('DIRECTION', a.direction), ('TOTAL_QTY', a.quantity), ('REM_QTY', a.rem_quantity), ('ARRIVAL_MID', mid),
+                ('AVG_TXN_PRICE', avg), ('SLIPPAGE', avg - mid if a.direction == 'BUY' else mid - avg)]
     return out
 
 
@@ -326,10 +368,10 @@ def _ns(t):
     return int(pd.Timestamp(t).value)
 
 
-def write_archives(kernel, trace, path):
+def write_archives(kernel, trace, path, spec=None):
     """Write the exchange's log, the order-book archive and the agents' logs under `path` with the reference's file
     names (Kernel.writeLog: the agent's name without blanks).  Returns the ExchangeArchive."""
-    ar = ExchangeArchive(kernel, trace)
+    ar = ExchangeArchive(kernel, trace, spec)
     os.makedirs(path, exist_ok=True)
 
     def put(df, name):

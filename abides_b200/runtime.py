@@ -207,6 +207,7 @@ def summary_log_rows(kernel):
     every TradingAgent.kernelStarting (TradingAgent.py:108), then per agent FINAL_CASH_POSITION / ENDING_CASH
     (TradingAgent.py:127-132) and, for the classes that report it, FINAL_VALUATION (ZeroIntelligenceAgent.py:93,
     ValueAgent.py:75, NoiseAgent.py:68).  Needs write_back() to have run."""
+    from abides_b200 import exchange_log
     rows = []
 
     def row(a, ev, val):
@@ -217,20 +218,8 @@ def summary_log_rows(kernel):
     for a in kernel.agents[1:]:
         row(a, 'FINAL_CASH_POSITION', a.holdings['CASH'])
         row(a, 'ENDING_CASH', a.marked_to_market)
-        if a.final_valuation is not None:
-            # ZI / HBL report an integer surplus, Value / Noise agents a ratio to the starting cash
-            zi = any(k.__name__ == "ZeroIntelligenceAgent" for k in type(a).__mro__)
-            row(a, 'FINAL_VALUATION', int(a.final_valuation) if zi else a.final_valuation)
-        if hasattr(a, "execution_time_horizon") and a.trade:  # ExecutionAgent.kernelStopping (:32-42)
-            avg, mid = a.average_transaction_price, a.arrival_price
-            if avg is None or mid is None:
-                raise RuntimeError("the reference raises in ExecutionAgent.kernelStopping: no fill or no arrival price")
-            row(a, 'DIRECTION', a.direction)
-            row(a, 'TOTAL_QTY', a.quantity)
-            row(a, 'REM_QTY', a.rem_quantity)
-            row(a, 'ARRIVAL_MID', mid)
-            row(a, 'AVG_TXN_PRICE', avg)
-            row(a, 'SLIPPAGE', avg - mid if a.direction == 'BUY' else mid - avg)
+        for ev, val in exchange_log.summary_tail(a):
+            row(a, ev, val)
     return rows
 
 
@@ -247,14 +236,14 @@ def fundamental_frame(kernel, trace):
     return sym, df.set_index('FundamentalTime')
 
 
-def write_logs(kernel, trace=None, root=".", exchange_log=None):
+def write_logs(kernel, trace=None, root=".", exchange_log=None, spec=None):
     """Kernel.writeSummaryLog (Kernel.py:523-532) and, when a trace was taken, what the agents archive at
     kernelTerminating: the exchange's fundamental series (ExchangeAgent.py:91-101) and -- when the trace carries the
     exchange-log records (run_spec_logged) -- the exchange's event log, its ORDERBOOK_<symbol>_FULL depth archive and
     the trading agents' logs (abides_b200/exchange_log.py).  bz2-pickled DataFrames under ./log/<log_dir>/ with the
     reference's file names, columns and dtypes.  `exchange_log`: None = write those archives iff the trace holds
     exchange-log records, True = the trace was taken with ABIDES_TRACE_EXCHANGE_LOG (a run without a single order
-    has none and still gets its archives), False = never."""
+    has none and still gets its archives), False = never; `spec`: the lowered instance (the logs of agents with log_orders=True need its latencies)."""
     import pandas as pd
     path = os.path.join(root, "log", kernel.log_dir)
     os.makedirs(path, exist_ok=True)
@@ -268,7 +257,7 @@ def write_logs(kernel, trace=None, root=".", exchange_log=None):
     if exchange_log and trace is not None:
         from abides_b200 import exchange_log
         try:
-            kernel.log_archive = exchange_log.write_archives(kernel, trace, path)
+            kernel.log_archive = exchange_log.write_archives(kernel, trace, path, spec=spec)
         except NotImplementedError as e:                 # the documented gaps (MODIFY_ORDER in the archives): say so, keep the run
             kernel.log_archive = None
             print("abides_b200: exchange / agent log archives not written: %s" % e, file=sys.stderr)

@@ -64,6 +64,18 @@ def digest(log_time, log_type, log_event, book=None):
     return out
 
 
+def hash_entry(files, log_files, log_start, log_time, log_type, log_event, book, ref_args):
+    logs = {}
+    for k, f in enumerate(log_files):
+        lo, hi = int(log_start[k]), int(log_start[k + 1])
+        logs[str(f)] = digest(log_time[lo:hi], log_type[lo:hi], log_event[lo:hi])
+    out = dict(files=[str(f) for f in files], logs=logs, ref_args=list(ref_args))
+    if book is not None:
+        b = digest([], [], [], book)
+        out.update(book_shape=b["book_shape"], book_sha256=b["book_sha256"])
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--name", required=True)
@@ -73,8 +85,8 @@ def main():
     ap.add_argument("--no-book-archive", action="store_true",
                     help="compat shim: skip ExchangeAgent.logOrderBookSnapshots (a long-format archive, wide_book=False, "
                          "fails in the reference itself under current pandas: pd.SparseDataFrame, ExchangeAgent.py:384)")
-    ap.add_argument("--hash-only", default=None, metavar="LOG_FILE",
-                    help="keep only the digest of this log file (and of the order-book archive) in exlog_hashes.json")
+    ap.add_argument("--hash-only", action="store_true",
+                    help="keep only the digests of the log files and of the order-book archive, in exlog_hashes.json")
     ap.add_argument("ref_args", nargs=argparse.REMAINDER)
     args = ap.parse_args()
     ref_args = [a for a in args.ref_args if a != "--"]
@@ -131,14 +143,11 @@ def main():
         log_start.append(log_start[-1] + len(df))
     if args.hash_only:
         import json
-        k = log_files.index(args.hash_only)
-        lo, hi = log_start[k], log_start[k + 1]
         path = os.path.join(args.out, "exlog_hashes.json")
         table = json.load(open(path)) if os.path.exists(path) else {}
-        table[args.name] = dict(digest(np.concatenate(times)[lo:hi], types[lo:hi], events[lo:hi], book or None),
-                                log_file=args.hash_only, files=files, ref_args=ref_args)
+        table[args.name] = hash_entry(files, log_files, log_start, np.concatenate(times), types, events, book or None, ref_args)
         json.dump(table, open(path, "w"), indent=1, sort_keys=True)
-        print(args.name, "->", path, table[args.name]["rows"], "rows")
+        print(args.name, "->", path, log_start[-1], "rows in", len(log_files), "logs")
         return
     np.savez_compressed(
         os.path.join(args.out, args.name + ".exlog.npz"), files=np.array(files, dtype=str),

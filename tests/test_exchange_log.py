@@ -210,12 +210,13 @@ def test_order_book_account_agrees_with_top_of_book_on_other_populations(name):
     assert bf.index.is_monotonic_increasing and bf.index.is_unique
 
 
-def test_exchange_log_and_book_archive_of_the_execution_config_match_reference_hashes():
-    """config/execution.py `-e` at 1/10 scale (TWAP agent: limit orders every minute, a MARKET order at the end; adaptive
-    market makers, momentum, value and noise agents), whole 09:30-11:30 session: the exchange's 381 019 log rows --
-    MARKET_ORDER rows and the notifications of their child limit orders included -- and the 30 214 x 1 322 order-book
-    archive hash to what the reference wrote (tests/golden/exlog_hashes.json, gen_exchange_log_golden.py --hash-only).
-    Every trading agent of that config logs its own orders, so no agent log is written."""
+def test_every_log_of_the_execution_config_matches_reference_hashes():
+    """config/execution.py `-e` at 1/10 scale, the whole 09:30-11:30 session, every agent logging its own orders
+    (tests/golden/exlog_hashes.json, gen_exchange_log_golden.py --hash-only): the exchange's 381 019 rows (MARKET_ORDER rows
+    and the notifications of their child limit orders included), the 30 214 x 1 322 order-book archive and the logs of
+    the two adaptive market makers (61 k rows each: ORDER_SUBMITTED, CANCEL_SUBMITTED at the send time recovered from
+    the deterministic latency, notifications, five-level depth rows), the ten momentum agents and the TWAP agent
+    (whole-book depth rows, its execution report) hash to what the reference wrote -- 539 338 rows in 14 files."""
     import json
     from abides_b200 import exchange_log
     from gen_exchange_log_golden import digest
@@ -234,17 +235,23 @@ def test_exchange_log_and_book_archive_of_the_execution_config_match_reference_h
     for f in ("ttl_messages", "last_trade", "slowest_agent_finish_time"):
         res[f][0] = d[f]
     runtime.write_back(kernel, runtime.RunOutput(hb, res, ares, 0.0, 1.0), 0)
-    ar = exchange_log.ExchangeArchive(kernel, d["trace"])
-    df = ar.exchange_frame()
-    t = df.index.to_numpy("datetime64[ns]")
-    ti = t.astype(np.int64)
-    ti[np.isnat(t)] = NAT
+    ar = exchange_log.ExchangeArchive(kernel, d["trace"], spec)
+    assert not ar.skipped_agents
+    frames = {name.replace(" ", "") + ".bz2": df for name, df in ar.agent_frames().items()}
+    frames[kernel.agents[0].name.replace(" ", "") + ".bz2"] = ar.exchange_frame()
+    assert sorted(frames) == sorted(want["logs"])
+    for name, df in frames.items():
+        t = df.index.to_numpy("datetime64[ns]")
+        ti = t.astype(np.int64)
+        ti[np.isnat(t)] = NAT
+        assert digest(ti, list(df.EventType), [canon(x) for x in df.Event]) == want["logs"][name], name
     b = ar.book_frame()
-    dense = b.sparse.to_coo().tocsr()
-    dense.sort_indices()
-    r, c = dense.nonzero()
-    book = dict(book_time=b.index.to_numpy("datetime64[ns]").astype(np.int64), book_quotes=[int(q) for q in b.columns],
-                book_row=r, book_col=c, book_val=np.asarray(dense[r, c]).ravel())
-    got = digest(ti, list(df.EventType), [canon(x) for x in df.Event], book)
-    assert got == {k: want[k] for k in got}
-    assert not ar.agent_rows and len(ar.skipped_agents) == 13
+    m = b.sparse.to_coo().tocsr()
+    m.sort_indices()
+    r, c = m.nonzero()
+    got = digest([], [], [], dict(book_time=b.index.to_numpy("datetime64[ns]").astype(np.int64),
+                                  book_quotes=[int(q) for q in b.columns], book_row=r, book_col=c,
+                                  book_val=np.asarray(m[r, c]).ravel()))
+    assert (got["book_shape"], got["book_sha256"]) == (want["book_shape"], want["book_sha256"])
+    # without the lowered instance the send times of cancellations are unknown: those agents get no log
+    assert len(exchange_log.ExchangeArchive(kernel, d["trace"]).skipped_agents) == 13
