@@ -397,8 +397,9 @@ def main():
                      "peak_source": peak_src, "kernel_ms_per_launch": kern_ms / args.steps,
                      "note": "dominant kernel lane_sim_kernel / sim_kernel: %d B algorithmic per message x messages per "
                              "launch / CUDA-event time of the launch (events on the library's launch stream); `traffic` = "
-                             "ncu DRAM bytes per message of the committed capture x messages per launch. The kernel is "
-                             "latency bound, not HBM bound: see DESIGN.md and profiles/" % ALGO_BYTES_PER_MESSAGE},
+                             "ncu DRAM bytes per message of the committed capture x messages per launch. The warp engine's "
+                             "kernel is bound by instruction fetch and dependent latency, the lane engine's at its bench size "
+                             "by the L2 / DRAM traffic of thread-local memory: DESIGN.md section 4 and profiles/" % ALGO_BYTES_PER_MESSAGE},
         "reference_note": REFERENCE_NOTE,
         "scaling_note": ("weak scaling: every rank runs its own %d instances, so the job at N GPUs is N times the N=1 job; "
                          "the reference arm always times one bounded CPU sample on one host, whatever N is"
